@@ -1,0 +1,248 @@
+// Stand-alone probe (developer tool, not part of the product): checks every
+// shared-memory operand image + descriptor combination the kernels in
+// infinitevl_b200/csrc rely on, against a CPU integer reference.  Run on a B200:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/umma_probe tools/umma_probe.cu
+//   ./tools/umma_probe
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../infinitevl_b200/csrc/sm100.cuh"
+
+using namespace ivl;
+
+struct ProbeArgs {
+  const uint8_t* a_img;
+  const uint8_t* b_img;
+  const float* d0;  // optional preload [128][N]
+  float* d;         // out [128][N]
+  uint32_t a_bytes, b_bytes;
+  uint32_t a_lbo, a_sbo, a_layout;
+  uint32_t b_lbo, b_sbo, b_layout;
+  uint32_t idesc;
+  uint32_t nk;
+  uint32_t n;
+  uint32_t a_off[8], b_off[8];
+};
+
+__global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 32768;
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar_load, p.a_bytes + p.b_bytes);
+    bulk_g2s(sA, p.a_img, p.a_bytes, &bar_load);
+    bulk_g2s(sB, p.b_img, p.b_bytes, &bar_load);
+  }
+  const uint32_t row = warp * 32 + lane;
+  const uint32_t taddr = tmem + ((warp * 32u) << 16);
+  if (p.d0) {
+    for (uint32_t c = 0; c < p.n; c += 32) {
+      uint32_t r[32];
+      for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(p.d0[row * p.n + c + i]);
+      tmem_st32(taddr + c, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  mbar_wait(&bar_load, 0);
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    for (uint32_t j = 0; j < p.nk; ++j) {
+      uint64_t da = umma_desc(smem_u32(sA) + p.a_off[j], p.a_lbo, p.a_sbo, p.a_layout);
+      uint64_t db = umma_desc(smem_u32(sB) + p.b_off[j], p.b_lbo, p.b_sbo, p.b_layout);
+      umma_bf16(tmem, da, db, p.idesc, (p.d0 != nullptr || j > 0) ? 1u : 0u);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (uint32_t c = 0; c < p.n; c += 8) {
+    uint32_t r[8];
+    tmem_ld8(taddr + c, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 8; ++i) p.d[row * p.n + c + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+// ---------------------------------------------------------------------------
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (uint16_t)(u >> 16);  // exact for the small integers used here
+}
+
+enum Lay { K_SW128, K_NONE, MN_SW128, MN_NONE };
+
+struct Operand {
+  std::vector<uint8_t> img;
+  uint32_t lbo, sbo, layout, major;
+  uint32_t off[8];
+};
+
+// X[mn][k], MN rows, K cols
+static Operand build(Lay lay, const std::vector<float>& X, int MN, int K, bool swap_lbo_sbo) {
+  Operand o;
+  o.img.assign(32768, 0);
+  auto put = [&](uint32_t byte, float v) {
+    uint16_t b = f2bf(v);
+    memcpy(&o.img[byte], &b, 2);
+  };
+  int nk = K / 16;
+  switch (lay) {
+    case K_SW128: {
+      uint32_t panel = MN * 128;
+      for (int m = 0; m < MN; ++m)
+        for (int k = 0; k < K; ++k)
+          put((k / 64) * panel + swz128(m * 128 + (k % 64) * 2), X[m * K + k]);
+      o.lbo = 16; o.sbo = 1024; o.layout = SWZ_128B; o.major = 0;
+      for (int j = 0; j < nk; ++j) o.off[j] = (j / 4) * panel + (j % 4) * 32;
+    } break;
+    case K_NONE: {
+      uint32_t lbo = 128, sbo = (K / 8) * 128;
+      for (int m = 0; m < MN; ++m)
+        for (int k = 0; k < K; ++k)
+          put((m / 8) * sbo + (k / 8) * lbo + (m % 8) * 16 + (k % 8) * 2, X[m * K + k]);
+      o.lbo = lbo; o.sbo = sbo; o.layout = SWZ_NONE; o.major = 0;
+      for (int j = 0; j < nk; ++j) o.off[j] = j * 2 * lbo;
+    } break;
+    case MN_SW128: {
+      uint32_t sbo = 1024, lbo = (K / 8) * 1024;
+      for (int m = 0; m < MN; ++m)
+        for (int k = 0; k < K; ++k)
+          put((m / 64) * lbo + swz128(k * 128 + (m % 64) * 2), X[m * K + k]);
+      o.lbo = lbo; o.sbo = sbo; o.layout = SWZ_128B; o.major = 1;
+      for (int j = 0; j < nk; ++j) o.off[j] = j * 2048;
+    } break;
+    case MN_NONE: {
+      uint32_t lbo = 128, sbo = (K / 8) * 128;
+      for (int m = 0; m < MN; ++m)
+        for (int k = 0; k < K; ++k)
+          put((m / 8) * sbo + (k / 8) * lbo + (k % 8) * 16 + (m % 8) * 2, X[m * K + k]);
+      o.lbo = lbo; o.sbo = sbo; o.layout = SWZ_NONE; o.major = 1;
+      for (int j = 0; j < nk; ++j) o.off[j] = j * 2 * lbo;
+    } break;
+  }
+  if (swap_lbo_sbo) std::swap(o.lbo, o.sbo);
+  return o;
+}
+
+static const char* lname(Lay l) {
+  switch (l) {
+    case K_SW128: return "K_SW128";
+    case K_NONE: return "K_NONE";
+    case MN_SW128: return "MN_SW128";
+    default: return "MN_NONE";
+  }
+}
+
+static int run(Lay la, bool swap_a, Lay lb, bool swap_b, int N, int K, bool neg_a, bool preload) {
+  const int M = 128;
+  std::vector<float> A(M * K), B(N * K), D0(M * N), ref(M * N);
+  srand(1234 + N * 7 + K);
+  for (auto& v : A) v = (float)((rand() % 7) - 3);
+  for (auto& v : B) v = (float)((rand() % 5) - 2);
+  for (auto& v : D0) v = (float)((rand() % 9) - 4);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = preload ? D0[m * N + n] : 0.f;
+      for (int k = 0; k < K; ++k) acc += (neg_a ? -1.f : 1.f) * A[m * K + k] * B[n * K + k];
+      ref[m * N + n] = acc;
+    }
+  Operand oa = build(la, A, M, K, swap_a), ob = build(lb, B, N, K, swap_b);
+  uint8_t *da, *db;
+  float *dd, *dd0;
+  cudaMalloc(&da, 32768); cudaMalloc(&db, 32768);
+  cudaMalloc(&dd, M * N * 4); cudaMalloc(&dd0, M * N * 4);
+  cudaMemcpy(da, oa.img.data(), 32768, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, ob.img.data(), 32768, cudaMemcpyHostToDevice);
+  cudaMemcpy(dd0, D0.data(), M * N * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dd, 0xff, M * N * 4);
+  ProbeArgs p{};
+  p.a_img = da; p.b_img = db; p.d0 = preload ? dd0 : nullptr; p.d = dd;
+  p.a_bytes = 32768; p.b_bytes = 32768;
+  p.a_lbo = oa.lbo; p.a_sbo = oa.sbo; p.a_layout = oa.layout;
+  p.b_lbo = ob.lbo; p.b_sbo = ob.sbo; p.b_layout = ob.layout;
+  p.idesc = umma_idesc_bf16(M, N, oa.major, ob.major, neg_a ? 1 : 0);
+  p.nk = K / 16; p.n = N;
+  memcpy(p.a_off, oa.off, sizeof(p.a_off));
+  memcpy(p.b_off, ob.off, sizeof(p.b_off));
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
+  probe_kernel<<<1, 128, 65536 + 1024>>>(p);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<float> out(M * N);
+  cudaMemcpy(out.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0;
+  int bad = 0;
+  for (int i = 0; i < M * N; ++i) {
+    double er = fabs((double)out[i] - ref[i]);
+    if (!(er <= 1e-3)) ++bad;
+    if (er > maxerr || er != er) maxerr = er;
+  }
+  printf("%-4s A=%-8s%s B=%-8s%s N=%-3d K=%-3d negA=%d preload=%d  bad=%d/%d maxerr=%g %s\n",
+         (bad == 0 && e == cudaSuccess) ? "PASS" : "FAIL", lname(la), swap_a ? "(swap)" : "      ",
+         lname(lb), swap_b ? "(swap)" : "      ", N, K, (int)neg_a, (int)preload, bad, M * N, maxerr,
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dd0);
+  if (e != cudaSuccess) { cudaDeviceReset(); }
+  return bad == 0 && e == cudaSuccess;
+}
+
+int main() {
+  int dev = 0;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  printf("device %s sm_%d%d SMs=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  // canonical GEMM images
+  run(K_SW128, false, K_SW128, false, 32, 64, false, false);
+  run(K_SW128, false, K_SW128, false, 32, 128, false, false);
+  run(K_SW128, false, K_SW128, false, 64, 128, false, false);
+  // no-swizzle K-major (both readings of LBO/SBO)
+  run(K_NONE, false, K_SW128, false, 32, 64, false, false);
+  run(K_NONE, true, K_SW128, false, 32, 64, false, false);
+  run(K_SW128, false, K_NONE, false, 32, 64, false, false);
+  run(K_SW128, false, K_NONE, true, 32, 64, false, false);
+  // MN-major A with swizzle (k-tilde^T operand)
+  run(MN_SW128, false, K_SW128, false, 32, 64, false, false);
+  run(MN_SW128, true, K_SW128, false, 32, 64, false, false);
+  // MN-major B without swizzle (state / v_new operands written by threads)
+  run(K_SW128, false, MN_NONE, false, 32, 64, false, false);
+  run(K_SW128, false, MN_NONE, true, 32, 64, false, false);
+  run(K_SW128, false, MN_NONE, false, 32, 128, false, false);
+  run(K_SW128, false, MN_NONE, true, 32, 128, false, false);
+  run(K_SW128, false, MN_NONE, false, 64, 128, false, false);
+  run(K_SW128, false, MN_NONE, true, 64, 128, false, false);
+  // MN-major A without swizzle
+  run(MN_NONE, false, K_SW128, false, 32, 64, false, false);
+  run(MN_NONE, true, K_SW128, false, 32, 64, false, false);
+  // both MN-major: the state update  S += k~^T v_new
+  run(MN_SW128, false, MN_NONE, false, 32, 64, false, false);
+  run(MN_SW128, false, MN_NONE, true, 32, 64, false, false);
+  // MN-major B with swizzle, N = 64
+  run(K_SW128, false, MN_SW128, false, 64, 64, false, false);
+  // negate A, accumulate on top of a tcgen05.st preload
+  run(K_SW128, false, K_SW128, false, 32, 128, true, false);
+  run(K_SW128, false, K_SW128, false, 32, 128, false, true);
+  run(K_SW128, false, K_SW128, false, 32, 128, true, true);
+  return 0;
+}
