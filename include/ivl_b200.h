@@ -1,0 +1,93 @@
+/*
+ * ivl_b200.h -- C ABI of the B200-native InfiniteVL hybrid-attention hot path.
+ *
+ * One shared library (libivl_b200.so), plain pointers and sizes, no C++ or
+ * torch types.  Every entry point
+ *   - runs asynchronously on the CUDA stream passed in (a cudaStream_t cast to void*),
+ *   - never allocates, never synchronises, never throws,
+ *   - returns IVL_OK or a negative IVL_ERR_* code (ivl_strerror() names it),
+ * so it is safe inside CUDA-graph capture (the reference demo captures the whole
+ * forward, inference_examples/demo_streaming_inference.py:473-486).
+ *
+ * Each function names the reference interface it replaces.  Paths are relative to
+ * the reference checkout; "fla/" = src/llamafactory/model/fla/, "std" =
+ * infinitevl/infinitevl_standard/modeling_infinitevl.py.
+ *
+ * Tensor layouts are the reference's time-first ones: q,k [B,T,H,K], v,o [B,T,H,V],
+ * g,beta [B,T,H], state [B,H,K,V]; all dense/contiguous.  bf16 is passed as
+ * uint16_t-sized storage (const void*).
+ */
+#ifndef IVL_B200_H_
+#define IVL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(IVL_BUILDING_DLL)
+#define IVL_API __attribute__((visibility("default")))
+#else
+#define IVL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IVL_OK 0
+#define IVL_ERR_BAD_SHAPE (-1)     /* unsupported head dims / sizes                     */
+#define IVL_ERR_NULL (-2)          /* required pointer is NULL                           */
+#define IVL_ERR_WORKSPACE (-3)     /* workspace too small                                */
+#define IVL_ERR_DTYPE (-4)         /* unknown dtype code                                 */
+#define IVL_ERR_LAUNCH (-5)        /* CUDA launch failed (cudaGetLastError was non-zero) */
+#define IVL_ERR_ARCH (-6)          /* device is not sm_100                               */
+
+#define IVL_DTYPE_F32 0
+#define IVL_DTYPE_BF16 1
+
+/* Library identification; also the cheapest "does the .so load" check. */
+IVL_API int ivl_abi_version(void);
+IVL_API const char* ivl_strerror(int code);
+
+/* ------------------------------------------------------------------------------------
+ * Gated DeltaNet, chunked prefill (T > 64 in the model, any T >= 1 here).
+ * Replaces chunk_gated_delta_rule(q,k,v,g,beta,scale,initial_state,output_final_state,
+ * cu_seqlens,use_qk_l2norm_in_kernel) -- fla/ops/gated_delta_rule/chunk.py:273-392,
+ * called from std:1298-1308 and fla/layers/gated_deltanet.py:275-286.
+ *
+ *   q,k   bf16 [B,T,H,128]      v bf16 [B,T,H,256]     g fp32 [B,T,H] (log decay)
+ *   beta  bf16 [B,T,H]          o bf16 [B,T,H,256]
+ *   h0    initial state [B,H,128,256] in h0_dtype, or NULL (zeros)
+ *   ht    final state   [B,H,128,256] in ht_dtype, or NULL (not written)
+ *   scale <= 0 selects K^-0.5;  l2norm_qk != 0 normalises q,k rows in-kernel (eps 1e-6).
+ *   workspace: ivl_gdn_chunk_workspace_bytes(B,T,H) bytes, 1024-byte aligned.
+ * Only H*K*V = (any H)*128*256 is supported (the InfiniteVL shape); else IVL_ERR_BAD_SHAPE.
+ * ---------------------------------------------------------------------------------- */
+IVL_API size_t ivl_gdn_chunk_workspace_bytes(int B, int T, int H);
+
+IVL_API int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                      const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T,
+                      int H, int K, int V, float scale, int l2norm_qk, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* The two halves of the above, exposed so that the bench can time them separately. */
+IVL_API int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                       int B, int T, int H, float scale, int l2norm_qk, void* workspace,
+                       size_t workspace_bytes, void* stream);
+IVL_API int ivl_gdn_chunk_scan(const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T,
+                       int H, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Gated DeltaNet, token recurrence (decode and q_len <= 64, std:1230).
+ * Replaces fused_recurrent_gated_delta_rule -- fla/ops/gated_delta_rule/fused_recurrent.py:218-335,
+ * called from std:1310-1320.  Same tensors as above; exact fp32 recurrence.
+ * h0 and ht may alias (in-place state update for CUDA graphs).
+ * ---------------------------------------------------------------------------------- */
+IVL_API int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, const float* g,
+                          const void* beta, const void* h0, int h0_dtype, void* o, void* ht,
+                          int ht_dtype, int B, int T, int H, int K, int V, float scale,
+                          int l2norm_qk, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVL_B200_H_ */

@@ -1,0 +1,60 @@
+"""ctypes binding of libivl_b200.so (the C ABI in include/ivl_b200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libivl_b200.so")
+
+IVL_DTYPE_F32 = 0
+IVL_DTYPE_BF16 = 1
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/ivl_b200.h declares
+SIGNATURES = {
+    "ivl_abi_version": (c_int, []),
+    "ivl_strerror": (c_char_p, [c_int]),
+    "ivl_gdn_chunk_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ivl_gdn_chunk_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
+                          + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "ivl_gdn_chunk_prep": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "ivl_gdn_chunk_scan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_int] * 3
+                           + [c_void_p, c_size_t, c_void_p]),
+    "ivl_gdn_recurrent_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
+                              + [c_float, c_int, c_void_p]),
+}
+
+
+class IvlError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load the shared library (building it in-tree first if it is absent and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) and build_if_missing:
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise IvlError(f"{LIB_PATH} not found: run `python -m infinitevl_b200.build` (there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and this table drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().ivl_strerror(code).decode()
+        raise IvlError(f"{what} failed: {msg} (code {code})")

@@ -1,0 +1,341 @@
+// Gated DeltaNet chunk pre-pass: everything that is parallel over (batch, head, chunk).
+//
+// Replaces, in one launch, the reference's l2norm x2, chunk_local_cumsum,
+// fwd_prepare_wy_repr and fwd_recompute_w_u kernels
+// (src/llamafactory/model/fla/modules/l2norm.py:21-42, ops/utils/cumsum.py:26-59,
+//  ops/gated_delta_rule/wy_fast.py:114-320) plus the intra-chunk attention matrix of
+// chunk_fwd_kernel_o (ops/common/chunk_o.py:77-113), and emits the operands of the
+// serial scan as ready-to-load tensor-core images (gdn_layout.cuh).
+//
+// Per (b, h, chunk c), with Qn, Kn the L2-normalised rows (rounded to bf16 as the
+// reference does, l2norm.py:42), G the in-chunk cumsum of g, Gamma_ij = exp(G_i - G_j):
+//   L  = tril_-1(diag(beta) Kn Kn^T * Gamma)                 fp32, tensor cores (mma.sync)
+//   T  = (I + L)^-1                                           fp32 forward substitution
+//   Wg = (T diag(beta exp G)) Kn,   U = (T diag(beta)) V      bf16 operands, fp32 accumulate
+//   P  = tril(Qn Kn^T * Gamma) * scale,  Qg = Qn exp(G) scale,  Kt = Kn exp(G_C - G)
+//
+// This kernel is throughput work (32K independent CTAs at 128K tokens); it uses the
+// warp-level mma.sync path.  The latency-critical scan uses tcgen05 (gdn_scan.cu).
+#include "gdn_layout.cuh"
+#include "sm100.cuh"
+
+namespace ivl {
+
+namespace {
+
+constexpr int PREP_THREADS = 128;
+constexpr int KH_LD = 136;  // bf16 elements per row: 272 B, rows shift by 16 B mod 128 -> conflict-free ldmatrix
+constexpr int V_LD = 264;
+constexpr int A_LD = 72;
+constexpr int LP_LD = 36;  // floats per row of one parity plane of L
+
+struct __align__(16) PrepSmem {
+  __nv_bfloat16 kh[64 * KH_LD];
+  __nv_bfloat16 qh[64 * KH_LD];
+  __nv_bfloat16 vb[64 * V_LD];
+  float Lp[2][64 * LP_LD + 4];  // L split by column parity: Lp[j & 1][i][j >> 1]
+  __nv_bfloat16 Aw[64 * A_LD];
+  __nv_bfloat16 Au[64 * A_LD];
+  float G[64];
+  float beta[64];
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                          uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+
+// Load 64 contiguous bf16 of one row half, L2-normalise over the full 128-wide row (the two
+// threads of a row combine their partial sums), round to bf16 (the reference's rounding point),
+// keep the rounded row in shared memory for the tensor-core products, and write the
+// exponentially weighted copy straight into its operand image in global memory.
+//   img_piece(p) returns the byte offset of 16-byte piece p (8 elements) of this thread's half row.
+template <class PieceOffset>
+__device__ __forceinline__ void norm_row_half(const __nv_bfloat16* src, bool valid, bool l2norm,
+                                              float weight, __nv_bfloat16* smem_row, uint8_t* img,
+                                              PieceOffset img_piece) {
+  uint4 raw[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+    raw[p] = valid ? __ldg(reinterpret_cast<const uint4*>(src) + p) : make_uint4(0, 0, 0, 0);
+  float ss = 0.f;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[p]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+      ss += lo * lo + hi * hi;
+    }
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  const float rstd = l2norm ? 1.0f / sqrtf(ss + 1e-6f) : 1.0f;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[p]);
+    uint4 nrm, wgt;
+    uint32_t* n = reinterpret_cast<uint32_t*>(&nrm);
+    uint32_t* g = reinterpret_cast<uint32_t*>(&wgt);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      n[e] = pack_bf16(bf16_lo(w[e]) * rstd, bf16_hi(w[e]) * rstd);
+      g[e] = pack_bf16(bf16_lo(n[e]) * weight, bf16_hi(n[e]) * weight);
+    }
+    *reinterpret_cast<uint4*>(smem_row + p * 8) = nrm;
+    *reinterpret_cast<uint4*>(img + img_piece(p)) = wgt;
+  }
+}
+
+__global__ void __launch_bounds__(PREP_THREADS, 2)
+gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
+                const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, int T, int H, float scale,
+                int l2norm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z, NT = gridDim.x;
+  const int t0 = c * GDN_C;
+  const int valid = min(GDN_C, T - t0);
+  const size_t tok0 = (size_t)b * T + t0;
+  const size_t ch = ((size_t)b * H + h) * NT + c;  // chunk-head index
+  uint8_t* blob = ws.blob + ch * BLOB_BYTES;
+  uint8_t* ublob = ws.ublob + ch * (GDN_NS * UBLOB_BYTES);
+
+  // ---- stage 0: async copy of the V tile, zero L, chunk-local cumsum of g ---------------
+  for (int i = tid; i < 64 * 32; i += PREP_THREADS) {
+    const int row = i >> 5, piece = i & 31;
+    __nv_bfloat16* dst = &s.vb[row * V_LD + piece * 8];
+    if (row < valid)
+      cp_async16(dst, v + ((tok0 + row) * H + h) * GDN_V + piece * 8);
+    else
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < 2 * (64 * LP_LD + 4); i += PREP_THREADS) (&s.Lp[0][0])[i] = 0.f;
+  if (warp == 0) {
+    float g0 = (lane < valid) ? g[(tok0 + lane) * H + h] : 0.f;
+    float g1 = (lane + 32 < valid) ? g[(tok0 + lane + 32) * H + h] : 0.f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      float a0 = __shfl_up_sync(0xffffffffu, g0, d), a1 = __shfl_up_sync(0xffffffffu, g1, d);
+      if (lane >= d) { g0 += a0; g1 += a1; }
+    }
+    g1 += __shfl_sync(0xffffffffu, g0, 31);
+    s.G[lane] = g0;
+    s.G[lane + 32] = g1;
+    s.beta[lane] = (lane < valid) ? __bfloat162float(beta[(tok0 + lane) * H + h]) : 0.f;
+    s.beta[lane + 32] = (lane + 32 < valid) ? __bfloat162float(beta[(tok0 + lane + 32) * H + h]) : 0.f;
+  }
+  __syncthreads();
+
+  // ---- stage 1: normalise q, k rows; emit Qg and Kt images --------------------------------
+  {
+    const int row = tid >> 1, half = tid & 1;
+    const bool ok = row < valid;
+    const float Gr = s.G[row], Gc = s.G[63];
+    const size_t off = ((tok0 + row) * H + h) * GDN_K + half * 64;
+    const int R = 64 + row;  // Qg occupies rows 64..127 of the stacked [-Wg ; Qg] operand
+    norm_row_half(q + off, ok, l2norm != 0, __expf(Gr) * scale, &s.qh[row * KH_LD + half * 64],
+                  blob + BLOB_OFF_A1, [&](int p) {
+                    return (uint32_t)((R >> 3) * 2048 + (half * 8 + p) * 128 + (R & 7) * 16);
+                  });
+    norm_row_half(k + off, ok, l2norm != 0, __expf(Gc - Gr), &s.kh[row * KH_LD + half * 64],
+                  blob + BLOB_OFF_KT, [&](int p) {
+                    return (uint32_t)((half * 8 + p) * 1024 + (row >> 3) * 128 + (row & 7) * 16);
+                  });
+    if (tid == 0) ws.gamma[ch] = __expf(Gc);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates
+  const int r0 = warp * 16;                 // this warp's 16-row strip
+
+  // ---- stage 2: Kn Kn^T and Qn Kn^T (lower triangle only) -> L (fp32, smem), P image -------
+  {
+    float ckk[8][4], cqk[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ckk[i][e] = cqk[i][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t ak[4], aq[4];
+      const int arow = r0 + (lane & 15), acol = ks * 16 + (lane >> 4) * 8;
+      ldsm_x4(smem_u32(&s.kh[arow * KH_LD + acol]), ak[0], ak[1], ak[2], ak[3]);
+      ldsm_x4(smem_u32(&s.qh[arow * KH_LD + acol]), aq[0], aq[1], aq[2], aq[3]);
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp) {
+        if (ntp <= warp) {  // column tiles right of the diagonal are never needed
+          uint32_t b0, b1, b2, b3;
+          const int n = ntp * 16 + (lane & 7) + (lane >> 4) * 8, kk = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(smem_u32(&s.kh[n * KH_LD + kk]), b0, b1, b2, b3);
+          mma16816(ckk[2 * ntp], ak, b0, b1);
+          mma16816(ckk[2 * ntp + 1], ak, b2, b3);
+          mma16816(cqk[2 * ntp], aq, b0, b1);
+          mma16816(cqk[2 * ntp + 1], aq, b2, b3);
+        }
+      }
+    }
+    const int i0 = r0 + gq, i1 = i0 + 8;
+    const float G0 = s.G[i0], G1 = s.G[i1], be0 = s.beta[i0], be1 = s.beta[i1];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int j0 = nt * 8 + 2 * tq, j1 = j0 + 1;
+      float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
+      if (nt <= 2 * warp + 1) {
+        const float Gj0 = s.G[j0], Gj1 = s.G[j1];
+        const float e00 = __expf(fminf(G0 - Gj0, 0.f)), e01 = __expf(fminf(G0 - Gj1, 0.f));
+        const float e10 = __expf(fminf(G1 - Gj0, 0.f)), e11 = __expf(fminf(G1 - Gj1, 0.f));
+        // strictly-lower entries of L; entries on/above the diagonal stay zero
+        if (i0 > j0) s.Lp[0][i0 * LP_LD + (j0 >> 1)] = be0 * ckk[nt][0] * e00;
+        if (i0 > j1) s.Lp[1][i0 * LP_LD + (j1 >> 1)] = be0 * ckk[nt][1] * e01;
+        if (i1 > j0) s.Lp[0][i1 * LP_LD + (j0 >> 1)] = be1 * ckk[nt][2] * e10;
+        if (i1 > j1) s.Lp[1][i1 * LP_LD + (j1 >> 1)] = be1 * ckk[nt][3] * e11;
+        p00 = (i0 >= j0) ? cqk[nt][0] * e00 * scale : 0.f;
+        p01 = (i0 >= j1) ? cqk[nt][1] * e01 * scale : 0.f;
+        p10 = (i1 >= j0) ? cqk[nt][2] * e10 * scale : 0.f;
+        p11 = (i1 >= j1) ? cqk[nt][3] * e11 * scale : 0.f;
+      }
+      uint8_t* pimg = blob + BLOB_OFF_P + nt * 128 + tq * 4;
+      *reinterpret_cast<uint32_t*>(pimg + (i0 >> 3) * 1024 + (i0 & 7) * 16) = pack_bf16(p00, p01);
+      *reinterpret_cast<uint32_t*>(pimg + (i1 >> 3) * 1024 + (i1 & 7) * 16) = pack_bf16(p10, p11);
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 3: T = (I + L)^-1 by forward substitution, one column per thread pair --------
+  // Thread (col, par) keeps the entries T[i][col] with i of parity `par` and accumulates the
+  // products over columns j of parity `par`; the pair exchanges its partial sums by shuffle.
+  {
+    const int col = tid >> 1, par = tid & 1;
+    const float* Lrow = &s.Lp[par][0];
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      float acc = 0.f;
+      const int n = (i + 1) >> 1;  // own-parity columns below the diagonal (rounded up; extras are zero)
+#pragma unroll
+      for (int j4 = 0; j4 < (n + 3) / 4; ++j4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(&Lrow[i * LP_LD + j4 * 4]);
+        acc = fmaf(l4.x, x[j4 * 4 + 0], acc);
+        if (j4 * 4 + 1 < n) acc = fmaf(l4.y, x[j4 * 4 + 1], acc);
+        if (j4 * 4 + 2 < n) acc = fmaf(l4.z, x[j4 * 4 + 2], acc);
+        if (j4 * 4 + 3 < n) acc = fmaf(l4.w, x[j4 * 4 + 3], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      const float xi = ((i == col) ? 1.f : 0.f) - acc;
+      if ((i & 1) == par) x[i >> 1] = xi;
+    }
+    const float bu = s.beta[col], bw = bu * __expf(s.G[col]);
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const int i = 2 * jj + par;
+      s.Aw[i * A_LD + col] = __float2bfloat16(x[jj] * bw);
+      s.Au[i * A_LD + col] = __float2bfloat16(x[jj] * bu);
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 4: Wg = Aw Kn (negated, into rows 0..63 of the A1 image), U = Au V ------------
+  {
+    const int i0 = r0 + gq, i1 = i0 + 8;
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks <= warp) {  // T is lower triangular
+        uint32_t a[4];
+        ldsm_x4(smem_u32(&s.Aw[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
+        const int kk = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int ntp = 0; ntp < 8; ++ntp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(smem_u32(&s.kh[kk * KH_LD + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
+          mma16816(acc[2 * ntp], a, b0, b1);
+          mma16816(acc[2 * ntp + 1], a, b2, b3);
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      uint8_t* img = blob + BLOB_OFF_A1 + nt * 128 + tq * 4;
+      *reinterpret_cast<uint32_t*>(img + (i0 >> 3) * 2048 + (i0 & 7) * 16) = pack_bf16(-acc[nt][0], -acc[nt][1]);
+      *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(-acc[nt][2], -acc[nt][3]);
+    }
+#pragma unroll
+    for (int hv = 0; hv < 2; ++hv) {  // two halves of 128 value columns
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        if (ks <= warp) {
+          uint32_t a[4];
+          ldsm_x4(smem_u32(&s.Au[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
+          const int kk = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+          for (int ntp = 0; ntp < 8; ++ntp) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4_t(smem_u32(&s.vb[kk * V_LD + hv * 128 + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
+            mma16816(acc[2 * ntp], a, b0, b1);
+            mma16816(acc[2 * ntp + 1], a, b2, b3);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const int colbase = hv * 128 + nt * 8;  // first of the 8 value columns of this tile
+        uint8_t* img = ublob + (colbase >> 5) * UBLOB_BYTES + ((colbase & 31) >> 3) * 1024 + tq * 4;
+        *reinterpret_cast<uint32_t*>(img + i0 * 16) = pack_bf16(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<uint32_t*>(img + i1 * 16) = pack_bf16(acc[nt][2], acc[nt][3]);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                            const GdnWorkspace& ws, int B, int T, int H, float scale, int l2norm,
+                            cudaStream_t stream) {
+  static bool configured = false;
+  const int smem = (int)sizeof(PrepSmem);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(gdn_num_chunks(T), H, B);
+  gdn_prep_kernel<<<grid, PREP_THREADS, smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
+      static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, T, H, scale, l2norm);
+  return cudaGetLastError();
+}
+
+}  // namespace ivl

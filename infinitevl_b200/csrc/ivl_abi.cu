@@ -1,0 +1,95 @@
+// extern "C" entry points of libivl_b200.so (declared in include/ivl_b200.h).
+// Argument validation + launch only; all math lives in the kernel files.
+#include <cuda_runtime.h>
+
+#include "../../include/ivl_b200.h"
+#include "gdn_layout.cuh"
+
+namespace ivl {
+cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                            const GdnWorkspace& ws, int B, int T, int H, float scale, int l2norm,
+                            cudaStream_t stream);
+cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype,
+                            int B, int T, int H, cudaStream_t stream);
+cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                                 const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H,
+                                 float scale, int l2norm, cudaStream_t stream);
+}  // namespace ivl
+
+namespace {
+inline bool bad_dtype(int d) { return d != IVL_DTYPE_F32 && d != IVL_DTYPE_BF16; }
+inline int check_gdn_shape(int B, int T, int H, int K, int V) {
+  if (B <= 0 || T <= 0 || H <= 0 || K != ivl::GDN_K || V != ivl::GDN_V) return IVL_ERR_BAD_SHAPE;
+  if (B > 65535 || H > 65535) return IVL_ERR_BAD_SHAPE;
+  return IVL_OK;
+}
+inline float default_scale(float scale, int K) { return scale > 0.f ? scale : 1.0f / sqrtf((float)K); }
+}  // namespace
+
+extern "C" {
+
+int ivl_abi_version(void) { return 1; }
+
+const char* ivl_strerror(int code) {
+  switch (code) {
+    case IVL_OK: return "ok";
+    case IVL_ERR_BAD_SHAPE: return "unsupported shape (need K=128, V=256, positive sizes)";
+    case IVL_ERR_NULL: return "required pointer is NULL";
+    case IVL_ERR_WORKSPACE: return "workspace too small or misaligned";
+    case IVL_ERR_DTYPE: return "unknown dtype code";
+    case IVL_ERR_LAUNCH: return "CUDA launch failed";
+    case IVL_ERR_ARCH: return "device is not sm_100";
+    default: return "unknown error";
+  }
+}
+
+size_t ivl_gdn_chunk_workspace_bytes(int B, int T, int H) {
+  if (B <= 0 || T <= 0 || H <= 0) return 0;
+  return ivl::gdn_workspace_bytes(B, T, H);
+}
+
+int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float* g, const void* beta, int B, int T,
+                       int H, float scale, int l2norm_qk, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_gdn_shape(B, T, H, ivl::GDN_K, ivl::GDN_V)) return e;
+  if (!q || !k || !v || !g || !beta || !workspace) return IVL_ERR_NULL;
+  if (workspace_bytes < ivl::gdn_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
+    return IVL_ERR_WORKSPACE;
+  ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H);
+  cudaError_t e = ivl::launch_gdn_prep(q, k, v, g, beta, ws, B, T, H, default_scale(scale, ivl::GDN_K), l2norm_qk,
+                                       static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_gdn_chunk_scan(const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_gdn_shape(B, T, H, ivl::GDN_K, ivl::GDN_V)) return e;
+  if (!o || !workspace) return IVL_ERR_NULL;
+  if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
+  if (workspace_bytes < ivl::gdn_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
+    return IVL_ERR_WORKSPACE;
+  ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H);
+  cudaError_t e = ivl::launch_gdn_scan(ws, h0, h0_dtype, o, ht, ht_dtype, B, T, H, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const float* g, const void* beta, const void* h0,
+                      int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H, int K, int V, float scale,
+                      int l2norm_qk, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_gdn_shape(B, T, H, K, V)) return e;
+  if (int e = ivl_gdn_chunk_prep(q, k, v, g, beta, B, T, H, scale, l2norm_qk, workspace, workspace_bytes, stream))
+    return e;
+  return ivl_gdn_chunk_scan(h0, h0_dtype, o, ht, ht_dtype, B, T, H, workspace, workspace_bytes, stream);
+}
+
+int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                          const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H, int K,
+                          int V, float scale, int l2norm_qk, void* stream) {
+  if (int e = check_gdn_shape(B, T, H, K, V)) return e;
+  if (!q || !k || !v || !g || !beta || !o) return IVL_ERR_NULL;
+  if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
+  cudaError_t e = ivl::launch_gdn_recurrent(q, k, v, g, beta, h0, h0 ? h0_dtype : 0, o, ht, ht ? ht_dtype : 0, B, T, H,
+                                            default_scale(scale, K), l2norm_qk, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""Operator layer: the reference's operator signatures on top of the C ABI.
+
+``chunk_gated_delta_rule`` and ``fused_recurrent_gated_delta_rule`` keep the names,
+argument meaning and error behaviour of
+src/llamafactory/model/fla/ops/gated_delta_rule/chunk.py:273-392 and
+.../fused_recurrent.py:218-335 (reference checkout), so the model code that calls
+them (infinitevl_standard/modeling_infinitevl.py:1297-1320) needs no change.
+PyTorch is used for device memory and the current stream only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import IVL_DTYPE_BF16, IVL_DTYPE_F32
+
+_workspaces: dict = {}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return IVL_DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return IVL_DTYPE_BF16
+    raise TypeError(f"state must be float32 or bfloat16, got {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def gdn_workspace(B: int, T: int, H: int, device) -> torch.Tensor:
+    """Cached scratch buffer for the chunk operator (grown on demand, reused across calls and
+    layers so that steady-state calls allocate nothing -- a CUDA-graph requirement)."""
+    lib = _lib.load()
+    need = lib.ivl_gdn_chunk_workspace_bytes(B, T, H)
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    off = (-ws.data_ptr()) % 1024
+    return ws[off:off + need]
+
+
+def _check_common(q, k, v, g, beta, initial_state, cu_seqlens, head_first):
+    if not q.is_cuda:
+        raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
+    assert q.dtype == k.dtype == v.dtype
+    assert len(beta.shape) == 3, "beta must be of shape [B, T, H]."
+    if cu_seqlens is not None:
+        if q.shape[0] != 1:
+            raise ValueError(
+                f"The batch size is expected to be 1 rather than {q.shape[0]} when using `cu_seqlens`."
+                f"Please flatten variable-length inputs before processing.")
+        if head_first:
+            raise RuntimeError("Sequences with variable lengths are not supported for head-first mode")
+        if initial_state is not None and initial_state.shape[0] != len(cu_seqlens) - 1:
+            raise ValueError(
+                f"The number of initial states is expected to be equal to the number of input sequences, "
+                f"i.e., {len(cu_seqlens) - 1} rather than {initial_state.shape[0]}.")
+
+
+def _run_chunk(q, k, v, g, beta, scale, h0, ht, o, l2norm):
+    lib = _lib.load()
+    B, T, H, K = q.shape
+    V = v.shape[-1]
+    ws = gdn_workspace(B, T, H, q.device)
+    code = lib.ivl_gdn_chunk_fwd(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(),
+        _ptr(h0), _dtype_code(h0) if h0 is not None else 0, o.data_ptr(),
+        _ptr(ht), _dtype_code(ht) if ht is not None else 0,
+        B, T, H, K, V, float(scale), int(l2norm), ws.data_ptr(), ws.numel(), _stream_ptr(q.device))
+    _lib.check(code, "ivl_gdn_chunk_fwd")
+
+
+def _run_recurrent(q, k, v, g, beta, scale, h0, ht, o, l2norm):
+    lib = _lib.load()
+    B, T, H, K = q.shape
+    V = v.shape[-1]
+    code = lib.ivl_gdn_recurrent_fwd(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(),
+        _ptr(h0), _dtype_code(h0) if h0 is not None else 0, o.data_ptr(),
+        _ptr(ht), _dtype_code(ht) if ht is not None else 0,
+        B, T, H, K, V, float(scale), int(l2norm), _stream_ptr(q.device))
+    _lib.check(code, "ivl_gdn_recurrent_fwd")
+
+
+def _gated_delta_rule(runner, q, k, v, g, beta, scale, initial_state, output_final_state, cu_seqlens, l2norm,
+                      state_out=None):
+    q, k, v = (x.to(torch.bfloat16).contiguous() for x in (q, k, v))
+    g = g.to(torch.float32).contiguous()
+    beta = beta.to(torch.bfloat16).contiguous()
+    B, T, H, K = q.shape
+    V = v.shape[-1]
+    o = torch.empty(B, T, H, V, dtype=torch.bfloat16, device=q.device)
+    if initial_state is not None:
+        initial_state = initial_state.contiguous()
+    if cu_seqlens is None:
+        ht = None
+        if output_final_state:
+            ht = state_out if state_out is not None else torch.empty(B, H, K, V, dtype=torch.float32, device=q.device)
+        runner(q, k, v, g, beta, scale, initial_state, ht, o, l2norm)
+        return o, ht
+    # packed variable-length sequences: every sequence is an independent scan over a contiguous
+    # token range of the flattened batch (fla/ops/gated_delta_rule/chunk.py:355-369)
+    bounds = [int(x) for x in cu_seqlens.tolist()]
+    N = len(bounds) - 1
+    ht = torch.empty(N, H, K, V, dtype=torch.float32, device=q.device) if output_final_state else None
+    for n in range(N):
+        s, e = bounds[n], bounds[n + 1]
+        if e <= s:
+            if ht is not None:
+                ht[n].copy_(initial_state[n] if initial_state is not None else torch.zeros_like(ht[n]))
+            continue
+        runner(q[:, s:e], k[:, s:e], v[:, s:e], g[:, s:e], beta[:, s:e], scale,
+               None if initial_state is None else initial_state[n:n + 1],
+               None if ht is None else ht[n:n + 1], o[:, s:e], l2norm)
+    return o, ht
+
+
+@torch.no_grad()
+def chunk_gated_delta_rule(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    g: torch.Tensor,
+    beta: torch.Tensor,
+    scale: Optional[float] = None,
+    initial_state: Optional[torch.Tensor] = None,
+    output_final_state: bool = False,
+    cu_seqlens: Optional[torch.LongTensor] = None,
+    head_first: bool = False,
+    use_qk_l2norm_in_kernel: bool = False,
+    state_out: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """q,k [B,T,H,K]; v [B,T,H,V]; g (log decay, fp32) and beta [B,T,H];
+    initial_state [N,H,K,V] (fp32 or bf16).  Returns (o [B,T,H,V] in q.dtype, final_state fp32 | None).
+
+    ``state_out`` (extension): write the final state into this preallocated fp32/bf16 buffer
+    instead of allocating -- what a CUDA-graph-captured cache update needs."""
+    _check_common(q, k, v, g, beta, initial_state, cu_seqlens, head_first)
+    assert q.dtype != torch.float32, "ChunkGatedDeltaRuleFunction does not support float32. Please use bfloat16."
+    if head_first:
+        q, k, v = (x.transpose(1, 2) for x in (q, k, v))
+        beta, g = beta.transpose(1, 2), g.transpose(1, 2)
+    if scale is None:
+        scale = k.shape[-1] ** -0.5
+    else:
+        assert scale > 0, "Scale must be positive."
+    out_dtype = q.dtype
+    o, ht = _gated_delta_rule(_run_chunk, q, k, v, g, beta, scale, initial_state, output_final_state, cu_seqlens,
+                              use_qk_l2norm_in_kernel, state_out)
+    o = o.to(out_dtype)
+    if head_first:
+        o = o.transpose(1, 2)
+    return o, ht
+
+
+@torch.no_grad()
+def fused_recurrent_gated_delta_rule(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    g: torch.Tensor,
+    beta: Optional[torch.Tensor] = None,
+    scale: Optional[float] = None,
+    initial_state: Optional[torch.Tensor] = None,
+    output_final_state: bool = False,
+    cu_seqlens: Optional[torch.LongTensor] = None,
+    head_first: bool = False,
+    use_qk_l2norm_in_kernel: bool = False,
+    state_out: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Token-serial form of the same operator (decode / q_len <= 64).  Time-first layout by
+    default, as the model calls it (the vendored copy defaulted to head_first=True but the
+    model never passes the flag and the pip package it runs against is time-first)."""
+    if beta is None:
+        beta = torch.ones_like(q[..., 0])
+    _check_common(q, k, v, g, beta, initial_state, cu_seqlens, head_first)
+    if head_first:
+        q, k, v = (x.transpose(1, 2) for x in (q, k, v))
+        beta, g = beta.transpose(1, 2), g.transpose(1, 2)
+    if scale is None:
+        scale = k.shape[-1] ** -0.5
+    else:
+        assert scale > 0, "scale must be positive"
+    out_dtype = q.dtype
+    o, ht = _gated_delta_rule(_run_recurrent, q, k, v, g, beta, scale, initial_state, output_final_state,
+                              cu_seqlens, use_qk_l2norm_in_kernel, state_out)
+    o = o.to(out_dtype)
+    if head_first:
+        o = o.transpose(1, 2)
+    return o, ht

@@ -67,7 +67,7 @@ def main():
             print(f"fla chunk_gated_delta_rule T={T}: {ms:.3f} ms", flush=True)
         # decode step
         q, k, v, g, beta, h0 = make_gdn_inputs(1)
-        fn = lambda: fused_recurrent_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+        fn = lambda: fused_recurrent_gated_delta_rule(q=q, k=k, v=v, g=g, beta=beta, initial_state=h0, output_final_state=True,
                                                       use_qk_l2norm_in_kernel=True)
         res["fla_recurrent_T1_ms"] = time_fn(fn, iters=50)
         # fixture
@@ -75,7 +75,7 @@ def main():
         q, k, v, g, beta, h0 = make_gdn_inputs(T, H=H, seed=7)
         o, ht = chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
                                        use_qk_l2norm_in_kernel=True)
-        o2, ht2 = fused_recurrent_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+        o2, ht2 = fused_recurrent_gated_delta_rule(q=q, k=k, v=v, g=g, beta=beta, initial_state=h0, output_final_state=True,
                                                    use_qk_l2norm_in_kernel=True)
         np.savez_compressed(os.path.join(OUT, "fla_triton_gdn_T256_H2_seed7.npz"),
                             o_chunk=o.float().cpu().numpy().astype(np.float16),
