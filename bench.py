@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the InfiniteVL hybrid-attention hot path on B200 (contract: see README / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--seq T] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one synthetic 128K-token sequence of the InfiniteVL-3B
+decoder: the token mixers of all 36 layers (27 Gated DeltaNet chunk-prefill calls, H=16 K=128 V=256,
+and 9 sliding-window attention calls, Hq=16 Hkv=2 D=128 W=8192), inputs resident in HBM.
+`value` = tokens / second through that path.  With N > 1 ranks the sequence is sharded by contiguous
+token range and every layer hands its DeltaNet state (and SWA K/V halo) to the next rank (strong scaling).
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_GDN_LAYERS = 27
+N_SWA_LAYERS = 9
+H, K, V = 16, 128, 256
+HQ, HKV, D, WINDOW = 16, 2, 128, 8192
+GDN_BYTES_PER_TOKEN = 24672          # q,k,v,g,beta read + o written, per token per layer
+GDN_STATE_BYTES = 2 * H * K * V * 4  # h0 read + hT written, per sequence per layer
+
+
+def swa_flops(T, Tk_prefix=0):
+    """4 * Hq * D * sum_t min(t + 1 + prefix, W)   (SURVEY.md 8d)."""
+    total = 0
+    lo = Tk_prefix
+    # sum over t in [0, T) of min(t + 1 + lo, W)
+    full_from = max(0, WINDOW - 1 - lo)          # first t with t + 1 + lo >= W
+    if full_from >= T:
+        total = T * (lo + 1) + T * (T - 1) // 2
+    else:
+        total = full_from * (lo + 1) + full_from * (full_from - 1) // 2 + (T - full_from) * WINDOW
+    return 4 * HQ * D * total
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class HotPath:
+    """Device-resident synthetic inputs of one rank's token range + the launches of one step."""
+
+    def __init__(self, T_local, rank, world, device, seed=0):
+        from inputs import gdn_inputs
+
+        from infinitevl_b200 import _lib, ops
+        self.lib = _lib.load()
+        self._lib_mod = _lib
+        self.ops = ops
+        self.T = T_local
+        self.rank, self.world = rank, world
+        self.dev = device
+        gen_T = min(T_local, 16384)  # generate on CPU in pieces, tile to length (values are i.i.d. anyway)
+        q, k, v, g, beta, h0 = gdn_inputs(T=gen_T, H=H, seed=seed + rank)
+        rep = (T_local + gen_T - 1) // gen_T
+        tile = lambda x: x.repeat(1, rep, *([1] * (x.dim() - 2)))[:, :T_local].contiguous().to(device)
+        self.q, self.k, self.v, self.g, self.beta = (tile(x) for x in (q, k, v, g, beta))
+        self.h0 = h0.to(device)
+        self.state_in = torch.empty_like(self.h0)
+        self.ht = torch.empty_like(self.h0)
+        self.o = torch.empty(1, T_local, H, V, dtype=torch.bfloat16, device=device)
+        self.ws = ops.gdn_workspace(1, T_local, H, device)
+        self.launches_per_step = 0
+        self.has_swa = False
+        try:
+            from infinitevl_b200 import swa
+            self.swa = swa
+            gen = torch.Generator().manual_seed(seed + 100 + rank)
+            mk = lambda h: torch.randn(1, gen_T, h, D, generator=gen).bfloat16().repeat(1, rep, 1, 1)[:, :T_local] \
+                .contiguous().to(device)
+            self.sq, self.sk, self.sv = mk(HQ), mk(HKV), mk(HKV)   # [B, T, H, D] (kernel-native layout)
+            halo = min(WINDOW - 1, T_local) if rank > 0 else 0
+            self.halo = halo
+            self.skv_full = None
+            if world > 1:
+                self.k_halo = torch.zeros(1, WINDOW - 1, HKV, D, dtype=torch.bfloat16, device=device)
+                self.v_halo = torch.zeros(1, WINDOW - 1, HKV, D, dtype=torch.bfloat16, device=device)
+            self.so = torch.empty(1, T_local, HQ, D, dtype=torch.bfloat16, device=device)
+            self.has_swa = True
+        except ImportError:
+            self.has_swa = False
+
+    # -- single kernels (for the roofline timing) ---------------------------------------------
+    def gdn_prep(self):
+        st = torch.cuda.current_stream().cuda_stream
+        self._lib_mod.check(self.lib.ivl_gdn_chunk_prep(
+            self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.g.data_ptr(), self.beta.data_ptr(),
+            1, self.T, H, 0.0, 1, self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_prep")
+
+    def gdn_scan(self, h0):
+        st = torch.cuda.current_stream().cuda_stream
+        self._lib_mod.check(self.lib.ivl_gdn_chunk_scan(
+            h0.data_ptr(), 0, self.o.data_ptr(), self.ht.data_ptr(), 0, 1, self.T, H,
+            self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_scan")
+
+    def step(self):
+        import torch.distributed as dist
+        n = 0
+        for layer in range(N_GDN_LAYERS + N_SWA_LAYERS):
+            if layer % 4 == 0:
+                if self.has_swa:
+                    n += self.swa_layer()
+                continue
+            self.gdn_prep()
+            h0 = self.h0
+            if self.world > 1 and self.rank > 0:
+                dist.recv(self.state_in, src=self.rank - 1)
+                h0 = self.state_in
+            self.gdn_scan(h0)
+            if self.world > 1 and self.rank < self.world - 1:
+                dist.send(self.ht, dst=self.rank + 1)
+            n += 2
+        self.launches_per_step = n
+        return n
+
+    def swa_layer(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            # halo hand-off: the last W-1 keys/values of this rank's range go to the next rank
+            if self.rank < self.world - 1:
+                dist.send(self.sk[:, -(WINDOW - 1):].contiguous(), dst=self.rank + 1)
+                dist.send(self.sv[:, -(WINDOW - 1):].contiguous(), dst=self.rank + 1)
+            if self.rank > 0:
+                dist.recv(self.k_halo, src=self.rank - 1)
+                dist.recv(self.v_halo, src=self.rank - 1)
+                kf = torch.cat([self.k_halo, self.sk], dim=1)
+                vf = torch.cat([self.v_halo, self.sv], dim=1)
+                self.swa.swa_attention_bthd(self.sq, kf, vf, window=WINDOW, out=self.so)
+                return 1
+        self.swa.swa_attention_bthd(self.sq, self.sk, self.sv, window=WINDOW, out=self.so)
+        return 1
+
+
+def time_events(fn, iters):
+    evs = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T = args.seq
+    assert T % (64 * world) == 0
+    T_local = T // world
+    hp = HotPath(T_local, rank, world, dev)
+    peaks = read_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        hp.step()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    if rank == 0:
+        sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    for _ in range(args.steps):
+        hp.step()
+    b.record()
+    barrier()
+    ms_total = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total.item() / args.steps
+
+    # ---- per-kernel timing for the roofline (device events on the launching stream) --------------
+    roof = None
+    kernels = {}
+    if rank == 0:
+        prep = time_events(hp.gdn_prep, 10)
+        scan = time_events(lambda: hp.gdn_scan(hp.h0), 10)
+        t_prep, t_scan = sum(prep) / len(prep), sum(scan) / len(scan)
+        alg_bytes = GDN_BYTES_PER_TOKEN * T_local + GDN_STATE_BYTES
+        achieved = alg_bytes / ((t_prep + t_scan) * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "gdn_chunk = gdn_prep_kernel + gdn_scan_kernel (one GDN layer)",
+                "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_bytes_per_launch": alg_bytes}
+        kernels = {"gdn_prep_ms": round(t_prep, 4), "gdn_scan_ms": round(t_scan, 4)}
+        if hp.has_swa:
+            swa_t = time_events(hp.swa_layer, 5) if world == 1 else None
+            if swa_t:
+                t_swa = sum(swa_t) / len(swa_t)
+                kernels["swa_fwd_ms"] = round(t_swa, 4)
+                kernels["swa_tflops"] = round(swa_flops(T_local) / (t_swa * 1e-3) / 1e12, 1)
+                kernels["swa_frac_of_bf16_sustained"] = round(kernels["swa_tflops"] / peaks["bf16_tflops_sustained"], 4)
+
+    # ---- end-to-end through the public operator API with HOST buffers ---------------------------
+    e2e = None
+    if world == 1:
+        e2e = run_e2e(hp, args)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(sample_T=args.cpu_sample, has_swa=hp.has_swa)
+
+    if rank == 0:
+        workload = (f"prefill hot path, T={T} tokens, InfiniteVL-3B mixers: {N_GDN_LAYERS}x GDN chunk (H16 K128 V256)"
+                    + (f" + {N_SWA_LAYERS}x SWA (Hq16 Hkv2 D128 W8192)" if hp.has_swa else " (SWA kernel not built: GDN layers only)"))
+        line = {
+            "metric": "prefill tokens/sec @128K seq InfiniteVL-3B hybrid-attention hot path",
+            "value": round(T / (ms_step * 1e-3), 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "seq_len": T, "batch": 1,
+                       "parallelism": f"sequence-chunk x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs (>3 GB per layer) exceed the 126 MB L2; no flush needed"},
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": hp.launches_per_step * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(hp, args):
+    """Same step, but the step's inputs start in pinned host memory and the result is read back."""
+    T = hp.T
+    host = {}
+    names = ["q", "k", "v", "g", "beta"] + (["sq", "sk", "sv"] if hp.has_swa else [])
+    for n in names:
+        host[n] = getattr(hp, n).cpu().pin_memory()
+    out_host = torch.empty(hp.o.shape, dtype=hp.o.dtype).pin_memory()
+    h2d = sum(x.numel() * x.element_size() for x in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    def e2e_step():
+        for n in names:
+            getattr(hp, n).copy_(host[n], non_blocking=True)
+        hp.step()
+        out_host.copy_(hp.o, non_blocking=True)
+
+    e2e_step()
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 3))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"value": round(T / (ms * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": round(ms, 3), "steps": steps,
+            "api": "infinitevl_b200 C ABI (ivl_gdn_chunk_prep/scan" + (", ivl_swa_fwd" if hp.has_swa else "") + ") with pinned host buffers"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (a port: the reference has no CPU path for this operator)
+# ------------------------------------------------------------------------------------------------
+def cpu_hot_path_seconds(sample_T, has_swa=True):
+    from inputs import gdn_inputs
+    from oracle import gdn_chunk_ref, swa_attention_ref
+    torch.set_num_threads(os.cpu_count())
+    q, k, v, g, beta, h0 = gdn_inputs(T=sample_T, H=H, seed=0)
+    t0 = time.perf_counter()
+    gdn_chunk_ref(q, k, v, g, beta, initial_state=h0)
+    t_gdn = time.perf_counter() - t0
+    t_swa = 0.0
+    if has_swa:
+        gen = torch.Generator().manual_seed(1)
+        sq = torch.randn(1, HQ, sample_T, D, generator=gen)
+        sk = torch.randn(1, HKV, sample_T, D, generator=gen)
+        sv = torch.randn(1, HKV, sample_T, D, generator=gen)
+        t0 = time.perf_counter()
+        swa_attention_ref(sq, sk, sv, window=WINDOW)
+        t_swa = time.perf_counter() - t0
+    return t_gdn, t_swa
+
+
+def cpu_baseline(sample_T=2048, has_swa=True):
+    t_gdn, t_swa = cpu_hot_path_seconds(sample_T, has_swa)
+    total = N_GDN_LAYERS * t_gdn + (N_SWA_LAYERS * t_swa if has_swa else 0.0)
+    return {"value": round(sample_T / total, 2), "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle (fp32 torch) hot path at T={sample_T}: one GDN layer {t_gdn:.3f}s x{N_GDN_LAYERS}"
+                      + (f" + one SWA layer {t_swa:.3f}s x{N_SWA_LAYERS}" if has_swa else "")
+                      + "; the reference has no CPU implementation of these operators (Triton / flash-attn only)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T = args.cpu_sample
+    has_swa = os.path.exists(os.path.join(ROOT, "infinitevl_b200", "swa.py"))
+    for _ in range(min(args.warmup, 1)):
+        cpu_hot_path_seconds(T, has_swa)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    tot = 0.0
+    for _ in range(steps):
+        t_gdn, t_swa = cpu_hot_path_seconds(T, has_swa)
+        tot += N_GDN_LAYERS * t_gdn + (N_SWA_LAYERS * t_swa if has_swa else 0.0)
+    sec = tot / steps
+    val = round(T / sec, 2)
+    cpu = {"value": val, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+           "sample": f"oracle hot path at T={T} (one layer of each kind timed, scaled by layer counts); "
+                     f"wall {time.perf_counter() - t0:.1f}s"}
+    line = {"impl": "reference", "metric": "prefill tokens/sec @128K seq InfiniteVL-3B hybrid-attention hot path",
+            "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": round(sec * 1e3, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CPU oracle of the same hot path on a bounded sample (T={T})", "seq_len": T,
+                       "batch": 1},
+            "cpu_baseline": cpu,
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--seq", type=int, default=131072)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,6 +87,22 @@ IVL_API int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, c
                           int ht_dtype, int B, int T, int H, int K, int V, float scale,
                           int l2norm_qk, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Sliding-window causal GQA attention, prefill / chunked prefill (any Tq >= 1, Tk >= Tq).
+ * Replaces the HF attention-interface callable ALL_ATTENTION_FUNCTIONS["flash_attention_2"]
+ * (flash-attn wheel) used at std:1092-1108:  key j visible to query i iff
+ * 0 <= (i + Tk - Tq) - j <= window - 1; the window is only enforced when Tk > window
+ * (transformers/modeling_flash_attention_utils.py:627-632), window <= 0 = plain causal.
+ *
+ *   q [B,Tq,Hq,128], k,v [B,Tk,Hkv,128], o [B,Tq,Hq,128]  bf16, innermost dim contiguous;
+ *   *_strides = {batch, time, head} strides in ELEMENTS (multiples of 8), so the HF layout
+ *   [B,H,T,D] views produced by `.view(B,T,H,D).transpose(1,2)` are accepted without a copy.
+ *   scale <= 0 selects D^-0.5.  D must be 128 and Hq a multiple of Hkv.
+ * ---------------------------------------------------------------------------------- */
+IVL_API int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides,
+                        const void* v, const int64_t* v_strides, void* o, const int64_t* o_strides, int B,
+                        int Tq, int Tk, int Hq, int Hkv, int D, int window, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ SIGNATURES = {
                            + [c_void_p, c_size_t, c_void_p]),
     "ivl_gdn_recurrent_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
                               + [c_float, c_int, c_void_p]),
+    "ivl_swa_fwd": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, c_void_p]),
 }
 
 

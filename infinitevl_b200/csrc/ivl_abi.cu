@@ -14,6 +14,9 @@ cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const void* h0, int h0_dtype
 cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, const float* g, const void* beta,
                                  const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H,
                                  float scale, int l2norm, cudaStream_t stream);
+cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
+                           const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
+                           int window, float scale, cudaStream_t stream);
 }  // namespace ivl
 
 namespace {
@@ -89,6 +92,27 @@ int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, const flo
   if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
   cudaError_t e = ivl::launch_gdn_recurrent(q, k, v, g, beta, h0, h0 ? h0_dtype : 0, o, ht, ht ? ht_dtype : 0, B, T, H,
                                             default_scale(scale, K), l2norm_qk, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides, const void* v,
+                const int64_t* v_strides, void* o, const int64_t* o_strides, int B, int Tq, int Tk, int Hq, int Hkv,
+                int D, int window, float scale, void* stream) {
+  if (B <= 0 || Tq <= 0 || Tk < Tq || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || D != 128 || B > 65535)
+    return IVL_ERR_BAD_SHAPE;
+  if ((Tq + 127) / 128 > 65535) return IVL_ERR_BAD_SHAPE;
+  if (!q || !k || !v || !o || !q_strides || !k_strides || !v_strides || !o_strides) return IVL_ERR_NULL;
+  long long qs[3], ks[3], vs[3], os[3];
+  for (int i = 0; i < 3; ++i) {
+    qs[i] = q_strides[i]; ks[i] = k_strides[i]; vs[i] = v_strides[i]; os[i] = o_strides[i];
+    if ((qs[i] | ks[i] | vs[i] | os[i]) & 7) return IVL_ERR_BAD_SHAPE;  // TMA / 16-byte vector alignment
+  }
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+       reinterpret_cast<uintptr_t>(o)) & 15)
+    return IVL_ERR_BAD_SHAPE;
+  const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, B, Tq, Tk, Hq, Hkv, window, sc,
+                                      static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 

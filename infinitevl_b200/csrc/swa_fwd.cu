@@ -1,0 +1,325 @@
+// Sliding-window causal GQA attention, prefill (any Tq >= 1): flash-attention forward on
+// tcgen05 tensor cores with TMA-fed operands and TMEM accumulators.
+//
+// Replaces the flash-attn wheel reached through the HF attention interface
+// (ALL_ATTENTION_FUNCTIONS["flash_attention_2"], infinitevl_standard/modeling_infinitevl.py:1092-1108;
+//  window rule transformers/modeling_flash_attention_utils.py:627-632): key j is visible to
+// query i iff 0 <= (i + Tk - Tq) - j <= window - 1 (window == 0: plain bottom-right causal).
+//
+// One CTA = 128 consecutive queries of one q-head; two CTAs per SM so that one CTA's softmax
+// overlaps the other's MMAs.  Per 64-key tile:
+//   MMA   S = Q K^T                  M128 N64 K128   (Q, K: K-major 128B-swizzled TMA tiles)
+//   warps row softmax (one thread per query row, no shuffles), lazy rescale of O in TMEM,
+//         P -> bf16 -> shared (K-major core-matrix image)
+//   MMA   O += P V                   M128 N128 K64   (V: MN-major 128B-swizzled TMA tile)
+// S is double-buffered in TMEM so S(t+1) is issued before P(t) is ready.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue.
+#include <cuda.h>
+
+#include "sm100.cuh"
+
+namespace ivl {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, HD = 128;
+constexpr int SWA_THREADS = 192;
+constexpr uint32_t Q_BYTES = BM * HD * 2;        // 32 KiB: 2 panels [128][64]
+constexpr uint32_t KT_BYTES_ = BN * HD * 2;      // 16 KiB: 2 panels [64][64]
+constexpr uint32_t OFF_Q = 0;
+constexpr uint32_t OFF_K = Q_BYTES;              // 2 stages
+constexpr uint32_t OFF_V = OFF_K + 2 * KT_BYTES_;
+constexpr uint32_t OFF_P = OFF_V + 2 * KT_BYTES_;
+constexpr uint32_t P_BYTES_ = BM * BN * 2;       // 16 KiB
+constexpr uint32_t DATA_BYTES = OFF_P + P_BYTES_;  // 112 KiB
+constexpr uint32_t SWA_SMEM = DATA_BYTES + 1024;   // barriers live in the alignment slack (or the tail)
+constexpr uint32_t TM_S = 0;      // 2 x 64 columns
+constexpr uint32_t TM_O = 128;    // 128 columns
+constexpr uint32_t TM_COLS = 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: O is only rescaled when the row max grows by > 2^8
+
+struct Bars {
+  uint64_t full[2], empty[2], q, s[2], sfree[2], p, pv;
+  uint32_t tmem_base;
+};
+
+struct SwaArgs {
+  __nv_bfloat16* o;
+  long long o_sb, o_st, o_sh;  // element strides of the output [B, Tq, Hq, D]
+  int Tq, Tk, Hq, group;       // group = Hq / Hkv
+  int window;                  // 0 = none
+  float scale_log2;            // softmax scale * log2(e)
+};
+
+__global__ void __launch_bounds__(SWA_THREADS, 2)
+swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, SwaArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t slack = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + slack;
+  Bars& bars = *reinterpret_cast<Bars*>(slack >= 128 ? smem_raw : smem + DATA_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, mt = blockIdx.y, b = blockIdx.z;
+  const int hk = h / a.group;
+  const int i0 = mt * BM;
+  const int shift = a.Tk - a.Tq;                           // bottom-right alignment
+  const int p_first = i0 + shift;
+  const int p_last = min(i0 + BM - 1, a.Tq - 1) + shift;
+  const int lo_key = a.window > 0 ? max(0, p_first - a.window + 1) : 0;
+  const int t_lo = lo_key / BN, t_hi = min(p_last, a.Tk - 1) / BN;
+  const int n_tiles = t_hi - t_lo + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1);
+      mbar_init(&bars.s[i], 1); mbar_init(&bars.sfree[i], 128);
+    }
+    mbar_init(&bars.q, 1); mbar_init(&bars.p, 128); mbar_init(&bars.pv, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) tmem_alloc<TM_COLS>(&bars.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    // ---------------------------------- TMA producer ------------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars.q, Q_BYTES);
+      tma_load_4d(smem + OFF_Q, &tmQ, 0, h, i0, b, &bars.q);
+      tma_load_4d(smem + OFF_Q + Q_BYTES / 2, &tmQ, 64, h, i0, b, &bars.q);
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t & 1;
+      if (t >= 2) mbar_wait(&bars.empty[s], ((t >> 1) - 1) & 1);
+      if (lane == 0) {
+        const int j0 = (t_lo + t) * BN;
+        uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
+        uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
+        mbar_arrive_expect_tx(&bars.full[s], 2 * KT_BYTES_);
+        tma_load_4d(kd, &tmK, 0, hk, j0, b, &bars.full[s]);
+        tma_load_4d(kd + KT_BYTES_ / 2, &tmK, 64, hk, j0, b, &bars.full[s]);
+        tma_load_4d(vd, &tmV, 0, hk, j0, b, &bars.full[s]);
+        tma_load_4d(vd + KT_BYTES_ / 2, &tmV, 64, hk, j0, b, &bars.full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------------------------- MMA issuer --------------------------------------
+    constexpr uint32_t idescS = umma_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t idescO = umma_idesc_bf16(BM, HD, 0, 1);
+    const uint32_t sb = smem_u32(smem);
+    const uint64_t dQ = umma_desc(sb + OFF_Q, 16, 1024, SWZ_128B);
+    const uint64_t dP = umma_desc(sb + OFF_P, 128, 1024, SWZ_NONE);
+    auto issue_s = [&](int t) {
+      const int s = t & 1;
+      const uint64_t dK = umma_desc(sb + OFF_K + s * KT_BYTES_, 16, 1024, SWZ_128B);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t qoff = ((j >> 2) * (Q_BYTES / 2) + (j & 3) * 32) >> 4;
+        const uint32_t koff = ((j >> 2) * (KT_BYTES_ / 2) + (j & 3) * 32) >> 4;
+        umma_bf16(tmem + TM_S + s * BN, dQ + qoff, dK + koff, idescS, j > 0);
+      }
+      umma_commit(&bars.s[s]);
+    };
+    mbar_wait(&bars.q, 0);
+    mbar_wait(&bars.full[0], 0);
+    tc_fence_after();
+    if (lane == 0) issue_s(0);
+    __syncwarp();
+    for (int t = 0; t < n_tiles; ++t) {
+      if (t + 1 < n_tiles) {
+        const int s1 = (t + 1) & 1;
+        mbar_wait(&bars.full[s1], ((t + 1) >> 1) & 1);
+        if (t + 1 >= 2) mbar_wait(&bars.sfree[s1], (((t + 1) >> 1) - 1) & 1);
+        tc_fence_after();
+        if (lane == 0) issue_s(t + 1);
+        __syncwarp();
+      }
+      mbar_wait(&bars.p, t & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const int s = t & 1;
+        // V tile: MN-major (d contiguous), two 64-wide d panels 8 KiB apart, 8-key groups 1 KiB apart
+        const uint64_t dV = umma_desc(sb + OFF_V + s * KT_BYTES_, KT_BYTES_ / 2, 1024, SWZ_128B);
+#pragma unroll
+        for (int j = 0; j < BN / 16; ++j)
+          umma_bf16(tmem + TM_O, dP + j * 16, dV + j * 128, idescO, (t > 0 || j > 0) ? 1u : 0u);
+        umma_commit(&bars.pv);
+        umma_commit(&bars.empty[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------- softmax / epilogue ------------------------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const int pos = i0 + row + shift;  // absolute key position of this query
+    uint8_t* p_dst = smem + OFF_P + (row >> 3) * 1024 + (row & 7) * 16;
+    float m = -INFINITY, l = 0.f;
+    uint32_t r[32];
+    float x[64];
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t & 1;
+      const int j0 = (t_lo + t) * BN;
+      mbar_wait(&bars.s[s], (t >> 1) & 1);
+      tc_fence_after();
+      tmem_ld32(tlane + TM_S + s * BN, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) * a.scale_log2;
+      tmem_ld32(tlane + TM_S + s * BN + 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[32 + i] = __uint_as_float(r[i]) * a.scale_log2;
+      tc_fence_before();
+      mbar_arrive(&bars.sfree[s]);
+      // masks only on boundary tiles (CTA-uniform test)
+      const bool need_mask = (j0 + BN - 1 > p_first) || (a.window > 0 && j0 < p_last - a.window + 1) ||
+                             (j0 + BN > a.Tk);
+      if (need_mask) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const int j = j0 + i;
+          const bool vis = (j <= pos) && (j < a.Tk) && (a.window <= 0 || pos - j < a.window);
+          x[i] = vis ? x[i] : -INFINITY;
+        }
+      }
+      float mx = x[0];
+#pragma unroll
+      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, x[i]);
+      // lazy rescale: the running max only moves when it would grow by more than 2^THRESHOLD
+      const bool grow = mx > m + RESCALE_THRESHOLD;  // also true for the first finite max (m = -inf)
+      const float m_new = grow ? mx : m;
+      if (t > 0) {
+        mbar_wait(&bars.pv, (t - 1) & 1);  // P buffer free, O complete up to tile t-1
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+          const float f = grow ? exp2f(m - m_new) : 1.f;  // exp2(-inf) = 0 wipes an all-masked prefix
+          l *= f;
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            tmem_ld32(tlane + TM_O + c, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            tmem_st32(tlane + TM_O + c, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      m = m_new;
+      const float m_eff = (m == -INFINITY) ? 0.f : m;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        x[i] = exp2f(x[i] - m_eff);
+        sum += x[i];
+      }
+      l += sum;
+#pragma unroll
+      for (int kg = 0; kg < 8; ++kg) {
+        uint4 w;
+        w.x = pack_bf16(x[kg * 8 + 0], x[kg * 8 + 1]);
+        w.y = pack_bf16(x[kg * 8 + 2], x[kg * 8 + 3]);
+        w.z = pack_bf16(x[kg * 8 + 4], x[kg * 8 + 5]);
+        w.w = pack_bf16(x[kg * 8 + 6], x[kg * 8 + 7]);
+        *reinterpret_cast<uint4*>(p_dst + kg * 128) = w;
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bars.p);
+    }
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(&bars.pv, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const int i = i0 + row;
+    __nv_bfloat16* dst = a.o + (long long)b * a.o_sb + (long long)i * a.o_st + (long long)h * a.o_sh;
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      tmem_ld32(tlane + TM_O + c, r);
+      tmem_ld_wait();
+      if (i < a.Tq) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(r[v4 * 8 + 0]) * inv, __uint_as_float(r[v4 * 8 + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(r[v4 * 8 + 2]) * inv, __uint_as_float(r[v4 * 8 + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(r[v4 * 8 + 4]) * inv, __uint_as_float(r[v4 * 8 + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(r[v4 * 8 + 6]) * inv, __uint_as_float(r[v4 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c + v4 * 8) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TM_COLS>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// [B, T, Hn, 128] bf16 tensor with element strides (sb, st, sh), innermost contiguous; box = 64 x 1 x rows x 1
+bool make_map(CUtensorMap* m, const void* ptr, int B, int T, int Hn, long long sb, long long st, long long sh,
+              int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)HD, (cuuint64_t)Hn, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)st * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// q [B,Tq,Hq,128], k/v [B,Tk,Hkv,128], o [B,Tq,Hq,128]; strides in elements (batch, time, head).
+cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
+                           const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
+                           int window, float scale, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(swa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWA_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  CUtensorMap tq, tk, tv;
+  if (!make_map(&tq, q, B, Tq, Hq, qs[0], qs[1], qs[2], BM) || !make_map(&tk, k, B, Tk, Hkv, ks[0], ks[1], ks[2], BN) ||
+      !make_map(&tv, v, B, Tk, Hkv, vs[0], vs[1], vs[2], BN))
+    return cudaErrorInvalidValue;
+  SwaArgs a;
+  a.o = static_cast<__nv_bfloat16*>(o);
+  a.o_sb = os[0]; a.o_st = os[1]; a.o_sh = os[2];
+  a.Tq = Tq; a.Tk = Tk; a.Hq = Hq; a.group = Hq / Hkv;
+  a.window = (window > 0 && Tk > window) ? window : 0;  // HF glue passes the window only when key_len > W
+  a.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(Hq, (Tq + BM - 1) / BM, B);
+  swa_fwd_kernel<<<grid, SWA_THREADS, SWA_SMEM, stream>>>(tq, tk, tv, a);
+  return cudaGetLastError();
+}
+
+}  // namespace ivl

@@ -1,0 +1,68 @@
+"""Sliding-window attention operator on top of the C ABI (ivl_swa_fwd).
+
+``sliding_window_attention_forward`` has the signature of the HF attention-interface
+callables the reference looks up by name (``ALL_ATTENTION_FUNCTIONS["flash_attention_2"]``,
+infinitevl_standard/modeling_infinitevl.py:1092-1108): it takes query [B,Hq,Tq,D] and
+key/value [B,Hkv,Tk,D] and returns (attn_output [B,Tq,Hq,D], None).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _strides3(t: torch.Tensor):
+    """(batch, time, head) element strides of a [B, T, H, D] view as a ctypes int64[3]."""
+    assert t.stride(3) == 1, "innermost (head_dim) axis must be contiguous"
+    return (ctypes.c_int64 * 3)(t.stride(0), t.stride(1), t.stride(2))
+
+
+def swa_attention_bthd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window: Optional[int] = None,
+                       scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,Tq,Hq,128], k/v [B,Tk,Hkv,128] (bf16; arbitrary batch/time/head strides) -> out [B,Tq,Hq,128].
+    Causal with bottom-right alignment; ``window`` keys visible (self included) once Tk > window."""
+    if not q.is_cuda:
+        raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16, "SWA kernel computes in bf16"
+    B, Tq, Hq, D = q.shape
+    Tk, Hkv = k.shape[1], k.shape[2]
+    assert k.shape == v.shape and k.shape[0] == B and k.shape[3] == D
+    fix = lambda t: t if (t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3]) and t.data_ptr() % 16 == 0) \
+        else t.contiguous()
+    q, k, v = fix(q), fix(k), fix(v)
+    if out is None:
+        out = torch.empty(B, Tq, Hq, D, dtype=torch.bfloat16, device=q.device)
+    lib = _lib.load()
+    code = lib.ivl_swa_fwd(q.data_ptr(), _strides3(q), k.data_ptr(), _strides3(k), v.data_ptr(), _strides3(v),
+                           out.data_ptr(), _strides3(out), B, Tq, Tk, Hq, Hkv, D, int(window or 0),
+                           float(scale or 0.0), torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(code, "ivl_swa_fwd")
+    return out
+
+
+def swa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window: Optional[int] = None,
+                  scale: Optional[float] = None) -> torch.Tensor:
+    """HF head-first layout: q [B,Hq,Tq,D], k/v [B,Hkv,Tk,D] -> [B,Tq,Hq,D]."""
+    return swa_attention_bthd(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), window, scale)
+
+
+def sliding_window_attention_forward(module, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
+                                     attention_mask: Optional[torch.Tensor] = None, dropout: float = 0.0,
+                                     scaling: Optional[float] = None, sliding_window: Optional[int] = None,
+                                     **kwargs) -> Tuple[torch.Tensor, None]:
+    """Drop-in for the HF attention interface (same arguments as transformers'
+    flash_attention_forward).  Padding masks are not supported -- the reference's FA2 path gets
+    ``attention_mask=None`` for unpadded batches, and its GDN layers ignore padding anyway
+    (modeling_infinitevl.py:1223)."""
+    if attention_mask is not None and attention_mask.dim() == 2 and not bool(attention_mask.all()):
+        raise NotImplementedError("padded batches are not supported by the B200 SWA kernel")
+    if dropout:
+        raise NotImplementedError("attention dropout is not supported (inference / dropout=0 training only)")
+    if scaling is None:
+        scaling = query.shape[-1] ** -0.5
+    out = swa_attention(query, key, value, window=sliding_window, scale=scaling)
+    return out, None

@@ -126,7 +126,7 @@ def main():
                         out=oa.numpy(), window=np.array(W))
 
     # caches: small window so the roll-over is exercised
-    cfg_small = InfiniteVLTextConfig(sliding_window=8, num_key_value_heads=1, num_attention_heads=2, hidden_size=8,
+    cfg_small = InfiniteVLTextConfig(use_sliding_window=True, sliding_window=8, num_key_value_heads=1, num_attention_heads=2, hidden_size=8,
                                      head_dim=4)
     cfg_small.head_dim = 4
     layer = M.StaticSlidingWindowLayerPrealloc(config=cfg_small, batch_size=1, dtype=torch.float32, zero_init=True)

@@ -1,0 +1,91 @@
+"""GPU parity tests of the sliding-window attention kernel vs the fp32 oracle (eager restatement,
+oracle/swa.py) -- tolerance err-ratio <= 5e-3 (bf16 P and output rounding), stated in BASELINE.md 3c."""
+import pytest
+import torch
+
+from oracle import err_ratio, swa_attention_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def swa():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from infinitevl_b200 import swa as _swa
+    return _swa
+
+
+def _qkv(B, Hq, Hkv, Tq, Tk, seed, scale=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    q = (torch.randn(B, Hq, Tq, 128, generator=gen) * scale).bfloat16()
+    k = (torch.randn(B, Hkv, Tk, 128, generator=gen) * scale).bfloat16()
+    v = torch.randn(B, Hkv, Tk, 128, generator=gen).bfloat16()
+    return q, k, v
+
+
+@pytest.mark.parametrize("Tq,Tk,window", [
+    (1, 1, None), (1, 300, None), (64, 64, None), (128, 128, None), (130, 130, None), (257, 257, 100),
+    (384, 384, 256), (200, 1000, 512), (5, 700, 300), (1024, 1024, 8192), (1, 9000, 8192), (300, 8500, 8192),
+])
+def test_swa_matches_oracle(swa, Tq, Tk, window):
+    q, k, v = _qkv(1, 16, 2, Tq, Tk, seed=Tq * 7 + Tk)
+    ref = swa_attention_ref(q, k, v, window=window)
+    out = swa.swa_attention(q.cuda(), k.cuda(), v.cuda(), window=window)
+    assert out.shape == (1, Tq, 16, 128) and out.dtype == torch.bfloat16
+    assert torch.isfinite(out).all()
+    assert err_ratio(ref, out.float().cpu()) < 5e-3
+
+
+def test_swa_batch_heads_and_peaky_scores(swa):
+    """B = 2, MHA-like grouping 4:4, and large-magnitude scores (exercises the lazy rescale path)."""
+    q, k, v = _qkv(2, 4, 4, 300, 300, seed=3, scale=3.0)
+    ref = swa_attention_ref(q, k, v, window=128)
+    out = swa.swa_attention(q.cuda(), k.cuda(), v.cuda(), window=128)
+    assert err_ratio(ref, out.float().cpu()) < 5e-3
+    # scores grow along the sequence -> running max keeps increasing
+    q, k, v = _qkv(1, 8, 2, 512, 512, seed=4)
+    ramp = torch.linspace(0.2, 6.0, 512)[None, None, :, None]
+    k = (k.float() * ramp).bfloat16()
+    ref = swa_attention_ref(q, k, v, window=None)
+    out = swa.swa_attention(q.cuda(), k.cuda(), v.cuda(), window=None)
+    assert err_ratio(ref, out.float().cpu()) < 5e-3
+
+
+def test_swa_hf_interface_and_strided_views(swa):
+    """The mixer hands over [B,H,T,D] *views* of [B,T,H*D] projections (std:1047-1054): no copies needed."""
+    gen = torch.Generator().manual_seed(9)
+    B, T = 1, 260
+    qp = torch.randn(B, T, 16 * 128, generator=gen).bfloat16().cuda()
+    kp = torch.randn(B, T, 2 * 128, generator=gen).bfloat16().cuda()
+    vp = torch.randn(B, T, 2 * 128, generator=gen).bfloat16().cuda()
+    q = qp.view(B, T, 16, 128).transpose(1, 2)
+    k = kp.view(B, T, 2, 128).transpose(1, 2)
+    v = vp.view(B, T, 2, 128).transpose(1, 2)
+    mod = type("M", (), {"num_key_value_groups": 8, "is_causal": True, "training": False})()
+    out, w = swa.sliding_window_attention_forward(mod, q, k, v, None, dropout=0.0, scaling=128 ** -0.5,
+                                                  sliding_window=8192)
+    assert w is None and out.shape == (B, T, 16, 128)
+    ref = swa_attention_ref(q.cpu(), k.cpu(), v.cpu(), window=8192)
+    assert err_ratio(ref, out.float().cpu()) < 5e-3
+    with pytest.raises(NotImplementedError):
+        swa.sliding_window_attention_forward(mod, q, k, v, None, dropout=0.1)
+
+
+def test_swa_window_property_at_full_size(swa):
+    """Size-independent property at the BASELINE shape (T = 32768, W = 8192): a query's output depends
+    only on the last W keys, so attention over the full sequence == attention over a suffix that starts
+    at least W-1 keys before the first query examined."""
+    T, W = 32768, 8192
+    q, k, v = _qkv(1, 16, 2, T, T, seed=11)
+    q, k, v = q.cuda(), k.cuda(), v.cuda()
+    full = swa.swa_attention(q, k, v, window=W)
+    assert torch.isfinite(full).all()
+    s = T - 1024                  # examine the last 1024 queries
+    lo = s - (W - 1)
+    part = swa.swa_attention(q[:, :, s:], k[:, :, lo:], v[:, :, lo:], window=W)
+    assert err_ratio(part.float(), full[:, s:].float()) < 2e-3
+    # and against the oracle on a slice the CPU can finish quickly
+    ref = swa_attention_ref(q[:, :, T - 64:].cpu(), k[:, :, T - 64 - (W - 1):].cpu(), v[:, :, T - 64 - (W - 1):].cpu(),
+                            window=W)
+    assert err_ratio(ref, full[:, T - 64:].float().cpu()) < 5e-3
