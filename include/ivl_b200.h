@@ -103,6 +103,34 @@ IVL_API int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, 
                         const void* v, const int64_t* v_strides, void* o, const int64_t* o_strides, int B,
                         int Tq, int Tk, int Hq, int Hkv, int D, int window, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Element-wise pieces of the two mixers (each one coalesced streaming launch).
+ * ---------------------------------------------------------------------------------- */
+
+/* Depthwise causal conv (kernel size 4) + optional SiLU with a carried input tail.
+ * Replaces ShortConvolution.forward/step -> causal_conv1d_fn / causal_conv1d_update
+ * (fla/modules/convolution.py:195-293).  x,y bf16 [B,T,D]; w bf16 [D,4] (the module's [D,1,4]);
+ * cache_in / cache_out bf16 [B,D,4] = the last 4 inputs, newest in column 3; either may be NULL.
+ * cache_in is left context (pip-fla semantics); cache_out must not alias cache_in.  D % 8 == 0. */
+IVL_API int ivl_short_conv_fwd(const void* x, const void* w, const void* cache_in, void* y, void* cache_out,
+                               int B, int T, int D, int activation_silu, void* stream);
+
+/* g = -exp(A_log[h]) * softplus(a + dt_bias[h]) (fp32), beta = sigmoid(b) (bf16) -- std:1293-1294.
+ * a, b bf16 [n_tokens, H] (outputs of a_proj / b_proj); A_log, dt_bias fp32 [H]. */
+IVL_API int ivl_gdn_gate_fwd(const void* a, const void* b, const float* A_log, const float* dt_bias, float* g,
+                             void* beta, int64_t n_tokens, int H, void* stream);
+
+/* y = x * rsqrt(mean(x^2) + eps) * w * gate * sigmoid(gate) over rows of 256 (FusedRMSNormGated,
+ * fla/modules/fused_norm_gate.py:26-95,735-797).  x, gate, y bf16 [rows,256]; w bf16 [256]. */
+IVL_API int ivl_rmsnorm_gated_fwd(const void* x, const void* gate, const void* w, void* y, int64_t rows, int dim,
+                                  float eps, void* stream);
+
+/* In-place rotary embedding of x [B,T,Hn,128] (strides {batch,time,head} in elements) with merged
+ * per-token cos/sin bf16 [B,T,128]; bit-exact with the reference's bf16 expression
+ * q*cos + rotate_half(q)*sin (std:949-984). */
+IVL_API int ivl_mrope_apply(void* x, const int64_t* x_strides, const void* cos, const void* sin, int B, int T,
+                            int Hn, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

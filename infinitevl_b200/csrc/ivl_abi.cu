@@ -17,6 +17,14 @@ cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, co
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
                            int window, float scale, cudaStream_t stream);
+cudaError_t launch_short_conv(const void* x, const void* w, const void* cache_in, void* y, void* cache_out, int B,
+                              int T, int D, int act, cudaStream_t stream);
+cudaError_t launch_gdn_gate(const void* a, const void* b, const float* A_log, const float* dt_bias, float* g,
+                            void* beta, long long n, int H, cudaStream_t stream);
+cudaError_t launch_rmsnorm_gated(const void* x, const void* gate, const void* w, void* y, long long rows, float eps,
+                                 cudaStream_t stream);
+cudaError_t launch_mrope(void* x, const long long* xs, const void* cosr, const void* sinr, int B, int T, int Hn,
+                         cudaStream_t stream);
 }  // namespace ivl
 
 namespace {
@@ -113,6 +121,44 @@ int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const in
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
   cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, B, Tq, Tk, Hq, Hkv, window, sc,
                                       static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_short_conv_fwd(const void* x, const void* w, const void* cache_in, void* y, void* cache_out, int B, int T,
+                       int D, int activation_silu, void* stream) {
+  if (B <= 0 || T <= 0 || D <= 0 || (D & 7) || B > 65535 || (T + 31) / 32 > 65535 * 32) return IVL_ERR_BAD_SHAPE;
+  if (!x || !w || !y) return IVL_ERR_NULL;
+  if (cache_out && cache_out == cache_in) return IVL_ERR_BAD_SHAPE;
+  if ((T + 31) / 32 > 65535) return IVL_ERR_BAD_SHAPE;
+  cudaError_t e = ivl::launch_short_conv(x, w, cache_in, y, cache_out, B, T, D, activation_silu,
+                                         static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_gdn_gate_fwd(const void* a, const void* b, const float* A_log, const float* dt_bias, float* g, void* beta,
+                     int64_t n_tokens, int H, void* stream) {
+  if (n_tokens <= 0 || H <= 0) return IVL_ERR_BAD_SHAPE;
+  if (!a || !b || !A_log || !dt_bias || !g || !beta) return IVL_ERR_NULL;
+  cudaError_t e = ivl::launch_gdn_gate(a, b, A_log, dt_bias, g, beta, (long long)n_tokens * H, H,
+                                       static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_rmsnorm_gated_fwd(const void* x, const void* gate, const void* w, void* y, int64_t rows, int dim, float eps,
+                          void* stream) {
+  if (rows <= 0 || dim != 256) return IVL_ERR_BAD_SHAPE;
+  if (!x || !gate || !w || !y) return IVL_ERR_NULL;
+  cudaError_t e = ivl::launch_rmsnorm_gated(x, gate, w, y, rows, eps, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_mrope_apply(void* x, const int64_t* x_strides, const void* cos, const void* sin, int B, int T, int Hn, int D,
+                    void* stream) {
+  if (B <= 0 || T <= 0 || Hn <= 0 || D != 128 || B > 65535) return IVL_ERR_BAD_SHAPE;
+  if (!x || !x_strides || !cos || !sin) return IVL_ERR_NULL;
+  long long xs[3] = {x_strides[0], x_strides[1], x_strides[2]};
+  if ((xs[0] | xs[1] | xs[2]) & 7) return IVL_ERR_BAD_SHAPE;
+  cudaError_t e = ivl::launch_mrope(x, xs, cos, sin, B, T, Hn, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 

@@ -1,0 +1,412 @@
+"""Host-side mirror of the reference's mixer / decoder-block interface for the hot path.
+
+Same class names, constructor arguments, parameter (state-dict) names and forward signatures as
+infinitevl/infinitevl_standard/modeling_infinitevl.py (GatedDeltaNet :1116-1347,
+InfiniteVLSelfAttention :986-1113, InfiniteVLDecoderLayer :1350-1429, InfiniteVLRotaryEmbedding
+:895-930) and the fla modules they use (ShortConvolution, FusedRMSNormGated), so a checkpoint of
+the reference loads with load_state_dict and the reference's callers need no change.  The
+token-mixing math runs in libivl_b200.so; projections are plain nn.Linear (cuBLAS).
+
+Everything here is inference-only (no autograd through the custom kernels): the backward pass is
+row f-1 of SURVEY.md section 8, not built yet.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops, swa
+from .cache import StaticCachePrealloc
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+# ------------------------------------------------------------------------------------------------
+# functional wrappers of the element-wise kernels
+# ------------------------------------------------------------------------------------------------
+def short_conv_silu(x: torch.Tensor, weight: torch.Tensor, cache: Optional[torch.Tensor] = None,
+                    output_final_state: bool = False, activation: Optional[str] = "silu",
+                    cache_out: Optional[torch.Tensor] = None):
+    """x bf16 [B,T,D]; weight [D,1,4] or [D,4]; cache [B,D,4] (left context) -> (y, final_state | None)."""
+    if not x.is_cuda:
+        raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
+    assert x.dtype == torch.bfloat16
+    B, T, D = x.shape
+    x = x.contiguous()
+    w = weight.reshape(D, -1).to(torch.bfloat16).contiguous()
+    assert w.shape[1] == 4, "the B200 short-conv kernel is specialised for kernel_size 4"
+    y = torch.empty_like(x)
+    if cache is not None:
+        cache = cache.to(torch.bfloat16).contiguous()
+    out_state = None
+    if output_final_state:
+        out_state = cache_out if cache_out is not None else torch.empty(B, D, 4, dtype=torch.bfloat16, device=x.device)
+    code = _lib.load().ivl_short_conv_fwd(x.data_ptr(), w.data_ptr(), None if cache is None else cache.data_ptr(),
+                                          y.data_ptr(), None if out_state is None else out_state.data_ptr(),
+                                          B, T, D, 1 if activation in ("silu", "swish") else 0, _stream(x))
+    _lib.check(code, "ivl_short_conv_fwd")
+    return y, out_state
+
+
+def gdn_gates(a: torch.Tensor, b: torch.Tensor, A_log: torch.Tensor, dt_bias: torch.Tensor):
+    """a, b bf16 [..., H] -> (g fp32 [..., H], beta bf16 [..., H])  (std:1293-1294)."""
+    H = a.shape[-1]
+    a, b = a.to(torch.bfloat16).contiguous(), b.to(torch.bfloat16).contiguous()
+    g = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+    beta = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    # keep the fp32 copies alive until the launch is enqueued: a temporary freed between the two
+    # conversions would hand the same allocator block to both
+    A32, dt32 = A_log.float().contiguous(), dt_bias.float().contiguous()
+    code = _lib.load().ivl_gdn_gate_fwd(a.data_ptr(), b.data_ptr(), A32.data_ptr(), dt32.data_ptr(), g.data_ptr(),
+                                        beta.data_ptr(), a.numel() // H, H, _stream(a))
+    _lib.check(code, "ivl_gdn_gate_fwd")
+    return g, beta
+
+
+def rmsnorm_gated(x: torch.Tensor, gate: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    assert x.shape == gate.shape and x.shape[-1] == 256 and x.dtype == torch.bfloat16
+    x, gate = x.contiguous(), gate.to(torch.bfloat16).contiguous()
+    y = torch.empty_like(x)
+    w = weight.to(torch.bfloat16).contiguous()
+    code = _lib.load().ivl_rmsnorm_gated_fwd(x.data_ptr(), gate.data_ptr(), w.data_ptr(), y.data_ptr(),
+                                             x.numel() // 256, 256, float(eps), _stream(x))
+    _lib.check(code, "ivl_rmsnorm_gated_fwd")
+    return y
+
+
+def mrope_select(cos: torch.Tensor, sin: torch.Tensor, mrope_section) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[3,B,T,D] tables -> [B,T,D]: channel section i of the doubled list takes position row i % 3 (std:972-978)."""
+    sec = list(mrope_section) * 2
+    cos = torch.cat([m[i % 3] for i, m in enumerate(cos.split(sec, dim=-1))], dim=-1)
+    sin = torch.cat([m[i % 3] for i, m in enumerate(sin.split(sec, dim=-1))], dim=-1)
+    return cos.contiguous(), sin.contiguous()
+
+
+def mrope_apply_(x_bthd: torch.Tensor, cos_btd: torch.Tensor, sin_btd: torch.Tensor) -> torch.Tensor:
+    """In-place rotation of a [B,T,H,128] bf16 view (any batch/time/head strides)."""
+    import ctypes
+    assert x_bthd.dtype == torch.bfloat16 and x_bthd.stride(3) == 1
+    B, T, Hn, D = x_bthd.shape
+    strides = (ctypes.c_int64 * 3)(x_bthd.stride(0), x_bthd.stride(1), x_bthd.stride(2))
+    c, s = cos_btd.to(torch.bfloat16).contiguous(), sin_btd.to(torch.bfloat16).contiguous()
+    code = _lib.load().ivl_mrope_apply(x_bthd.data_ptr(), strides, c.data_ptr(), s.data_ptr(), B, T, Hn, D,
+                                       _stream(x_bthd))
+    _lib.check(code, "ivl_mrope_apply")
+    return x_bthd
+
+
+# ------------------------------------------------------------------------------------------------
+# modules (reference parameter names)
+# ------------------------------------------------------------------------------------------------
+class ShortConvolution(nn.Module):
+    """Depthwise causal conv + SiLU; weight [hidden_size, 1, kernel_size] like the nn.Conv1d the
+    reference subclasses (fla/modules/convolution.py:124-293)."""
+
+    def __init__(self, hidden_size: int, kernel_size: int = 4, bias: bool = False, activation: Optional[str] = "silu",
+                 **kwargs):
+        super().__init__()
+        if bias:
+            raise NotImplementedError("conv bias is not used by InfiniteVL (conv_bias=False)")
+        self.hidden_size, self.kernel_size, self.activation = hidden_size, kernel_size, activation
+        self.weight = nn.Parameter(torch.empty(hidden_size, 1, kernel_size))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        self.bias = None
+
+    def forward(self, x: torch.Tensor, cache: Optional[torch.Tensor] = None, output_final_state: bool = False,
+                cu_seqlens=None, **kwargs):
+        if cu_seqlens is not None:
+            raise NotImplementedError("packed variable-length input is not supported by the B200 short conv yet")
+        return short_conv_silu(x, self.weight, cache, output_final_state, self.activation)
+
+
+class FusedRMSNormGated(nn.Module):
+    def __init__(self, hidden_size: int, eps: float = 1e-5, **kwargs):
+        super().__init__()
+        self.hidden_size, self.eps = hidden_size, eps
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+
+    def forward(self, x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+        return rmsnorm_gated(x, g, self.weight, self.eps)
+
+
+class InfiniteVLRMSNorm(nn.Module):
+    """Qwen2RMSNorm (fp32 inside, eps 1e-6); token-local, not part of the hot path (plain torch)."""
+
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, hidden_states):
+        dt = hidden_states.dtype
+        h = hidden_states.to(torch.float32)
+        h = h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + self.variance_epsilon)
+        return self.weight * h.to(dt)
+
+
+class InfiniteVLRotaryEmbedding(nn.Module):
+    """cos/sin tables [3,B,T,head_dim] from M-RoPE position ids [3,B,T] (std:895-930)."""
+
+    def __init__(self, config, device=None):
+        super().__init__()
+        head_dim = getattr(config, "head_dim", None) or config.hidden_size // config.num_attention_heads
+        rs = getattr(config, "rope_scaling", None) or {}
+        theta = rs.get("rope_theta", getattr(config, "rope_theta", 1e6))
+        inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+        self.register_buffer("inv_freq", inv_freq.to(device) if device is not None else inv_freq, persistent=False)
+        self.attention_scaling = 1.0
+
+    @torch.no_grad()
+    def forward(self, x, position_ids):
+        inv = self.inv_freq[None, None, :, None].float().expand(3, position_ids.shape[1], -1, 1).to(x.device)
+        pos = position_ids[:, :, None, :].float()
+        freqs = (inv @ pos).transpose(2, 3)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        return (emb.cos() * self.attention_scaling).to(x.dtype), (emb.sin() * self.attention_scaling).to(x.dtype)
+
+
+class GatedDeltaNet(nn.Module):
+    """Gated DeltaNet mixer (std:1116-1347).  forward(hidden_states, attention_mask=None,
+    past_key_values=None, cache_position=None, **kw) -> (o, None)."""
+
+    def __init__(self, config, layer_idx: int):
+        super().__init__()
+        self.mode = getattr(config, "mode", "chunk")
+        self.hidden_size = config.hidden_size
+        self.expand_v = config.expand_v
+        self.norm_eps = getattr(config, "norm_eps", 1e-5)
+        self.use_gate = getattr(config, "use_gate", True)
+        self.use_short_conv = getattr(config, "use_short_conv", True)
+        self.conv_size = getattr(config, "conv_size", 4)
+        self.num_heads = config.num_linear_heads
+        self.num_key_value_heads = getattr(config, "num_linear_key_value_heads", self.num_heads)
+        self.head_dim = getattr(config, "linear_head_dim", None) or config.hidden_size // config.num_attention_heads
+        self.key_dim = int(self.num_key_value_heads * self.head_dim)
+        self.value_dim = int(self.key_dim * self.expand_v)
+        self.head_k_dim = self.head_dim
+        self.head_v_dim = int(self.head_dim * self.expand_v)
+        self.layer_idx = layer_idx
+        if not math.isclose(self.head_dim * self.expand_v, self.head_v_dim, rel_tol=1e-5):
+            raise ValueError(f"expand_v={self.expand_v} does not produce an integer head_v_dim")
+        assert self.mode in ["chunk", "fused_recurrent"], f"Not suppoerted mode `{self.mode}`."
+        if not (self.use_short_conv and self.use_gate):
+            raise NotImplementedError("the B200 path implements the shipped configuration (short conv + output gate)")
+        if (self.head_k_dim, self.head_v_dim, self.conv_size) != (128, 256, 4):
+            raise NotImplementedError("the B200 kernels are specialised for head dims K=128, V=256 and conv_size=4")
+        self.q_proj = nn.Linear(self.hidden_size, self.num_heads * self.head_dim, bias=False)
+        self.k_proj = nn.Linear(self.hidden_size, self.key_dim, bias=False)
+        self.v_proj = nn.Linear(self.hidden_size, self.value_dim, bias=False)
+        self.a_proj = nn.Linear(self.hidden_size, self.num_heads, bias=False)
+        self.b_proj = nn.Linear(self.hidden_size, self.num_heads, bias=False)
+        A = torch.empty(self.num_heads, dtype=torch.float32).uniform_(0, 16)
+        self.A_log = nn.Parameter(torch.log(A))
+        self.A_log._no_weight_decay = True
+        dt = torch.exp(torch.rand(self.num_heads) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))
+        dt = torch.clamp(dt, min=1e-4)
+        self.dt_bias = nn.Parameter(dt + torch.log(-torch.expm1(-dt)))
+        self.dt_bias._no_weight_decay = True
+        self.q_conv1d = ShortConvolution(self.num_heads * self.head_dim, self.conv_size, activation="silu")
+        self.k_conv1d = ShortConvolution(self.key_dim, self.conv_size, activation="silu")
+        self.v_conv1d = ShortConvolution(self.value_dim, self.conv_size, activation="silu")
+        self.g_proj = nn.Linear(self.hidden_size, self.num_heads * self.head_v_dim, bias=False)
+        self.o_norm = FusedRMSNormGated(self.head_v_dim, eps=self.norm_eps)
+        self.o_proj = nn.Linear(self.num_heads * self.head_v_dim, self.hidden_size, bias=False)
+
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                past_key_values=None, cache_position: Optional[torch.LongTensor] = None, **kwargs):
+        # padding masks are ignored, exactly as the reference does (std:1223)
+        B, q_len, _ = hidden_states.shape
+        mode = "fused_recurrent" if q_len <= 64 else self.mode
+        prev_q = prev_k = prev_v = recurrent_state = None
+        use_cache = past_key_values is not None
+        if use_cache:
+            (prev_q, prev_k, prev_v), recurrent_state = past_key_values.update(
+                layer_idx=self.layer_idx, key_states=None, value_states=None, conv_state=None, recurrent_state=None,
+                cache_kwargs={"op": "get", "cache_position": cache_position})
+        q, new_q = self.q_conv1d(self.q_proj(hidden_states), cache=prev_q, output_final_state=use_cache)
+        k, new_k = self.k_conv1d(self.k_proj(hidden_states), cache=prev_k, output_final_state=use_cache)
+        v, new_v = self.v_conv1d(self.v_proj(hidden_states), cache=prev_v, output_final_state=use_cache)
+        q = q.view(B, q_len, self.num_heads, self.head_k_dim)
+        k = k.view(B, q_len, self.num_key_value_heads, self.head_k_dim)
+        v = v.view(B, q_len, self.num_key_value_heads, self.head_v_dim)
+        g, beta = gdn_gates(self.a_proj(hidden_states), self.b_proj(hidden_states), self.A_log, self.dt_bias)
+        fn = ops.chunk_gated_delta_rule if mode == "chunk" else ops.fused_recurrent_gated_delta_rule
+        o, next_state = fn(q=q, k=k, v=v, g=g, beta=beta, initial_state=recurrent_state,
+                           output_final_state=use_cache, use_qk_l2norm_in_kernel=True)
+        if use_cache:
+            past_key_values.update(layer_idx=self.layer_idx, key_states=None, value_states=None,
+                                   conv_state=(new_q, new_k, new_v), recurrent_state=next_state,
+                                   cache_kwargs={"op": "set", "delta_len": q_len, "cache_position": cache_position})
+        gate = self.g_proj(hidden_states).view(B, q_len, self.num_heads, self.head_v_dim)
+        o = self.o_norm(o, gate)
+        o = self.o_proj(o.reshape(B, q_len, self.num_heads * self.head_v_dim))
+        return o, None
+
+
+class InfiniteVLSelfAttention(nn.Module):
+    """Sliding-window attention mixer (std:986-1113)."""
+
+    def __init__(self, config, layer_idx: Optional[int] = None):
+        super().__init__()
+        self.config = config
+        self.layer_idx = layer_idx
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.head_dim = self.hidden_size // self.num_heads
+        self.num_key_value_heads = config.num_key_value_heads
+        self.num_key_value_groups = self.num_heads // self.num_key_value_heads
+        self.is_causal = True
+        self.attention_dropout = getattr(config, "attention_dropout", 0.0)
+        self.rope_scaling = getattr(config, "rope_scaling", None) or {"mrope_section": [16, 24, 24]}
+        self.scaling = self.head_dim ** -0.5
+        if self.head_dim * self.num_heads != self.hidden_size:
+            raise ValueError(f"hidden_size must be divisible by num_heads (got `hidden_size`: {self.hidden_size}"
+                             f" and `num_heads`: {self.num_heads}).")
+        self.q_proj = nn.Linear(self.hidden_size, self.num_heads * self.head_dim, bias=True)
+        self.k_proj = nn.Linear(self.hidden_size, self.num_key_value_heads * self.head_dim, bias=True)
+        self.v_proj = nn.Linear(self.hidden_size, self.num_key_value_heads * self.head_dim, bias=True)
+        self.o_proj = nn.Linear(self.num_heads * self.head_dim, self.hidden_size, bias=False)
+        layer_types = getattr(config, "layer_types", None)
+        is_sliding = layer_types is None or layer_idx is None or layer_types[layer_idx] == "sliding_attention"
+        self.sliding_window = getattr(config, "sliding_window", None) if is_sliding else None
+        self.rotary_emb = InfiniteVLRotaryEmbedding(config=config)
+
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.LongTensor] = None, past_key_values=None, output_attentions: bool = False,
+                use_cache: bool = False, cache_position: Optional[torch.LongTensor] = None,
+                position_embeddings: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, **kwargs):
+        B, q_len, _ = hidden_states.shape
+        q = self.q_proj(hidden_states).view(B, q_len, self.num_heads, self.head_dim)
+        k = self.k_proj(hidden_states).view(B, q_len, self.num_key_value_heads, self.head_dim)
+        v = self.v_proj(hidden_states).view(B, q_len, self.num_key_value_heads, self.head_dim)
+        cos, sin = position_embeddings
+        if cos.dim() == 4:  # [3,B,T,D] M-RoPE tables -> merged [B,T,D]
+            cos, sin = mrope_select(cos, sin, self.rope_scaling["mrope_section"])
+        mrope_apply_(q, cos, sin)
+        mrope_apply_(k, cos, sin)
+        key_states, value_states = k.transpose(1, 2), v.transpose(1, 2)  # [B,H,T,D] views, as the cache expects
+        if past_key_values is not None:
+            key_states, value_states = past_key_values.update(
+                layer_idx=self.layer_idx, key_states=key_states, value_states=value_states, conv_state=None,
+                recurrent_state=None, cache_kwargs={"sin": sin, "cos": cos, "cache_position": cache_position})
+        out, _ = swa.sliding_window_attention_forward(self, q.transpose(1, 2), key_states, value_states, None,
+                                                      dropout=0.0, scaling=self.scaling,
+                                                      sliding_window=self.sliding_window)
+        out = self.o_proj(out.reshape(B, q_len, self.num_heads * self.head_dim))
+        return out, None
+
+
+class InfiniteVLTextMLP(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.gate_proj = nn.Linear(config.hidden_size, config.intermediate_size, bias=False)
+        self.up_proj = nn.Linear(config.hidden_size, config.intermediate_size, bias=False)
+        self.down_proj = nn.Linear(config.intermediate_size, config.hidden_size, bias=False)
+
+    def forward(self, x):
+        return self.down_proj(F.silu(self.gate_proj(x)) * self.up_proj(x))
+
+
+class InfiniteVLDecoderLayer(nn.Module):
+    """RMSNorm -> mixer -> +res -> RMSNorm -> MLP -> +res (std:1350-1429)."""
+
+    def __init__(self, config, layer_idx: int):
+        super().__init__()
+        self.hidden_size = config.hidden_size
+        self.layer_type = config.layer_types[layer_idx]
+        if self.layer_type == "linear_attention":
+            self.self_attn = GatedDeltaNet(config, layer_idx)
+        elif self.layer_type in ("full_attention", "sliding_attention"):
+            self.self_attn = InfiniteVLSelfAttention(config, layer_idx)
+        else:
+            raise ValueError(f"unknown layer type {self.layer_type}")
+        self.mlp = InfiniteVLTextMLP(config)
+        self.input_layernorm = InfiniteVLRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_attention_layernorm = InfiniteVLRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.attention_type = self.layer_type
+
+    @torch.no_grad()
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_values=None,
+                output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
+        residual = hidden_states
+        hidden_states = self.input_layernorm(hidden_states)
+        hidden_states, _ = self.self_attn(hidden_states=hidden_states, attention_mask=attention_mask,
+                                          position_ids=position_ids, past_key_values=past_key_values,
+                                          output_attentions=output_attentions, use_cache=use_cache,
+                                          cache_position=cache_position, position_embeddings=position_embeddings,
+                                          **kwargs)
+        hidden_states = residual + hidden_states
+        residual = hidden_states
+        hidden_states = self.mlp(self.post_attention_layernorm(hidden_states))
+        return (residual + hidden_states,)
+
+
+class HybridTextConfig:
+    """Minimal stand-in for InfiniteVLTextConfig (configuration_infinitevl.py:208-286) with the shipped
+    3B values (config.json:15-47); any object with these attributes works in its place."""
+
+    def __init__(self, **kw):
+        d = dict(hidden_size=2048, intermediate_size=11008, num_hidden_layers=36, num_attention_heads=16,
+                 num_key_value_heads=2, rms_norm_eps=1e-6, use_sliding_window=True, sliding_window=8192,
+                 attention_dropout=0.0, rope_theta=1e6,
+                 rope_scaling={"rope_type": "default", "mrope_section": [16, 24, 24], "rope_theta": 1e6},
+                 num_linear_heads=16, num_linear_key_value_heads=16, linear_head_dim=128, expand_v=2, mode="chunk",
+                 use_gate=True, use_short_conv=True, conv_size=4, conv_bias=False, norm_eps=1e-5,
+                 max_position_embeddings=128000, layer_types=None)
+        d.update(kw)
+        for k_, v_ in d.items():
+            setattr(self, k_, v_)
+        if self.layer_types is None:
+            self.layer_types = ["sliding_attention" if i % 4 == 0 else "linear_attention"
+                                for i in range(self.num_hidden_layers)]
+        if not self.use_sliding_window:
+            self.sliding_window = None
+        self.head_dim = self.hidden_size // self.num_attention_heads
+
+
+class HybridDecoder(nn.Module):
+    """The decoder stack of InfiniteVLTextModel without embeddings / lm_head (std:1455-1591): what the hot
+    path lives in.  forward(inputs_embeds [B,T,hidden], position_ids [3,B,T] or [B,T]) -> hidden states."""
+
+    def __init__(self, config, mixers_only: bool = False):
+        super().__init__()
+        self.config = config
+        self.layers = nn.ModuleList([InfiniteVLDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.norm = InfiniteVLRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.rotary_emb = InfiniteVLRotaryEmbedding(config=config)
+        self.mixers_only = mixers_only
+
+    def allocate_inference_cache(self, batch_size: int, device=None, dtype=None):
+        p = next(self.parameters())
+        return StaticCachePrealloc(config=self.config, batch_size=batch_size, device=device or p.device,
+                                   dtype=dtype or p.dtype)
+
+    @torch.no_grad()
+    def forward(self, inputs_embeds, position_ids=None, past_key_values=None, cache_position=None, use_cache=None):
+        B, T, _ = inputs_embeds.shape
+        if cache_position is None:
+            past = past_key_values.get_seq_length() if past_key_values is not None else 0
+            cache_position = torch.arange(past, past + T, device=inputs_embeds.device)
+        if position_ids is None:
+            position_ids = cache_position.view(1, 1, -1).expand(3, B, -1)
+        elif position_ids.dim() == 2:
+            position_ids = position_ids[None].expand(3, -1, -1)
+        cos, sin = self.rotary_emb(inputs_embeds, position_ids)
+        cos, sin = mrope_select(cos, sin, self.config.rope_scaling["mrope_section"])
+        h = inputs_embeds
+        for layer in self.layers:
+            if self.mixers_only:
+                h = h + layer.self_attn(hidden_states=layer.input_layernorm(h), past_key_values=past_key_values,
+                                        cache_position=cache_position, position_embeddings=(cos, sin))[0]
+            else:
+                h = layer(h, position_ids=position_ids, past_key_values=past_key_values,
+                          cache_position=cache_position, position_embeddings=(cos, sin))[0]
+        return self.norm(h)

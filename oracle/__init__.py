@@ -36,3 +36,5 @@ from .swa import (  # noqa: F401
 from .cache import (  # noqa: F401
     SlidingWindowCacheRef, LinearCacheRef, swa_mask_sizes_ref,
 )
+from .block import hybrid_decoder_ref, mlp_ref, swa_mixer_ref  # noqa: F401,E402
+from .gdn import gdn_mixer_ref  # noqa: F401,E402

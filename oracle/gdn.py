@@ -209,8 +209,13 @@ def gdn_mixer_ref(
     norm_eps: float = 1e-5,
     mode: Optional[str] = None,
     dtype=torch.float32,
+    proj_dtype=None,
 ):
     """Whole GatedDeltaNet.forward (std:1215-1347) on [B, T, hidden].
+
+    ``proj_dtype=torch.bfloat16`` rounds every projection output to bf16, which is what the
+    reference's bf16 model does -- the decay g is very sensitive to
+    the rounding of a_proj's output, so mixer-level comparisons of a bf16 model need it.
 
     ``params`` uses the reference's parameter names: q_proj.weight,
     k_proj.weight, v_proj.weight, a_proj.weight, b_proj.weight, A_log, dt_bias,
@@ -219,7 +224,9 @@ def gdn_mixer_ref(
     """
     B, T, _ = hidden.shape
     x = hidden.to(dtype)
-    lin = lambda name: x @ params[name + ".weight"].to(dtype).t()
+    def lin(name):
+        y = x @ params[name + ".weight"].to(dtype).t()
+        return y if proj_dtype is None else y.to(proj_dtype).to(dtype)
     cq, ck, cv = conv_cache if conv_cache is not None else (None, None, None)
     q, ncq = short_conv_ref(lin("q_proj"), params["q_conv1d.weight"], cq, dtype=dtype)
     k, nck = short_conv_ref(lin("k_proj"), params["k_conv1d.weight"], ck, dtype=dtype)

@@ -1,0 +1,101 @@
+"""CPU tests: the product's cache classes against the reference's own trace (bit-exact integer /
+copy semantics, SURVEY.md rows a-C1..a-C3) and the demo's clone protocol."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from infinitevl_b200.cache import StaticCachePrealloc, StaticLinearLayerPrealloc, StaticSlidingWindowLayerPrealloc
+from infinitevl_b200.modeling import HybridTextConfig
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=True)
+
+
+def test_swa_layer_matches_reference_trace(golden_dir):
+    z = _load(golden_dir, "ref_swa_cache.npz")
+    cfg = HybridTextConfig(sliding_window=int(z["window"]), num_key_value_heads=1, num_attention_heads=2,
+                           hidden_size=8)
+    layer = StaticSlidingWindowLayerPrealloc(config=cfg, batch_size=1, dtype=torch.float32, zero_init=True)
+    assert layer.capacity == 7 and layer.is_sliding
+    base = 0
+    for step, n in enumerate(z["steps"]):
+        n = int(n)
+        kk = torch.arange(base, base + n, dtype=torch.float32)[None, None, :, None].expand(1, 1, n, 4).contiguous()
+        buf_ptr = layer._buf_keys.data_ptr()
+        fk, fv = layer.update(kk, kk * 2)
+        base += n
+        kv_len, kv_off = layer.get_mask_sizes(torch.arange(n))
+        assert [n, kv_len, kv_off, layer.size, layer.cumulative_length, fk.shape[-2]] == [int(x) for x in z["sizes"][step]]
+        assert np.array_equal(fk[0, 0, :, 0].numpy(), z["full"][step])
+        assert np.array_equal(layer.keys[0, 0, :, 0].numpy(), z["tail"][step])
+        assert layer._buf_keys.data_ptr() == buf_ptr and layer.keys.data_ptr() == buf_ptr  # fixed addresses
+    with pytest.raises(ValueError):
+        layer.crop(3)  # forbidden once the window has filled (std:192-194)
+    with pytest.raises(ValueError):
+        layer.update(torch.zeros(2, 1, 1, 4), torch.zeros(2, 1, 1, 4))
+    with pytest.raises(RuntimeError):
+        layer.batch_repeat_interleave(2)
+
+
+def test_linear_layer_matches_reference(golden_dir):
+    z = _load(golden_dir, "ref_linear_cache.npz")
+    cfg = HybridTextConfig(num_linear_heads=2, num_linear_key_value_heads=2, linear_head_dim=4, expand_v=2, conv_size=4)
+    lin = StaticLinearLayerPrealloc(config=cfg, batch_size=1, dtype=torch.bfloat16, zero_init=True)
+    assert [list(lin.conv_state_q.shape) + [0], list(lin.conv_state_v.shape) + [0], list(lin.recurrent_state.shape)] \
+        == [list(x) for x in z["shapes"]]
+    first = lin.update(cache_kwargs={"op": "get"})
+    assert first == ((None, None, None), None)
+    assert lin.update(cache_kwargs={"op": "get"})[1] is lin.recurrent_state
+    t = lambda n: torch.from_numpy(z[n])
+    ptr = lin.recurrent_state.data_ptr()
+    lin.update(conv_state=(t("cq"), t("ck"), t("cv")), recurrent_state=t("state_in"),
+               cache_kwargs={"op": "set", "delta_len": 7})
+    (cq, ck, cv), st = lin.update(cache_kwargs={"op": "get"})
+    assert st.data_ptr() == ptr and st.dtype == torch.bfloat16
+    assert torch.equal(st.float(), t("state_out")) and torch.equal(cq.float(), t("cq_out")) and torch.equal(cv.float(), t("cv_out"))
+    assert lin.get_seq_length() == int(z["seq_len"]) and lin.get_mask_sizes(torch.arange(3)) == (10, 0)
+    with pytest.raises(RuntimeError):
+        lin.update(recurrent_state=torch.zeros(1, 2, 4, 9), cache_kwargs={"op": "set"})
+    with pytest.raises(RuntimeError):
+        lin.update(conv_state=(torch.zeros(1, 9, 4), None, None), cache_kwargs={"op": "set"})
+
+
+def test_cache_container_and_demo_clone_protocol():
+    """inference_examples/demo_streaming_inference.py:111-160 deep-copies these attributes layer by layer."""
+    cfg = HybridTextConfig(num_hidden_layers=8, sliding_window=16)
+    cache = StaticCachePrealloc(config=cfg, batch_size=1, dtype=torch.bfloat16, zero_init=True)
+    assert len(cache.layers) == 8
+    assert [l.is_sliding for l in cache.layers] == [True, False, False, False, True, False, False, False]
+    total = sum(l._buf_keys.numel() * 2 for l in cache.layers if l.is_sliding) + \
+        sum(l.recurrent_state.numel() for l in cache.layers if not l.is_sliding)
+    assert total == 2 * 2 * 2 * 15 * 128 + 6 * 16 * 128 * 256
+    sw, lin = cache.layers[0], cache.layers[1]
+    for attr in ("_buf_keys", "_buf_values", "keys", "values", "size", "cumulative_length", "capacity", "sliding_window"):
+        assert hasattr(sw, attr)
+    for attr in ("recurrent_state", "conv_state_q", "conv_state_k", "conv_state_v", "seq_len", "start"):
+        assert hasattr(lin, attr)
+    k = torch.randn(1, 2, 5, 128).bfloat16()
+    fk, _ = cache.update(0, k, k)
+    assert fk.shape[-2] == 5 and cache.get_seq_length(0) == 5
+    # clone as the demo does: copy buffers, re-slice views, copy counters
+    clone = StaticCachePrealloc(config=cfg, batch_size=1, dtype=torch.bfloat16, zero_init=True)
+    src, dst = cache.layers[0], clone.layers[0]
+    dst._buf_keys.copy_(src._buf_keys); dst._buf_values.copy_(src._buf_values)
+    dst.size, dst.cumulative_length = src.size, src.cumulative_length
+    dst.keys, dst.values = dst._buf_keys[:, :, :dst.size, :], dst._buf_values[:, :, :dst.size, :]
+    k2 = torch.randn(1, 2, 1, 128).bfloat16()
+    a, _ = cache.update(0, k2, k2)
+    b, _ = clone.update(0, k2, k2)
+    assert torch.equal(a, b)
+    # full-config memory: 27 x (1 MiB + 64 KiB) + 9 x 8.4 MB in bf16 (SURVEY.md a-C3)
+    big = StaticCachePrealloc(config=HybridTextConfig(), batch_size=1, dtype=torch.bfloat16, device="meta")
+    nbytes = 0
+    for l in big.layers:
+        if l.is_sliding:
+            nbytes += 2 * l._buf_keys.numel() * 2
+        else:
+            nbytes += 2 * (l.recurrent_state.numel() + l.conv_state_q.numel() + l.conv_state_k.numel() + l.conv_state_v.numel())
+    assert nbytes == 27 * (16 * 128 * 256 * 2 + (2048 + 2048 + 4096) * 4 * 2) + 9 * 2 * 2 * 8191 * 128 * 2

@@ -1,0 +1,186 @@
+"""GPU parity tests of the element-wise kernels, the two mixers and one hybrid decoder block
+against the fp32 oracle (BASELINE.json config 1: [SWA, GDN, GDN, GDN] at the 3B dims, T = 1024)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import (SlidingWindowCacheRef, err_ratio, gdn_mixer_ref, hybrid_decoder_ref, mrope_apply_ref,
+                    mrope_cos_sin_ref, rmsnorm_gated_ref, short_conv_ref, swa_mixer_ref)
+from oracle.gdn import gdn_gate_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from infinitevl_b200 import modeling
+    return modeling
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ---------------------------------------------------------------- element-wise kernels ---------
+@pytest.mark.parametrize("T", [1, 3, 4, 50, 1000])
+@pytest.mark.parametrize("with_cache", [False, True])
+def test_short_conv(M, T, with_cache):
+    g = gen(T)
+    D = 2048
+    x = torch.randn(2, T, D, generator=g).bfloat16()
+    w = (torch.randn(D, 1, 4, generator=g) * 0.5).bfloat16()
+    cache = torch.randn(2, D, 4, generator=g).bfloat16() if with_cache else None
+    ry, rs = short_conv_ref(x, w, cache)
+    y, s = M.short_conv_silu(x.cuda(), w.cuda(), None if cache is None else cache.cuda(), output_final_state=True)
+    assert err_ratio(ry, y.float().cpu()) < 4e-3   # bf16 output rounding only
+    assert torch.equal(s.float().cpu(), rs)        # the carried tail is a copy of inputs: bit-exact
+
+
+def test_short_conv_streaming_equals_one_shot(M):
+    g = gen(7)
+    x = torch.randn(1, 300, 4096, generator=g).bfloat16().cuda()
+    w = (torch.randn(4096, 1, 4, generator=g) * 0.5).bfloat16().cuda()
+    y, s = M.short_conv_silu(x, w, None, output_final_state=True)
+    outs, c = [], None
+    for a, b in ((0, 257), (257, 258), (258, 259), (259, 300)):
+        yi, c = M.short_conv_silu(x[:, a:b], w, c, output_final_state=True)
+        outs.append(yi)
+    assert torch.equal(torch.cat(outs, 1), y) and torch.equal(c, s)
+
+
+def test_gates_and_gated_norm(M):
+    g = gen(3)
+    a = torch.randn(1, 500, 16, generator=g).bfloat16()
+    b = torch.randn(1, 500, 16, generator=g).bfloat16()
+    A_log = torch.log(torch.empty(16).uniform_(0.01, 16, generator=g))
+    dt_bias = torch.randn(16, generator=g)
+    rg, rb = gdn_gate_ref(a, b, A_log, dt_bias)
+    dg, db = M.gdn_gates(a.cuda(), b.cuda(), A_log.cuda(), dt_bias.cuda())
+    assert dg.dtype == torch.float32 and err_ratio(rg, dg.cpu()) < 1e-5
+    assert err_ratio(rb, db.float().cpu()) < 3e-3
+    o = torch.randn(700, 16, 256, generator=g).bfloat16()
+    gate = torch.randn(700, 16, 256, generator=g).bfloat16()
+    w = torch.rand(256, generator=g).bfloat16()
+    ref = rmsnorm_gated_ref(o, gate, w, eps=1e-5)
+    out = M.rmsnorm_gated(o.cuda(), gate.cuda(), w.cuda(), 1e-5)
+    assert err_ratio(ref, out.float().cpu()) < 4e-3
+
+
+def test_mrope_bit_exact(M):
+    g = gen(5)
+    T = 333
+    pos = torch.stack([torch.arange(T), torch.randint(0, 50, (T,), generator=g), torch.randint(0, 50, (T,), generator=g)])[:, None]
+    cos, sin = mrope_cos_sin_ref(pos, 128, 1e6, out_dtype=torch.bfloat16)
+    q = torch.randn(1, 16, T, 128, generator=g).bfloat16()
+    k = torch.randn(1, 2, T, 128, generator=g).bfloat16()
+    rq, rk = mrope_apply_ref(q, k, cos, sin, (16, 24, 24))
+    cm, sm = M.mrope_select(cos.cuda(), sin.cuda(), [16, 24, 24])
+    # strided [B,T,H,D] views of a [B,T,H*D] projection output, rotated in place
+    qp = q.transpose(1, 2).reshape(1, T, 16 * 128).contiguous().cuda()
+    kp = k.transpose(1, 2).reshape(1, T, 2 * 128).contiguous().cuda()
+    M.mrope_apply_(qp.view(1, T, 16, 128), cm, sm)
+    M.mrope_apply_(kp.view(1, T, 2, 128), cm, sm)
+    assert torch.equal(qp.view(1, T, 16, 128).transpose(1, 2).cpu(), rq)
+    assert torch.equal(kp.view(1, T, 2, 128).transpose(1, 2).cpu(), rk)
+
+
+# ---------------------------------------------------------------- mixers -----------------------
+def _init(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith("A_log"):
+                p.copy_(torch.log(torch.empty(p.shape).uniform_(0.01, 16, generator=g)))
+            elif name.endswith("dt_bias"):
+                dt = torch.exp(torch.empty(p.shape).uniform_(-6.9, -2.3, generator=g))
+                p.copy_(dt + torch.log(-torch.expm1(-dt)))
+            elif "norm" in name:
+                p.fill_(1.0)
+            elif "conv1d" in name:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    return module
+
+
+def _params(module):
+    return {k: v.detach().float().cpu() for k, v in module.state_dict().items()}
+
+
+def test_gated_deltanet_mixer_and_streaming(M):
+    cfg = M.HybridTextConfig(num_hidden_layers=4)
+    mod = _init(M.GatedDeltaNet(cfg, 1), 11).bfloat16().cuda()
+    p = _params(mod)
+    x = torch.randn(1, 700, 2048, generator=gen(12)).bfloat16()
+    ref, rconv, rstate = gdn_mixer_ref(x, p, proj_dtype=torch.bfloat16)
+    out, _ = mod(x.cuda())
+    assert err_ratio(ref, out.float().cpu()) < 1.5e-2
+    # streaming with the reference's cache protocol: 300-token prefill, a 200-token frame, then decode steps
+    cache = M.StaticCachePrealloc(config=cfg, batch_size=1, device="cuda", dtype=torch.bfloat16)
+    outs = []
+    for a, b in ((0, 300), (300, 500), (500, 501), (501, 502), (502, 700)):
+        y, _ = mod(x[:, a:b].cuda(), past_key_values=cache, cache_position=torch.arange(a, b, device="cuda"))
+        outs.append(y)
+    assert err_ratio(ref, torch.cat(outs, 1).float().cpu()) < 1.5e-2
+    lin = cache.layers[1]
+    assert lin.seq_len == 700 and lin.recurrent_state.dtype == torch.bfloat16
+    assert err_ratio(rstate, lin.recurrent_state.float().cpu()) < 1.5e-2
+    assert err_ratio(rconv[2], lin.conv_state_v.float().cpu()) < 1e-2
+
+
+def test_self_attention_mixer_with_cache(M):
+    cfg = M.HybridTextConfig(num_hidden_layers=4, sliding_window=256)
+    mod = _init(M.InfiniteVLSelfAttention(cfg, 0), 21).bfloat16().cuda()
+    p = _params(mod)
+    T = 600
+    x = torch.randn(1, T, 2048, generator=gen(22)).bfloat16()
+    pos = torch.arange(T)[None, None].expand(3, 1, -1)
+    cos, sin = mrope_cos_sin_ref(pos, 128, 1e6)
+    ref = swa_mixer_ref(x, p, cos, sin, cache=None, window=256)
+    cb, sb = cos.bfloat16().cuda(), sin.bfloat16().cuda()
+    out, _ = mod(x.cuda(), position_embeddings=(cb, sb))
+    assert err_ratio(ref, out.float().cpu()) < 1.5e-2
+    # chunked prefill + decode through the sliding-window cache
+    cache = M.StaticCachePrealloc(config=cfg, batch_size=1, device="cuda", dtype=torch.bfloat16)
+    rc = SlidingWindowCacheRef(256)
+    outs, refs = [], []
+    for a, b in ((0, 200), (200, 520), (520, 521), (521, 600)):
+        y, _ = mod(x[:, a:b].cuda(), past_key_values=cache, cache_position=torch.arange(a, b, device="cuda"),
+                   position_embeddings=(cb[:, :, a:b], sb[:, :, a:b]))
+        outs.append(y)
+        refs.append(swa_mixer_ref(x[:, a:b], p, cos[:, :, a:b], sin[:, :, a:b], cache=rc, window=256))
+        assert cache.layers[0].size == rc.size and cache.layers[0].cumulative_length == rc.cumulative_length
+    assert err_ratio(torch.cat(refs, 1), torch.cat(outs, 1).float().cpu()) < 1.5e-2
+    assert err_ratio(ref, torch.cat(outs, 1).float().cpu()) < 1.5e-2  # chunked == one-shot under the window rule
+
+
+def test_hybrid_block_config1(M):
+    """BASELINE.json config 1: one hybrid block (1 SWA + 3 GDN incl. norms and MLPs), T = 1024, 3B dims,
+    synthetic image+text M-RoPE positions; bf16 CUDA path vs fp32 CPU oracle with identical weights."""
+    cfg = M.HybridTextConfig(num_hidden_layers=4)
+    dec = _init(M.HybridDecoder(cfg), 31).bfloat16().cuda()
+    p = _params(dec)
+    T = 1024
+    # 16 text tokens, then 3 frames of 16x16 vision tokens each followed by 80 text tokens
+    t_ids, h_ids, w_ids, nxt = [], [], [], 0
+    def text(n):
+        nonlocal nxt
+        for _ in range(n):
+            t_ids.append(nxt); h_ids.append(nxt); w_ids.append(nxt); nxt += 1
+    text(16)
+    for f in range(3):
+        base = nxt
+        for hh in range(16):
+            for ww in range(16):
+                t_ids.append(base + 2 * f * 0); h_ids.append(base + hh); w_ids.append(base + ww)
+        nxt = base + 16
+        text(80)
+    pos = torch.tensor([t_ids, h_ids, w_ids])[:, None, :]
+    assert pos.shape == (3, 1, T)
+    x = torch.randn(1, T, 2048, generator=gen(32)).bfloat16()
+    ref = hybrid_decoder_ref(x, p, cfg.layer_types, pos, proj_dtype=torch.bfloat16)
+    out = dec(x.cuda(), position_ids=pos.cuda())
+    assert torch.isfinite(out).all()
+    assert err_ratio(ref, out.float().cpu()) < 2e-2
