@@ -103,6 +103,14 @@ IVL_API int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, 
                         const void* v, const int64_t* v_strides, void* o, const int64_t* o_strides, int B,
                         int Tq, int Tk, int Hq, int Hkv, int D, int window, float scale, void* stream);
 
+/* Decode step of the same attention: ONE new query token per sequence (Tq == 1) against the
+ * cached window, split over the key axis (HBM-bound).  q, o bf16 [B,1,Hq,128] contiguous; k, v as
+ * above.  workspace: ivl_swa_decode_workspace_bytes(B, Tk, Hq) bytes of fp32 scratch. */
+IVL_API size_t ivl_swa_decode_workspace_bytes(int B, int Tk, int Hq);
+IVL_API int ivl_swa_decode_fwd(const void* q, const void* k, const int64_t* k_strides, const void* v,
+                               const int64_t* v_strides, void* o, int B, int Tk, int Hq, int Hkv, int D,
+                               int window, float scale, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Element-wise pieces of the two mixers (each one coalesced streaming launch).
  * ---------------------------------------------------------------------------------- */

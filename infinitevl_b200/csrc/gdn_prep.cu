@@ -23,17 +23,17 @@ namespace ivl {
 
 namespace {
 
-constexpr int PREP_THREADS = 128;
+constexpr int PREP_THREADS = 256;  // 8 warps: warp w owns rows 16*(w>>1).. of the chunk and column half (w&1)
 constexpr int KH_LD = 136;  // bf16 elements per row: 272 B, rows shift by 16 B mod 128 -> conflict-free ldmatrix
 constexpr int V_LD = 264;
 constexpr int A_LD = 72;
-constexpr int LP_LD = 36;  // floats per row of one parity plane of L
+constexpr int LP_LD = 20;  // floats per row of one residue plane of L (16 used)
 
 struct __align__(16) PrepSmem {
   __nv_bfloat16 kh[64 * KH_LD];
   __nv_bfloat16 qh[64 * KH_LD];
   __nv_bfloat16 vb[64 * V_LD];
-  float Lp[2][64 * LP_LD + 4];  // L split by column parity: Lp[j & 1][i][j >> 1]
+  float Lp[4][64 * LP_LD + 4];  // L split by column residue: Lp[j & 3][i][j >> 2]; +4 staggers the planes' banks
   __nv_bfloat16 Aw[64 * A_LD];
   __nv_bfloat16 Au[64 * A_LD];
   float G[64];
@@ -63,22 +63,22 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
 }
 
-// Load 64 contiguous bf16 of one row half, L2-normalise over the full 128-wide row (the two
-// threads of a row combine their partial sums), round to bf16 (the reference's rounding point),
-// keep the rounded row in shared memory for the tensor-core products, and write the
-// exponentially weighted copy straight into its operand image in global memory.
-//   img_piece(p) returns the byte offset of 16-byte piece p (8 elements) of this thread's half row.
+// Load 32 contiguous bf16 (one quarter of a 128-wide row), L2-normalise over the full row (the four
+// threads of a row combine their partial sums), round to bf16 (the reference's rounding point), keep
+// the rounded row in shared memory for the tensor-core products, and write the exponentially
+// weighted copy straight into its operand image in global memory.
+//   img_piece(p) returns the byte offset of 16-byte piece p (8 elements) of this thread's quarter row.
 template <class PieceOffset>
-__device__ __forceinline__ void norm_row_half(const __nv_bfloat16* src, bool valid, bool l2norm,
-                                              float weight, __nv_bfloat16* smem_row, uint8_t* img,
-                                              PieceOffset img_piece) {
-  uint4 raw[8];
+__device__ __forceinline__ void norm_row_quarter(const __nv_bfloat16* src, bool valid, bool l2norm,
+                                                 float weight, __nv_bfloat16* smem_row, uint8_t* img,
+                                                 PieceOffset img_piece) {
+  uint4 raw[4];
 #pragma unroll
-  for (int p = 0; p < 8; ++p)
+  for (int p = 0; p < 4; ++p)
     raw[p] = valid ? __ldg(reinterpret_cast<const uint4*>(src) + p) : make_uint4(0, 0, 0, 0);
   float ss = 0.f;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) {
+  for (int p = 0; p < 4; ++p) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[p]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -87,9 +87,10 @@ __device__ __forceinline__ void norm_row_half(const __nv_bfloat16* src, bool val
     }
   }
   ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
   const float rstd = l2norm ? 1.0f / sqrtf(ss + 1e-6f) : 1.0f;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) {
+  for (int p = 0; p < 4; ++p) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[p]);
     uint4 nrm, wgt;
     uint32_t* n = reinterpret_cast<uint32_t*>(&nrm);
@@ -130,7 +131,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = tid; i < 2 * (64 * LP_LD + 4); i += PREP_THREADS) (&s.Lp[0][0])[i] = 0.f;
+  for (int i = tid; i < 4 * (64 * LP_LD + 4); i += PREP_THREADS) (&s.Lp[0][0])[i] = 0.f;
   if (warp == 0) {
     float g0 = (lane < valid) ? g[(tok0 + lane) * H + h] : 0.f;
     float g1 = (lane + 32 < valid) ? g[(tok0 + lane + 32) * H + h] : 0.f;
@@ -149,32 +150,34 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
 
   // ---- stage 1: normalise q, k rows; emit Qg and Kt images --------------------------------
   {
-    const int row = tid >> 1, half = tid & 1;
+    const int row = tid >> 2, qt = tid & 3;  // 4 threads per row, 32 elements each
     const bool ok = row < valid;
     const float Gr = s.G[row], Gc = s.G[63];
-    const size_t off = ((tok0 + row) * H + h) * GDN_K + half * 64;
+    const size_t off = ((tok0 + row) * H + h) * GDN_K + qt * 32;
     const int R = 64 + row;  // Qg occupies rows 64..127 of the stacked [-Wg ; Qg] operand
-    norm_row_half(q + off, ok, l2norm != 0, __expf(Gr) * scale, &s.qh[row * KH_LD + half * 64],
-                  blob + BLOB_OFF_A1, [&](int p) {
-                    return (uint32_t)((R >> 3) * 2048 + (half * 8 + p) * 128 + (R & 7) * 16);
-                  });
-    norm_row_half(k + off, ok, l2norm != 0, __expf(Gc - Gr), &s.kh[row * KH_LD + half * 64],
-                  blob + BLOB_OFF_KT, [&](int p) {
-                    return (uint32_t)((half * 8 + p) * 1024 + (row >> 3) * 128 + (row & 7) * 16);
-                  });
+    norm_row_quarter(q + off, ok, l2norm != 0, __expf(Gr) * scale, &s.qh[row * KH_LD + qt * 32],
+                     blob + BLOB_OFF_A1, [&](int p) {
+                       return (uint32_t)((R >> 3) * 2048 + (qt * 4 + p) * 128 + (R & 7) * 16);
+                     });
+    norm_row_quarter(k + off, ok, l2norm != 0, __expf(Gc - Gr), &s.kh[row * KH_LD + qt * 32],
+                     blob + BLOB_OFF_KT, [&](int p) {
+                       return (uint32_t)((qt * 4 + p) * 1024 + (row >> 3) * 128 + (row & 7) * 16);
+                     });
     if (tid == 0) ws.gamma[ch] = __expf(Gc);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates
-  const int r0 = warp * 16;                 // this warp's 16-row strip
+  const int strip = warp >> 1, half = warp & 1;
+  const int r0 = strip * 16;                // this warp's 16-row strip
 
   // ---- stage 2: Kn Kn^T and Qn Kn^T (lower triangle only) -> L (fp32, smem), P image -------
+  // warp (strip, half) computes column tiles 4*half .. 4*half+3 (32 key columns)
   {
-    float ckk[8][4], cqk[8][4];
+    float ckk[4][4], cqk[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) ckk[i][e] = cqk[i][e] = 0.f;
 #pragma unroll
@@ -184,37 +187,39 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       ldsm_x4(smem_u32(&s.kh[arow * KH_LD + acol]), ak[0], ak[1], ak[2], ak[3]);
       ldsm_x4(smem_u32(&s.qh[arow * KH_LD + acol]), aq[0], aq[1], aq[2], aq[3]);
 #pragma unroll
-      for (int ntp = 0; ntp < 4; ++ntp) {
-        if (ntp <= warp) {  // column tiles right of the diagonal are never needed
+      for (int pp = 0; pp < 2; ++pp) {
+        const int ntp = half * 2 + pp;  // pair of 8-column tiles
+        if (ntp <= strip) {             // column tiles right of the diagonal are never needed
           uint32_t b0, b1, b2, b3;
           const int n = ntp * 16 + (lane & 7) + (lane >> 4) * 8, kk = ks * 16 + ((lane >> 3) & 1) * 8;
           ldsm_x4(smem_u32(&s.kh[n * KH_LD + kk]), b0, b1, b2, b3);
-          mma16816(ckk[2 * ntp], ak, b0, b1);
-          mma16816(ckk[2 * ntp + 1], ak, b2, b3);
-          mma16816(cqk[2 * ntp], aq, b0, b1);
-          mma16816(cqk[2 * ntp + 1], aq, b2, b3);
+          mma16816(ckk[2 * pp], ak, b0, b1);
+          mma16816(ckk[2 * pp + 1], ak, b2, b3);
+          mma16816(cqk[2 * pp], aq, b0, b1);
+          mma16816(cqk[2 * pp + 1], aq, b2, b3);
         }
       }
     }
     const int i0 = r0 + gq, i1 = i0 + 8;
     const float G0 = s.G[i0], G1 = s.G[i1], be0 = s.beta[i0], be1 = s.beta[i1];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int lt = 0; lt < 4; ++lt) {
+      const int nt = half * 4 + lt;
       const int j0 = nt * 8 + 2 * tq, j1 = j0 + 1;
       float p00 = 0.f, p01 = 0.f, p10 = 0.f, p11 = 0.f;
-      if (nt <= 2 * warp + 1) {
+      if (nt <= 2 * strip + 1) {
         const float Gj0 = s.G[j0], Gj1 = s.G[j1];
         const float e00 = __expf(fminf(G0 - Gj0, 0.f)), e01 = __expf(fminf(G0 - Gj1, 0.f));
         const float e10 = __expf(fminf(G1 - Gj0, 0.f)), e11 = __expf(fminf(G1 - Gj1, 0.f));
         // strictly-lower entries of L; entries on/above the diagonal stay zero
-        if (i0 > j0) s.Lp[0][i0 * LP_LD + (j0 >> 1)] = be0 * ckk[nt][0] * e00;
-        if (i0 > j1) s.Lp[1][i0 * LP_LD + (j1 >> 1)] = be0 * ckk[nt][1] * e01;
-        if (i1 > j0) s.Lp[0][i1 * LP_LD + (j0 >> 1)] = be1 * ckk[nt][2] * e10;
-        if (i1 > j1) s.Lp[1][i1 * LP_LD + (j1 >> 1)] = be1 * ckk[nt][3] * e11;
-        p00 = (i0 >= j0) ? cqk[nt][0] * e00 * scale : 0.f;
-        p01 = (i0 >= j1) ? cqk[nt][1] * e01 * scale : 0.f;
-        p10 = (i1 >= j0) ? cqk[nt][2] * e10 * scale : 0.f;
-        p11 = (i1 >= j1) ? cqk[nt][3] * e11 * scale : 0.f;
+        if (i0 > j0) s.Lp[j0 & 3][i0 * LP_LD + (j0 >> 2)] = be0 * ckk[lt][0] * e00;
+        if (i0 > j1) s.Lp[j1 & 3][i0 * LP_LD + (j1 >> 2)] = be0 * ckk[lt][1] * e01;
+        if (i1 > j0) s.Lp[j0 & 3][i1 * LP_LD + (j0 >> 2)] = be1 * ckk[lt][2] * e10;
+        if (i1 > j1) s.Lp[j1 & 3][i1 * LP_LD + (j1 >> 2)] = be1 * ckk[lt][3] * e11;
+        p00 = (i0 >= j0) ? cqk[lt][0] * e00 * scale : 0.f;
+        p01 = (i0 >= j1) ? cqk[lt][1] * e01 * scale : 0.f;
+        p10 = (i1 >= j0) ? cqk[lt][2] * e10 * scale : 0.f;
+        p11 = (i1 >= j1) ? cqk[lt][3] * e11 * scale : 0.f;
       }
       uint8_t* pimg = blob + BLOB_OFF_P + nt * 128 + tq * 4;
       *reinterpret_cast<uint32_t*>(pimg + (i0 >> 3) * 1024 + (i0 & 7) * 16) = pack_bf16(p00, p01);
@@ -223,35 +228,37 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   }
   __syncthreads();
 
-  // ---- stage 3: T = (I + L)^-1 by forward substitution, one column per thread pair --------
-  // Thread (col, par) keeps the entries T[i][col] with i of parity `par` and accumulates the
-  // products over columns j of parity `par`; the pair exchanges its partial sums by shuffle.
+  // ---- stage 3: T = (I + L)^-1 by forward substitution, one column per thread quad ---------
+  // Thread (col, res) keeps the entries T[i][col] with i % 4 == res and accumulates the products
+  // over columns j with j % 4 == res; the quad combines its partial sums by shuffle.
   {
-    const int col = tid >> 1, par = tid & 1;
-    const float* Lrow = &s.Lp[par][0];
-    float x[32];
+    const int col = tid >> 2, res = tid & 3;
+    const float* Lrow = &s.Lp[res][0];
+    float x[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = 0.f;
+    for (int i = 0; i < 16; ++i) x[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
-      float acc = 0.f;
-      const int n = (i + 1) >> 1;  // own-parity columns below the diagonal (rounded up; extras are zero)
+      float acc0 = 0.f, acc1 = 0.f;
+      const int n = (i + 3) >> 2;  // own-residue columns below the diagonal (rounded up; extras are zero)
 #pragma unroll
       for (int j4 = 0; j4 < (n + 3) / 4; ++j4) {
         const float4 l4 = *reinterpret_cast<const float4*>(&Lrow[i * LP_LD + j4 * 4]);
-        acc = fmaf(l4.x, x[j4 * 4 + 0], acc);
-        if (j4 * 4 + 1 < n) acc = fmaf(l4.y, x[j4 * 4 + 1], acc);
-        if (j4 * 4 + 2 < n) acc = fmaf(l4.z, x[j4 * 4 + 2], acc);
-        if (j4 * 4 + 3 < n) acc = fmaf(l4.w, x[j4 * 4 + 3], acc);
+        acc0 = fmaf(l4.x, x[j4 * 4 + 0], acc0);
+        if (j4 * 4 + 1 < n) acc1 = fmaf(l4.y, x[j4 * 4 + 1], acc1);
+        if (j4 * 4 + 2 < n) acc0 = fmaf(l4.z, x[j4 * 4 + 2], acc0);
+        if (j4 * 4 + 3 < n) acc1 = fmaf(l4.w, x[j4 * 4 + 3], acc1);
       }
+      float acc = acc0 + acc1;
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       const float xi = ((i == col) ? 1.f : 0.f) - acc;
-      if ((i & 1) == par) x[i >> 1] = xi;
+      if ((i & 3) == res) x[i >> 2] = xi;
     }
     const float bu = s.beta[col], bw = bu * __expf(s.G[col]);
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-      const int i = 2 * jj + par;
+    for (int jj = 0; jj < 16; ++jj) {
+      const int i = 4 * jj + res;
       s.Aw[i * A_LD + col] = __float2bfloat16(x[jj] * bw);
       s.Au[i * A_LD + col] = __float2bfloat16(x[jj] * bu);
     }
@@ -259,61 +266,64 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   __syncthreads();
 
   // ---- stage 4: Wg = Aw Kn (negated, into rows 0..63 of the A1 image), U = Au V ------------
+  // warp (strip, half): key dims 64*half..+63 of Wg, value columns 128*half..+127 of U
   {
     const int i0 = r0 + gq, i1 = i0 + 8;
-    float acc[16][4];
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      if (ks <= warp) {  // T is lower triangular
+      if (ks <= strip) {  // T is lower triangular
         uint32_t a[4];
         ldsm_x4(smem_u32(&s.Aw[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
         const int kk = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-        for (int ntp = 0; ntp < 8; ++ntp) {
+        for (int ntp = 0; ntp < 4; ++ntp) {
           uint32_t b0, b1, b2, b3;
-          ldsm_x4_t(smem_u32(&s.kh[kk * KH_LD + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
+          ldsm_x4_t(smem_u32(&s.kh[kk * KH_LD + half * 64 + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
           mma16816(acc[2 * ntp], a, b0, b1);
           mma16816(acc[2 * ntp + 1], a, b2, b3);
         }
       }
     }
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
+    for (int lt = 0; lt < 8; ++lt) {
+      const int nt = half * 8 + lt;
       uint8_t* img = blob + BLOB_OFF_A1 + nt * 128 + tq * 4;
-      *reinterpret_cast<uint32_t*>(img + (i0 >> 3) * 2048 + (i0 & 7) * 16) = pack_bf16(-acc[nt][0], -acc[nt][1]);
-      *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(-acc[nt][2], -acc[nt][3]);
+      *reinterpret_cast<uint32_t*>(img + (i0 >> 3) * 2048 + (i0 & 7) * 16) = pack_bf16(-acc[lt][0], -acc[lt][1]);
+      *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(-acc[lt][2], -acc[lt][3]);
     }
 #pragma unroll
-    for (int hv = 0; hv < 2; ++hv) {  // two halves of 128 value columns
+    for (int hv = 0; hv < 2; ++hv) {  // two passes of 64 value columns
+      const int vbase = half * 128 + hv * 64;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        if (ks <= warp) {
+        if (ks <= strip) {
           uint32_t a[4];
           ldsm_x4(smem_u32(&s.Au[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
           const int kk = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-          for (int ntp = 0; ntp < 8; ++ntp) {
+          for (int ntp = 0; ntp < 4; ++ntp) {
             uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(smem_u32(&s.vb[kk * V_LD + hv * 128 + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
+            ldsm_x4_t(smem_u32(&s.vb[kk * V_LD + vbase + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
             mma16816(acc[2 * ntp], a, b0, b1);
             mma16816(acc[2 * ntp + 1], a, b2, b3);
           }
         }
       }
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt) {
-        const int colbase = hv * 128 + nt * 8;  // first of the 8 value columns of this tile
+      for (int lt = 0; lt < 8; ++lt) {
+        const int colbase = vbase + lt * 8;  // first of the 8 value columns of this tile
         uint8_t* img = ublob + (colbase >> 5) * UBLOB_BYTES + ((colbase & 31) >> 3) * 1024 + tq * 4;
-        *reinterpret_cast<uint32_t*>(img + i0 * 16) = pack_bf16(acc[nt][0], acc[nt][1]);
-        *reinterpret_cast<uint32_t*>(img + i1 * 16) = pack_bf16(acc[nt][2], acc[nt][3]);
+        *reinterpret_cast<uint32_t*>(img + i0 * 16) = pack_bf16(acc[lt][0], acc[lt][1]);
+        *reinterpret_cast<uint32_t*>(img + i1 * 16) = pack_bf16(acc[lt][2], acc[lt][3]);
       }
     }
   }

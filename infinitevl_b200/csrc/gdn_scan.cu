@@ -45,10 +45,22 @@ constexpr uint32_t TM_D1 = 0;    // two accumulators of 32 columns
 constexpr uint32_t TM_S = 64;    // state, 32 columns
 constexpr uint32_t TM_COLS = 128;
 
+// Developer-only timeline probe (compiled in with -DIVL_TRACE by tools/trace_scan.py; never in the product build)
+#ifdef IVL_TRACE
+__device__ long long ivl_trace_buf[64 * 16];
+#define TR(slot)                                                                                         \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && c >= 1000 && c < 1064)                        \
+      ivl_trace_buf[(c - 1000) * 16 + (slot)] = clock64();                                               \
+  } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
+
 struct Bars {
   uint64_t full[STAGES], empty[STAGES];
-  uint64_t a[2], o[2], d1free[2];
-  uint64_t vn, s, sready;
+  uint64_t a[2], o[2];
+  uint64_t vnst, s, sb;
   uint32_t tmem_base;
 };
 
@@ -79,10 +91,16 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.a[i], 1); mbar_init(&bars.o[i], 1); mbar_init(&bars.d1free[i], 64); }
-    mbar_init(&bars.vn, 64);
+    // epilogue warps arrive once per warp (lane 0 after __syncwarp)
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars.a[i], 1); mbar_init(&bars.o[i], 1); }
     mbar_init(&bars.s, 1);
-    mbar_init(&bars.sready, 128);
+    // sb   (4 warps): bf16 shadow of S_c in shared memory + stage c landed  -> MMA-A(c) may be issued.
+    //                 The O warps arrive here only after they finished reading D1 of chunk c-2, so the
+    //                 accumulator buffer MMA-A(c) overwrites is free without a separate barrier.
+    // vnst (2 + 4):   v_new(c) in shared memory (2 VN warps) and gamma_c S_c back in TMEM (4 warps)
+    //                 -> MMA-B(c) / MMA-C(c) may be issued.
+    mbar_init(&bars.sb, 4);
+    mbar_init(&bars.vnst, 6);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TM_COLS>(&bars.tmem_base);
@@ -101,51 +119,47 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
     for (int c = 0; c < NT; ++c) {
       const int s = c % STAGES, it = c / STAGES;
       if (c >= STAGES) mbar_wait(&bars.empty[s], (it - 1) & 1);
-      if (lane == 0) {
-        uint8_t* st = smem + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&bars.full[s], BLOB_BYTES + UBLOB_BYTES);
-        bulk_g2s(st + ST_OFF_BLOB, blob + (size_t)c * BLOB_BYTES, BLOB_BYTES, &bars.full[s]);
-        bulk_g2s(st + ST_OFF_U, ublob + (size_t)c * (GDN_NS * UBLOB_BYTES), UBLOB_BYTES, &bars.full[s]);
-      }
-      __syncwarp();
+      uint8_t* st = smem + s * STAGE_BYTES;
+      mbar_arrive_expect_tx_ws(&bars.full[s], BLOB_BYTES + UBLOB_BYTES);
+      bulk_g2s_ws(st + ST_OFF_BLOB, blob + (size_t)c * BLOB_BYTES, BLOB_BYTES, &bars.full[s]);
+      bulk_g2s_ws(st + ST_OFF_U, ublob + (size_t)c * (GDN_NS * UBLOB_BYTES), UBLOB_BYTES, &bars.full[s]);
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------------
+    // All 32 lanes run this code converged; the elected lane issues (umma_*_ws), so the operands stay in
+    // uniform registers.  Two barrier waits per chunk.
     {
       constexpr uint32_t idescA = umma_idesc_bf16(128, GDN_BV, /*a_mn=*/0, /*b_mn=*/1);
       constexpr uint32_t idescB = umma_idesc_bf16(128, GDN_BV, /*a_mn=*/1, /*b_mn=*/1);
       const uint32_t sbase = smem_u32(smem);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint64_t dSb = umma_desc(sbase + OFF_SB, 128, 2048, SWZ_NONE);
       const uint64_t dVn = umma_desc(sbase + OFF_VN, 128, 1024, SWZ_NONE);
       for (int c = 0; c < NT; ++c) {
-        const int s = c % STAGES, it = c / STAGES, buf = c & 1;
+        const int s = c % STAGES, buf = c & 1;
         const uint32_t st = sbase + s * STAGE_BYTES;
         const uint64_t dA1 = umma_desc(st + ST_OFF_A1, 128, 2048, SWZ_NONE);
         const uint64_t dKt = umma_desc(st + ST_OFF_KT, 128, 1024, SWZ_NONE);
         const uint64_t dP = umma_desc(st + ST_OFF_P, 128, 1024, SWZ_NONE);
-        const uint32_t d1 = tmem + TM_D1 + buf * GDN_BV;
-        mbar_wait(&bars.full[s], it & 1);
-        mbar_wait(&bars.sready, c & 1);
-        if (c >= 2) mbar_wait(&bars.d1free[buf], ((c >> 1) - 1) & 1);
+        const uint32_t d1 = tm + TM_D1 + buf * GDN_BV;
+        mbar_wait(&bars.sb, c & 1);
         tc_fence_after();
-        if (lane == 0) {
+        TR(0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) umma_bf16(d1, dA1 + j * 16, dSb + j * 16, idescA, j > 0);
-          umma_commit(&bars.a[buf]);
-        }
-        __syncwarp();
-        mbar_wait(&bars.vn, c & 1);
+        for (int j = 0; j < 8; ++j) umma_bf16_ws(d1, dA1 + j * 16, dSb + j * 16, idescA, j > 0);
+        umma_commit_ws(&bars.a[buf]);
+        TR(1);
+        mbar_wait(&bars.vnst, c & 1);
         tc_fence_after();
-        if (lane == 0) {
+        TR(3);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) umma_bf16(tmem + TM_S, dKt + j * 16, dVn + j * 16, idescB, 1);
-          umma_commit(&bars.s);
+        for (int j = 0; j < 4; ++j) umma_bf16_ws(tm + TM_S, dKt + j * 16, dVn + j * 16, idescB, 1);
+        umma_commit_ws(&bars.s);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) umma_bf16(d1, dP + j * 16, dVn + j * 16, idescA, 1);
-          umma_commit(&bars.o[buf]);
-          umma_commit(&bars.empty[s]);
-        }
-        __syncwarp();
+        for (int j = 0; j < 4; ++j) umma_bf16_ws(d1, dP + j * 16, dVn + j * 16, idescA, 1);
+        umma_commit_ws(&bars.o[buf]);
+        umma_commit_ws(&bars.empty[s]);
+        TR(4);
       }
     }
   } else {
@@ -184,30 +198,35 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
         }
       }
       store_row_bf16(sb_dst, 2048, x);
+      fence_async_smem();
+      mbar_wait(&bars.full[0], 0);  // the epilogue warps vouch for the stage on behalf of the MMA warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.sb);
       const float g0 = __ldg(gamma);
 #pragma unroll
       for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(x[i] * g0);
       tmem_st32(tlane + TM_S, r);
       tmem_st_wait();
-      fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bars.sready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.vnst);
     }
 
     for (int c = 0; c < NT; ++c) {
-      const int s = c % STAGES, it = c / STAGES, buf = c & 1;
+      const int s = c % STAGES, buf = c & 1;
       const float gnext = (c + 1 < NT) ? __ldg(gamma + c + 1) : 1.f;
       if (is_vn) {
         // v_new = U - Wg S   (A1 holds -Wg, so the accumulator is added)
-        const uint8_t* usrc = smem + s * STAGE_BYTES + ST_OFF_U + tok * 16;
-        mbar_wait(&bars.full[s], it & 1);
+        const uint8_t* usrc = smem + s * STAGE_BYTES + ST_OFF_U + tok * 16;  // stage c was awaited in the S hand-over of c-1
         uint4 u[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) u[p] = *reinterpret_cast<const uint4*>(usrc + p * 1024);
         mbar_wait(&bars.a[buf], (c >> 1) & 1);
         tc_fence_after();
+        if (quad == 0) TR(5);
         tmem_ld32(tlane + TM_D1 + buf * GDN_BV, r);
         tmem_ld_wait();
+        if (quad == 0) TR(6);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const uint32_t* w = reinterpret_cast<const uint32_t*>(&u[p]);
@@ -220,24 +239,35 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
         store_row_bf16(vn_dst, 1024, x);
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(&bars.vn);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.vnst);
+        if (quad == 0) TR(7);
       }
-      // state hand-over: S_{c+1} is complete once MMA-B has retired
+      // state hand-over: S_{c+1} is complete once MMA-B has retired.  While waiting for it, make sure the
+      // next chunk's operands have landed (off the critical path here, and it spares the MMA warp a wait).
+      if (c + 1 < NT) mbar_wait(&bars.full[(c + 1) % STAGES], ((c + 1) / STAGES) & 1);
       mbar_wait(&bars.s, c & 1);
       tc_fence_after();
+      if (quad == 0) TR(8);
       tmem_ld32(tlane + TM_S, r);
       tmem_ld_wait();
+      if (quad == 0) TR(9);
       if (c + 1 < NT) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]);
         store_row_bf16(sb_dst, 2048, x);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.sb);   // MMA-A of the next chunk may start
+        if (quad == 0) TR(10);
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(x[i] * gnext);
         tmem_st32(tlane + TM_S, r);
         tmem_st_wait();
-        fence_async_smem();
         tc_fence_before();
-        mbar_arrive(&bars.sready);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.vnst); // MMA-B of the next chunk may accumulate
+        if (quad == 0) TR(11);
       } else if (ht != nullptr) {
         const size_t soff = (((size_t)b * H + h) * GDN_K + row) * GDN_V + slice * GDN_BV;
         if (ht_dtype == 0) {
@@ -256,10 +286,9 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
         // output rows: O = Qg S + P Vn (scale and exp(G) are folded into Qg and P)
         mbar_wait(&bars.o[buf], (c >> 1) & 1);
         tc_fence_after();
+        if (quad == 2) TR(12);
         tmem_ld32(tlane + TM_D1 + buf * GDN_BV, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&bars.d1free[buf]);
+        tmem_ld_wait();  // D1[buf] is free again once this warp's next sb arrival is observed by the MMA warp
         const int t = c * GDN_C + tok;
         if (t < T) {
 #pragma unroll
@@ -289,5 +318,11 @@ cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const void* h0, int h0_dtype
                                                              ht_dtype, T, H, gdn_num_chunks(T));
   return cudaGetLastError();
 }
+
+#ifdef IVL_TRACE
+extern "C" __attribute__((visibility("default"))) int ivl_debug_read_trace(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, ivl_trace_buf, sizeof(long long) * n);
+}
+#endif
 
 }  // namespace ivl

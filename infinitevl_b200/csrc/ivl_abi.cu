@@ -23,6 +23,10 @@ cudaError_t launch_gdn_gate(const void* a, const void* b, const float* A_log, co
                             void* beta, long long n, int H, cudaStream_t stream);
 cudaError_t launch_rmsnorm_gated(const void* x, const void* gate, const void* w, void* y, long long rows, float eps,
                                  cudaStream_t stream);
+size_t swa_decode_workspace_bytes(int B, int Tk, int Hq);
+cudaError_t launch_swa_decode(const void* q, const void* k, const long long* ks, const void* v, const long long* vs,
+                              void* o, int B, int Tk, int Hq, int Hkv, int window, float scale, void* workspace,
+                              cudaStream_t stream);
 cudaError_t launch_mrope(void* x, const long long* xs, const void* cosr, const void* sinr, int B, int T, int Hn,
                          cudaStream_t stream);
 }  // namespace ivl
@@ -121,6 +125,29 @@ int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const in
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
   cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, B, Tq, Tk, Hq, Hkv, window, sc,
                                       static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+size_t ivl_swa_decode_workspace_bytes(int B, int Tk, int Hq) {
+  if (B <= 0 || Tk <= 0 || Hq <= 0) return 0;
+  return ivl::swa_decode_workspace_bytes(B, Tk, Hq);
+}
+
+int ivl_swa_decode_fwd(const void* q, const void* k, const int64_t* k_strides, const void* v, const int64_t* v_strides,
+                       void* o, int B, int Tk, int Hq, int Hkv, int D, int window, float scale, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (B <= 0 || Tk <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 8 || D != 128 || B > 65535)
+    return IVL_ERR_BAD_SHAPE;
+  if (!q || !k || !v || !o || !k_strides || !v_strides || !workspace) return IVL_ERR_NULL;
+  if (workspace_bytes < ivl::swa_decode_workspace_bytes(B, Tk, Hq)) return IVL_ERR_WORKSPACE;
+  long long ks[3], vs[3];
+  for (int i = 0; i < 3; ++i) {
+    ks[i] = k_strides[i]; vs[i] = v_strides[i];
+    if ((ks[i] | vs[i]) & 7) return IVL_ERR_BAD_SHAPE;
+  }
+  const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  cudaError_t e = ivl::launch_swa_decode(q, k, ks, v, vs, o, B, Tk, Hq, Hkv, window, sc, workspace,
+                                         static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 

@@ -72,9 +72,9 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1);
-      mbar_init(&bars.s[i], 1); mbar_init(&bars.sfree[i], 128);
+      mbar_init(&bars.s[i], 1); mbar_init(&bars.sfree[i], 4);
     }
-    mbar_init(&bars.q, 1); mbar_init(&bars.p, 128); mbar_init(&bars.pv, 1);
+    mbar_init(&bars.q, 1); mbar_init(&bars.p, 4); mbar_init(&bars.pv, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
@@ -86,31 +86,28 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (warp == 0) {
     // ---------------------------------- TMA producer ------------------------------------
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars.q, Q_BYTES);
-      tma_load_4d(smem + OFF_Q, &tmQ, 0, h, i0, b, &bars.q);
-      tma_load_4d(smem + OFF_Q + Q_BYTES / 2, &tmQ, 64, h, i0, b, &bars.q);
-    }
+    mbar_arrive_expect_tx_ws(&bars.q, Q_BYTES);
+    tma_load_4d_ws(smem + OFF_Q, &tmQ, 0, h, i0, b, &bars.q);
+    tma_load_4d_ws(smem + OFF_Q + Q_BYTES / 2, &tmQ, 64, h, i0, b, &bars.q);
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t & 1;
       if (t >= 2) mbar_wait(&bars.empty[s], ((t >> 1) - 1) & 1);
-      if (lane == 0) {
-        const int j0 = (t_lo + t) * BN;
-        uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
-        uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
-        mbar_arrive_expect_tx(&bars.full[s], 2 * KT_BYTES_);
-        tma_load_4d(kd, &tmK, 0, hk, j0, b, &bars.full[s]);
-        tma_load_4d(kd + KT_BYTES_ / 2, &tmK, 64, hk, j0, b, &bars.full[s]);
-        tma_load_4d(vd, &tmV, 0, hk, j0, b, &bars.full[s]);
-        tma_load_4d(vd + KT_BYTES_ / 2, &tmV, 64, hk, j0, b, &bars.full[s]);
-      }
-      __syncwarp();
+      const int j0 = (t_lo + t) * BN;
+      uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
+      uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
+      mbar_arrive_expect_tx_ws(&bars.full[s], 2 * KT_BYTES_);
+      tma_load_4d_ws(kd, &tmK, 0, hk, j0, b, &bars.full[s]);
+      tma_load_4d_ws(kd + KT_BYTES_ / 2, &tmK, 64, hk, j0, b, &bars.full[s]);
+      tma_load_4d_ws(vd, &tmV, 0, hk, j0, b, &bars.full[s]);
+      tma_load_4d_ws(vd + KT_BYTES_ / 2, &tmV, 64, hk, j0, b, &bars.full[s]);
     }
   } else if (warp == 1) {
     // ---------------------------------- MMA issuer --------------------------------------
+    // All 32 lanes run converged; the elected lane issues (umma_*_ws) so descriptors stay in uniform registers.
     constexpr uint32_t idescS = umma_idesc_bf16(BM, BN, 0, 0);
     constexpr uint32_t idescO = umma_idesc_bf16(BM, HD, 0, 1);
     const uint32_t sb = smem_u32(smem);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint64_t dQ = umma_desc(sb + OFF_Q, 16, 1024, SWZ_128B);
     const uint64_t dP = umma_desc(sb + OFF_P, 128, 1024, SWZ_NONE);
     auto issue_s = [&](int t) {
@@ -120,37 +117,34 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int j = 0; j < 8; ++j) {
         const uint32_t qoff = ((j >> 2) * (Q_BYTES / 2) + (j & 3) * 32) >> 4;
         const uint32_t koff = ((j >> 2) * (KT_BYTES_ / 2) + (j & 3) * 32) >> 4;
-        umma_bf16(tmem + TM_S + s * BN, dQ + qoff, dK + koff, idescS, j > 0);
+        umma_bf16_ws(tm + TM_S + s * BN, dQ + qoff, dK + koff, idescS, j > 0);
       }
-      umma_commit(&bars.s[s]);
+      umma_commit_ws(&bars.s[s]);
     };
     mbar_wait(&bars.q, 0);
     mbar_wait(&bars.full[0], 0);
     tc_fence_after();
-    if (lane == 0) issue_s(0);
-    __syncwarp();
+    issue_s(0);
     for (int t = 0; t < n_tiles; ++t) {
       if (t + 1 < n_tiles) {
         const int s1 = (t + 1) & 1;
         mbar_wait(&bars.full[s1], ((t + 1) >> 1) & 1);
         if (t + 1 >= 2) mbar_wait(&bars.sfree[s1], (((t + 1) >> 1) - 1) & 1);
         tc_fence_after();
-        if (lane == 0) issue_s(t + 1);
-        __syncwarp();
+        issue_s(t + 1);
       }
       mbar_wait(&bars.p, t & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const int s = t & 1;
         // V tile: MN-major (d contiguous), two 64-wide d panels 8 KiB apart, 8-key groups 1 KiB apart
         const uint64_t dV = umma_desc(sb + OFF_V + s * KT_BYTES_, KT_BYTES_ / 2, 1024, SWZ_128B);
 #pragma unroll
         for (int j = 0; j < BN / 16; ++j)
-          umma_bf16(tmem + TM_O, dP + j * 16, dV + j * 128, idescO, (t > 0 || j > 0) ? 1u : 0u);
-        umma_commit(&bars.pv);
-        umma_commit(&bars.empty[s]);
+          umma_bf16_ws(tm + TM_O, dP + j * 16, dV + j * 128, idescO, (t > 0 || j > 0) ? 1u : 0u);
+        umma_commit_ws(&bars.pv);
+        umma_commit_ws(&bars.empty[s]);
       }
-      __syncwarp();
     }
   } else {
     // ---------------------------------- softmax / epilogue ------------------------------
@@ -176,7 +170,8 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[32 + i] = __uint_as_float(r[i]) * a.scale_log2;
       tc_fence_before();
-      mbar_arrive(&bars.sfree[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.sfree[s]);
       // masks only on boundary tiles (CTA-uniform test)
       const bool need_mask = (j0 + BN - 1 > p_first) || (a.window > 0 && j0 < p_last - a.window + 1) ||
                              (j0 + BN > a.Tk);
@@ -231,7 +226,8 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&bars.p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.p);
     }
     // epilogue: O / l -> bf16 -> global
     mbar_wait(&bars.pv, (n_tiles - 1) & 1);

@@ -15,6 +15,9 @@ import torch
 from . import _lib
 
 
+_decode_ws: dict = {}
+
+
 def _strides3(t: torch.Tensor):
     """(batch, time, head) element strides of a [B, T, H, D] view as a ctypes int64[3]."""
     assert t.stride(3) == 1, "innermost (head_dim) axis must be contiguous"
@@ -37,6 +40,20 @@ def swa_attention_bthd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window
     if out is None:
         out = torch.empty(B, Tq, Hq, D, dtype=torch.bfloat16, device=q.device)
     lib = _lib.load()
+    if Tq == 1 and Hq // Hkv <= 8 and out.is_contiguous():
+        # decode step: split-KV kernel (HBM-bound) instead of the tensor-core prefill kernel
+        q = q.contiguous()
+        need = lib.ivl_swa_decode_workspace_bytes(B, Tk, Hq)
+        key = (q.device.index, torch.cuda.current_stream(q.device).cuda_stream)
+        ws = _decode_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=q.device)
+            _decode_ws[key] = ws
+        code = lib.ivl_swa_decode_fwd(q.data_ptr(), k.data_ptr(), _strides3(k), v.data_ptr(), _strides3(v),
+                                      out.data_ptr(), B, Tk, Hq, Hkv, D, int(window or 0), float(scale or 0.0),
+                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream(q.device).cuda_stream)
+        _lib.check(code, "ivl_swa_decode_fwd")
+        return out
     code = lib.ivl_swa_fwd(q.data_ptr(), _strides3(q), k.data_ptr(), _strides3(k), v.data_ptr(), _strides3(v),
                            out.data_ptr(), _strides3(out), B, Tq, Tk, Hq, Hkv, D, int(window or 0),
                            float(scale or 0.0), torch.cuda.current_stream(q.device).cuda_stream)
