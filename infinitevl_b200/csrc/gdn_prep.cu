@@ -27,13 +27,13 @@ constexpr int PREP_THREADS = 256;  // 8 warps: warp w owns rows 16*(w>>1).. of t
 constexpr int KH_LD = 136;  // bf16 elements per row: 272 B, rows shift by 16 B mod 128 -> conflict-free ldmatrix
 constexpr int V_LD = 264;
 constexpr int A_LD = 72;
-constexpr int LP_LD = 20;  // floats per row of one residue plane of L (16 used)
+constexpr int L_LD = 68;   // fp32 row stride of L and of T = (I + L)^-1
 
 struct __align__(16) PrepSmem {
   __nv_bfloat16 kh[64 * KH_LD];
   __nv_bfloat16 qh[64 * KH_LD];
   __nv_bfloat16 vb[64 * V_LD];
-  float Lp[4][64 * LP_LD + 4];  // L split by column residue: Lp[j & 3][i][j >> 2]; +4 staggers the planes' banks
+  float L[64 * L_LD];  // strictly lower triangular, fp32
   __nv_bfloat16 Aw[64 * A_LD];
   __nv_bfloat16 Au[64 * A_LD];
   float G[64];
@@ -68,14 +68,15 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 // the rounded row in shared memory for the tensor-core products, and write the exponentially
 // weighted copy straight into its operand image in global memory.
 //   img_piece(p) returns the byte offset of 16-byte piece p (8 elements) of this thread's quarter row.
-template <class PieceOffset>
-__device__ __forceinline__ void norm_row_quarter(const __nv_bfloat16* src, bool valid, bool l2norm,
-                                                 float weight, __nv_bfloat16* smem_row, uint8_t* img,
-                                                 PieceOffset img_piece) {
-  uint4 raw[4];
+__device__ __forceinline__ void load_row_quarter(const __nv_bfloat16* src, bool valid, uint4* raw) {
 #pragma unroll
   for (int p = 0; p < 4; ++p)
     raw[p] = valid ? __ldg(reinterpret_cast<const uint4*>(src) + p) : make_uint4(0, 0, 0, 0);
+}
+
+template <class PieceOffset>
+__device__ __forceinline__ void norm_row_quarter(const uint4* raw, bool l2norm, float weight,
+                                                 __nv_bfloat16* smem_row, uint8_t* img, PieceOffset img_piece) {
   float ss = 0.f;
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
@@ -105,11 +106,22 @@ __device__ __forceinline__ void norm_row_quarter(const __nv_bfloat16* src, bool 
   }
 }
 
+#ifdef IVL_TRACE
+__device__ long long ivl_prep_trace[16 * 8];
+#define PTR(slot)                                                                     \
+  do {                                                                                \
+    if (blockIdx.x >= 1000 && blockIdx.x < 1016 && blockIdx.y == 3 && threadIdx.x == 0) \
+      ivl_prep_trace[(blockIdx.x - 1000) * 8 + (slot)] = clock64();                   \
+  } while (0)
+#else
+#define PTR(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(PREP_THREADS, 2)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
                 const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, int T, int H, float scale,
-                int l2norm) {
+                int l2norm, int prefetch_ahead) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -121,7 +133,37 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   uint8_t* blob = ws.blob + ch * BLOB_BYTES;
   uint8_t* ublob = ws.ublob + ch * (GDN_NS * UBLOB_BYTES);
 
-  // ---- stage 0: async copy of the V tile, zero L, chunk-local cumsum of g ---------------
+  PTR(0);
+  // ---- stage 0: issue every global load of the chunk up front (q, k rows into registers, V by cp.async,
+  //      g / beta), then the chunk-local cumsum of g ------------------------------------------------
+  uint4 rawq[4], rawk[4];
+  {
+    const int row = tid >> 2, qt = tid & 3;  // 4 threads per row, 32 elements each
+    const size_t off = ((tok0 + row) * H + h) * GDN_K + qt * 32;
+    load_row_quarter(q + off, row < valid, rawq);
+    load_row_quarter(k + off, row < valid, rawk);
+  }
+  {
+    // Warm L2 for the CTA that will run on this SM slot one wave later (CTAs are dispatched in linear
+    // block order, chunk fastest): its q/k/v/g/beta lines then hit L2 instead of paying HBM latency
+    // at the head of a short CTA.
+    const long long ahead = (long long)c + (long long)NT * h + prefetch_ahead;
+    const int pc = (int)(ahead % NT), ph = (int)(ahead / NT);
+    if (ph < H) {
+      const size_t ptok = (size_t)b * T + (size_t)pc * GDN_C;
+      const int row = tid >> 2, qt = tid & 3;
+      if (pc * GDN_C + row < T) {
+        const size_t poff = ((ptok + row) * H + ph) * GDN_K + qt * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + poff));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(k + poff));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v + ((ptok + row) * H + ph) * GDN_V + qt * 64));
+        if (qt == 0) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (ptok + row) * H + ph));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(beta + (ptok + row) * H + ph));
+        }
+      }
+    }
+  }
   for (int i = tid; i < 64 * 32; i += PREP_THREADS) {
     const int row = i >> 5, piece = i & 31;
     __nv_bfloat16* dst = &s.vb[row * V_LD + piece * 8];
@@ -131,7 +173,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = tid; i < 4 * (64 * LP_LD + 4); i += PREP_THREADS) (&s.Lp[0][0])[i] = 0.f;
+  for (int i = tid; i < 64 * L_LD; i += PREP_THREADS) s.L[i] = 0.f;
   if (warp == 0) {
     float g0 = (lane < valid) ? g[(tok0 + lane) * H + h] : 0.f;
     float g1 = (lane + 32 < valid) ? g[(tok0 + lane + 32) * H + h] : 0.f;
@@ -147,19 +189,18 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     s.beta[lane + 32] = (lane + 32 < valid) ? __bfloat162float(beta[(tok0 + lane + 32) * H + h]) : 0.f;
   }
   __syncthreads();
+  PTR(1);
 
   // ---- stage 1: normalise q, k rows; emit Qg and Kt images --------------------------------
   {
-    const int row = tid >> 2, qt = tid & 3;  // 4 threads per row, 32 elements each
-    const bool ok = row < valid;
+    const int row = tid >> 2, qt = tid & 3;
     const float Gr = s.G[row], Gc = s.G[63];
-    const size_t off = ((tok0 + row) * H + h) * GDN_K + qt * 32;
     const int R = 64 + row;  // Qg occupies rows 64..127 of the stacked [-Wg ; Qg] operand
-    norm_row_quarter(q + off, ok, l2norm != 0, __expf(Gr) * scale, &s.qh[row * KH_LD + qt * 32],
+    norm_row_quarter(rawq, l2norm != 0, __expf(Gr) * scale, &s.qh[row * KH_LD + qt * 32],
                      blob + BLOB_OFF_A1, [&](int p) {
                        return (uint32_t)((R >> 3) * 2048 + (qt * 4 + p) * 128 + (R & 7) * 16);
                      });
-    norm_row_quarter(k + off, ok, l2norm != 0, __expf(Gc - Gr), &s.kh[row * KH_LD + qt * 32],
+    norm_row_quarter(rawk, l2norm != 0, __expf(Gc - Gr), &s.kh[row * KH_LD + qt * 32],
                      blob + BLOB_OFF_KT, [&](int p) {
                        return (uint32_t)((qt * 4 + p) * 1024 + (row >> 3) * 128 + (row & 7) * 16);
                      });
@@ -167,6 +208,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+  PTR(2);
 
   const int gq = lane >> 2, tq = lane & 3;  // mma fragment coordinates
   const int strip = warp >> 1, half = warp & 1;
@@ -212,10 +254,10 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
         const float e00 = __expf(fminf(G0 - Gj0, 0.f)), e01 = __expf(fminf(G0 - Gj1, 0.f));
         const float e10 = __expf(fminf(G1 - Gj0, 0.f)), e11 = __expf(fminf(G1 - Gj1, 0.f));
         // strictly-lower entries of L; entries on/above the diagonal stay zero
-        if (i0 > j0) s.Lp[j0 & 3][i0 * LP_LD + (j0 >> 2)] = be0 * ckk[lt][0] * e00;
-        if (i0 > j1) s.Lp[j1 & 3][i0 * LP_LD + (j1 >> 2)] = be0 * ckk[lt][1] * e01;
-        if (i1 > j0) s.Lp[j0 & 3][i1 * LP_LD + (j0 >> 2)] = be1 * ckk[lt][2] * e10;
-        if (i1 > j1) s.Lp[j1 & 3][i1 * LP_LD + (j1 >> 2)] = be1 * ckk[lt][3] * e11;
+        if (i0 > j0) s.L[i0 * L_LD + j0] = be0 * ckk[lt][0] * e00;
+        if (i0 > j1) s.L[i0 * L_LD + j1] = be0 * ckk[lt][1] * e01;
+        if (i1 > j0) s.L[i1 * L_LD + j0] = be1 * ckk[lt][2] * e10;
+        if (i1 > j1) s.L[i1 * L_LD + j1] = be1 * ckk[lt][3] * e11;
         p00 = (i0 >= j0) ? cqk[lt][0] * e00 * scale : 0.f;
         p01 = (i0 >= j1) ? cqk[lt][1] * e01 * scale : 0.f;
         p10 = (i1 >= j0) ? cqk[lt][2] * e10 * scale : 0.f;
@@ -227,44 +269,101 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     }
   }
   __syncthreads();
+  PTR(3);
 
-  // ---- stage 3: T = (I + L)^-1 by forward substitution, one column per thread quad ---------
-  // Thread (col, res) keeps the entries T[i][col] with i % 4 == res and accumulates the products
-  // over columns j with j % 4 == res; the quad combines its partial sums by shuffle.
-  {
-    const int col = tid >> 2, res = tid & 3;
-    const float* Lrow = &s.Lp[res][0];
+  // ---- stage 3: T = (I + L)^-1, blocked 4 x 4 in 16 x 16 tiles -------------------------------------
+  //   diagonal tiles  T_ii = (I + L_ii)^-1                      fp32 forward substitution (16 steps)
+  //   below diagonal  T_ij = -T_ii sum_{k=j}^{i-1} L_ik T_kj    tensor cores, operands split hi + lo in
+  //                                                             bf16 (3 MMAs per product ~ fp32 accuracy)
+  // T lives in the (now dead) q tile; the reference likewise solves in fp32 and rounds the result to
+  // bf16 afterwards (wy_fast.py:188-210,342-343; 16 x 16 tiles as in pip-fla's solve_tril).
+  float* Tm = reinterpret_cast<float*>(s.qh);
+  static_assert(sizeof(float) * 64 * L_LD <= sizeof(__nv_bfloat16) * 64 * KH_LD, "T must fit in the q tile");
+  // tiles above the diagonal are zero (6 tiles x 256 entries); everything else is written below
+  for (int e = tid; e < 6 * 256; e += PREP_THREADS) {
+    const int t6 = e >> 8, rr = (e >> 4) & 15, cc = e & 15;
+    const int ti = (t6 < 3) ? 0 : (t6 < 5 ? 1 : 2);
+    const int tj = (t6 < 3) ? t6 + 1 : (t6 < 5 ? t6 - 1 : 3);
+    Tm[(ti * 16 + rr) * L_LD + tj * 16 + cc] = 0.f;
+  }
+  if (tid < 64) {
+    // one column of one diagonal tile per thread
+    const int blk = tid >> 4, col = tid & 15, base = blk * 16;
     float x[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = 0.f;
+    for (int i = 0; i < 16; ++i) {
+      float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) {
-      float acc0 = 0.f, acc1 = 0.f;
-      const int n = (i + 3) >> 2;  // own-residue columns below the diagonal (rounded up; extras are zero)
-#pragma unroll
-      for (int j4 = 0; j4 < (n + 3) / 4; ++j4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(&Lrow[i * LP_LD + j4 * 4]);
-        acc0 = fmaf(l4.x, x[j4 * 4 + 0], acc0);
-        if (j4 * 4 + 1 < n) acc1 = fmaf(l4.y, x[j4 * 4 + 1], acc1);
-        if (j4 * 4 + 2 < n) acc0 = fmaf(l4.z, x[j4 * 4 + 2], acc0);
-        if (j4 * 4 + 3 < n) acc1 = fmaf(l4.w, x[j4 * 4 + 3], acc1);
-      }
-      float acc = acc0 + acc1;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      const float xi = ((i == col) ? 1.f : 0.f) - acc;
-      if ((i & 3) == res) x[i >> 2] = xi;
+      for (int j = 0; j < i; ++j) acc = fmaf(s.L[(base + i) * L_LD + base + j], x[j], acc);
+      x[i] = ((i == col) ? 1.f : 0.f) - acc;
     }
-    const float bu = s.beta[col], bw = bu * __expf(s.G[col]);
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-      const int i = 4 * jj + res;
-      s.Aw[i * A_LD + col] = __float2bfloat16(x[jj] * bw);
-      s.Au[i * A_LD + col] = __float2bfloat16(x[jj] * bu);
+    for (int i = 0; i < 16; ++i) Tm[(base + i) * L_LD + base + col] = x[i];
+  }
+  __syncthreads();
+  PTR(4);
+  if (warp < 6) {
+    // warps 2j, 2j+1 own tile column j (8 of its 16 columns each -- columns of T are independent) and walk
+    // down it; each 16x16x8 product is 3 split MMAs
+    const int j = warp >> 1, nh = warp & 1;
+    auto split = [](float a, float b, uint32_t& hi, uint32_t& lo) {
+      const __nv_bfloat16 ha = __float2bfloat16(a), hb = __float2bfloat16(b);
+      hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+      lo = pack_bf16(a - __bfloat162float(ha), b - __bfloat162float(hb));
+    };
+    // acc[4] += X(rows xr..+15, cols xc..+15) * Y(rows yr..+15, cols yc..+7), X and Y fp32 in shared memory
+    auto tile_mma = [&](float* acc, const float* X, int xr, int xc, const float* Y, int yr, int yc) {
+      uint32_t ah[4], al[4];
+      const float* xa = X + (xr + gq) * L_LD + xc + 2 * tq;
+      split(xa[0], xa[1], ah[0], al[0]);
+      split(xa[8 * L_LD], xa[8 * L_LD + 1], ah[1], al[1]);
+      split(xa[8], xa[9], ah[2], al[2]);
+      split(xa[8 * L_LD + 8], xa[8 * L_LD + 9], ah[3], al[3]);
+      const float* yb = Y + (yr + 2 * tq) * L_LD + yc + gq;
+      uint32_t bh0, bl0, bh1, bl1;
+      split(yb[0], yb[L_LD], bh0, bl0);
+      split(yb[8 * L_LD], yb[9 * L_LD], bh1, bl1);
+      mma16816(acc, ah, bh0, bh1);
+      mma16816(acc, ah, bl0, bl1);
+      mma16816(acc, al, bh0, bh1);
+    };
+    const int nc = j * 16 + nh * 8;  // first of this warp's 8 columns
+    for (int i = j + 1; i < 4; ++i) {
+      float m[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int kb = j; kb < i; ++kb) tile_mma(m, s.L, i * 16, kb * 16, Tm, kb * 16, nc);
+      // stage M_ij in tile (i, j) of T (not read by anyone else), then T_ij = -T_ii M_ij
+      float* dst = Tm + (i * 16) * L_LD + nc;
+      dst[gq * L_LD + 2 * tq] = m[0];
+      dst[gq * L_LD + 2 * tq + 1] = m[1];
+      dst[(gq + 8) * L_LD + 2 * tq] = m[2];
+      dst[(gq + 8) * L_LD + 2 * tq + 1] = m[3];
+      __syncwarp();
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      tile_mma(t, Tm, i * 16, i * 16, Tm, i * 16, nc);
+      __syncwarp();
+      dst[gq * L_LD + 2 * tq] = -t[0];
+      dst[gq * L_LD + 2 * tq + 1] = -t[1];
+      dst[(gq + 8) * L_LD + 2 * tq] = -t[2];
+      dst[(gq + 8) * L_LD + 2 * tq + 1] = -t[3];
+      __syncwarp();
     }
   }
   __syncthreads();
-
+  PTR(5);
+  // T -> the two bf16 A operands: Aw = T diag(beta exp G), Au = T diag(beta); a thread keeps one column
+  {
+    const int cc = tid & 63, rbase = tid >> 6;
+    const float bu = s.beta[cc], bw = bu * __expf(s.G[cc]);
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int i = rbase + 4 * it;
+      const float tv = Tm[i * L_LD + cc];
+      s.Aw[i * A_LD + cc] = __float2bfloat16(tv * bw);
+      s.Au[i * A_LD + cc] = __float2bfloat16(tv * bu);
+    }
+  }
+  __syncthreads();
+  PTR(6);
   // ---- stage 4: Wg = Aw Kn (negated, into rows 0..63 of the A1 image), U = Au V ------------
   // warp (strip, half): key dims 64*half..+63 of Wg, value columns 128*half..+127 of U
   {
@@ -327,9 +426,16 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       }
     }
   }
+  PTR(7);
 }
 
 }  // namespace
+
+#ifdef IVL_TRACE
+extern "C" __attribute__((visibility("default"))) int ivl_debug_read_prep_trace(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, ivl_prep_trace, sizeof(long long) * n);
+}
+#endif
 
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                             const GdnWorkspace& ws, int B, int T, int H, float scale, int l2norm,
@@ -341,10 +447,18 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  static int resident = 0;
+  if (resident == 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident = 2 * sms;
+  }
   dim3 grid(gdn_num_chunks(T), H, B);
   gdn_prep_kernel<<<grid, PREP_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
-      static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, T, H, scale, l2norm);
+      static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, T, H, scale, l2norm,
+      resident);
   return cudaGetLastError();
 }
 

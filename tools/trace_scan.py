@@ -45,3 +45,11 @@ for i in order:
     print(f"{names[i]:14s} +{med[i]:8.0f}")
 nxt = np.median(t[5:60, 0] - t[4:59, 0])
 print("next M:ready at +", nxt)
+
+pb = (ctypes.c_longlong * (16 * 8))()
+lib.ivl_debug_read_prep_trace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+assert lib.ivl_debug_read_prep_trace(pb, 16 * 8) == 0
+pt = np.array(pb[:]).reshape(16, 8).astype(np.int64)
+d = np.median(np.diff(pt, axis=1), axis=0)
+print("prep phases (cycles): loads+cumsum", d[0], "| norm+images", d[1], "| KK/QK+L,P", d[2], "| zero T + diag solve", d[3],
+      "| tile products", d[4], "| T->Aw,Au", d[5], "| W,U mma+stores", d[6], "| total", np.median(pt[:, 7] - pt[:, 0]))

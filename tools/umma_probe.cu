@@ -25,6 +25,8 @@ struct ProbeArgs {
   uint32_t nk;
   uint32_t n;
   uint32_t a_off[8], b_off[8];
+  uint32_t lane_off;   // lane field added to the accumulator address (M = 64 experiments)
+  uint32_t overwrite;  // first MMA overwrites even when a preload exists
 };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
     for (uint32_t j = 0; j < p.nk; ++j) {
       uint64_t da = umma_desc(smem_u32(sA) + p.a_off[j], p.a_lbo, p.a_sbo, p.a_layout);
       uint64_t db = umma_desc(smem_u32(sB) + p.b_off[j], p.b_lbo, p.b_sbo, p.b_layout);
-      umma_bf16(tmem, da, db, p.idesc, (p.d0 != nullptr || j > 0) ? 1u : 0u);
+      umma_bf16(tmem + (p.lane_off << 16), da, db, p.idesc, ((p.d0 != nullptr && !p.overwrite) || j > 0) ? 1u : 0u);
     }
     umma_commit(&bar_mma);
   }
@@ -208,6 +210,54 @@ static int run(Lay la, bool swap_a, Lay lb, bool swap_b, int N, int K, bool neg_
   return bad == 0 && e == cudaSuccess;
 }
 
+// M = 64: which TMEM lanes receive which accumulator rows?  (lane_off = lane field of the D address)
+static void run_m64(int lane_off) {
+  const int M = 64, N = 32, K = 64;
+  std::vector<float> A(M * K), B(N * K), D0(128 * N, 0.f), ref(M * N);
+  srand(99);
+  for (auto& v : A) v = (float)((rand() % 7) - 3);
+  for (auto& v : B) v = (float)((rand() % 5) - 2);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc += A[m * K + k] * B[n * K + k];
+      ref[m * N + n] = acc + 1000.f * (m + 1);  // make every row unique: add a row tag through D0? (done below)
+    }
+  Operand oa = build(K_SW128, A, M, K, false), ob = build(K_SW128, B, N, K, false);
+  uint8_t *da, *db; float *dd, *dd0;
+  cudaMalloc(&da, 32768); cudaMalloc(&db, 32768); cudaMalloc(&dd, 128 * N * 4); cudaMalloc(&dd0, 128 * N * 4);
+  cudaMemcpy(da, oa.img.data(), 32768, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, ob.img.data(), 32768, cudaMemcpyHostToDevice);
+  for (int l = 0; l < 128; ++l) for (int n = 0; n < N; ++n) D0[l * N + n] = -7777.f;  // sentinel preload
+  cudaMemcpy(dd0, D0.data(), 128 * N * 4, cudaMemcpyHostToDevice);
+  ProbeArgs p{};
+  p.a_img = da; p.b_img = db; p.d0 = dd0; p.d = dd; p.a_bytes = 32768; p.b_bytes = 32768;
+  p.a_lbo = oa.lbo; p.a_sbo = oa.sbo; p.a_layout = oa.layout; p.b_lbo = ob.lbo; p.b_sbo = ob.sbo; p.b_layout = ob.layout;
+  p.idesc = umma_idesc_bf16(M, N, 0, 0); p.nk = K / 16; p.n = N;
+  memcpy(p.a_off, oa.off, sizeof(p.a_off)); memcpy(p.b_off, ob.off, sizeof(p.b_off));
+  p.lane_off = lane_off; p.overwrite = 1;
+  probe_kernel<<<1, 128, 65536 + 1024>>>(p);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<float> out(128 * N);
+  cudaMemcpy(out.data(), dd, 128 * N * 4, cudaMemcpyDeviceToHost);
+  printf("M=64 lane_off=%d (%s): lane->row map: ", lane_off, e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+  for (int l = 0; l < 128; ++l) {
+    int found = -2;
+    if (out[l * N] == -7777.f && out[l * N + 5] == -7777.f) found = -1;  // untouched
+    else
+      for (int m = 0; m < M; ++m) {
+        bool ok = true;
+        for (int n = 0; n < N && ok; ++n) ok = fabs(out[l * N + n] - (ref[m * N + n] - 1000.f * (m + 1))) < 1e-3;
+        if (ok) { found = m; break; }
+      }
+    if (l % 16 == 0) printf("| L%d: ", l);
+    printf("%d ", found);
+  }
+  printf("\n");
+  cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(dd0);
+  if (e != cudaSuccess) cudaDeviceReset();
+}
+
 int main() {
   int dev = 0;
   cudaDeviceProp prop;
@@ -244,5 +294,7 @@ int main() {
   run(K_SW128, false, K_SW128, false, 32, 128, true, false);
   run(K_SW128, false, K_SW128, false, 32, 128, false, true);
   run(K_SW128, false, K_SW128, false, 32, 128, true, true);
+  run_m64(0);
+  run_m64(16);
   return 0;
 }
