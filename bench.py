@@ -279,8 +279,11 @@ def run_ours(args):
 
     # ---- end-to-end through the public operator API with HOST buffers ---------------------------
     e2e = None
+    decode = None
     if world == 1:
         e2e = run_e2e(hp, args)
+        if hp.has_swa:
+            decode = run_decode(dev, peaks)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -297,12 +300,61 @@ def run_ours(args):
             "config": {"workload": workload, "seq_len": T, "batch": 1,
                        "parallelism": f"sequence-chunk x{world}" if world > 1 else "single GPU",
                        "l2": "inputs (>3 GB per layer) exceed the 126 MB L2; no flush needed"},
-            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "decode": decode,
             "gpu_launches": hp.launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_decode(dev, peaks, context=524288, steps=50):
+    """Decode step of the hot path (BASELINE.json config 3): after a 512K-token context the state is constant
+    size -- 27 DeltaNet states (bf16, as the reference caches them) and 9 full 8191-token K/V windows -- so one
+    step is 27 token-recurrence launches + 9 split-KV attention launches, captured in one CUDA graph."""
+    from inputs import gdn_inputs
+
+    from infinitevl_b200 import ops, swa
+    q, k, v, g, beta, h0 = gdn_inputs(T=1, H=H, seed=5, device=dev)
+    states = [h0.to(torch.bfloat16).clone() for _ in range(N_GDN_LAYERS)]
+    gen = torch.Generator().manual_seed(6)
+    kc = [torch.randn(1, WINDOW, HKV, D, generator=gen).bfloat16().to(dev) for _ in range(N_SWA_LAYERS)]
+    vc = [torch.randn(1, WINDOW, HKV, D, generator=gen).bfloat16().to(dev) for _ in range(N_SWA_LAYERS)]
+    sq = torch.randn(1, 1, HQ, D, generator=gen).bfloat16().to(dev)
+    so = torch.empty_like(sq)
+
+    def step():
+        for st in states:
+            ops.fused_recurrent_gated_delta_rule(q, k, v, g, beta, initial_state=st, output_final_state=True,
+                                                 use_qk_l2norm_in_kernel=True, state_out=st)
+        for kk, vv in zip(kc, vc):
+            swa.swa_attention_bthd(sq, kk, vv, window=WINDOW, out=so)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    alg = N_GDN_LAYERS * 2 * H * K * V * 2 + N_SWA_LAYERS * 2 * HKV * WINDOW * D * 2
+    return {"step_ms": round(ms, 4), "context_tokens": context, "launches_per_step": N_GDN_LAYERS + 2 * N_SWA_LAYERS,
+            "algorithmic_bytes": alg, "achieved_gbs": round(alg / (ms * 1e-3) / 1e9, 1),
+            "hbm_frac": round(alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+            "what": "27x GDN token recurrence (bf16 state in place) + 9x SWA split-KV decode over an 8192-key window, "
+                    "one CUDA graph; state size is independent of the context length"}
 
 
 def run_e2e(hp, args):

@@ -12,9 +12,9 @@
 //   warps row softmax (one thread per query row, no shuffles), lazy rescale of O in TMEM,
 //         P -> bf16 -> shared (K-major core-matrix image)
 //   MMA   O += P V                   M128 N128 K64   (V: MN-major 128B-swizzled TMA tile)
-// The eight K = 16 steps of S alternate between two TMEM accumulators that the softmax adds: at N = 64 one
-// MMA is shorter than the tensor pipe's accumulate latency, so a single accumulator would serialise on it.
-// S(t+1) is issued as soon as the softmax warps have pulled S(t) out of TMEM, i.e. before P(t) is ready.
+// S is double-buffered in TMEM so S(t+1) is issued before P(t) is ready.  The softmax is instruction-issue
+// bound (ncu: tensor and XU pipes ~50 % each, profiles/r01c_summary.md), so its inner loops use the packed
+// FP32x2 instructions of sm_100 (scale and max subtraction in one FFMA2, row sum in FADD2).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue.
 #include <cuda.h>
 
@@ -35,13 +35,13 @@ constexpr uint32_t OFF_P = OFF_V + 2 * KT_BYTES_;
 constexpr uint32_t P_BYTES_ = BM * BN * 2;       // 16 KiB
 constexpr uint32_t DATA_BYTES = OFF_P + P_BYTES_;  // 112 KiB
 constexpr uint32_t SWA_SMEM = DATA_BYTES + 1024;   // barriers live in the alignment slack (or the tail)
-constexpr uint32_t TM_S = 0;      // 2 partial accumulators x 64 columns
+constexpr uint32_t TM_S = 0;      // 2 buffers x 64 columns
 constexpr uint32_t TM_O = 128;    // 128 columns
 constexpr uint32_t TM_COLS = 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: O is only rescaled when the row max grows by > 2^8
 
 struct Bars {
-  uint64_t full[2], empty[2], q, s, sfree, p, pv;
+  uint64_t full[2], empty[2], q, s[2], sfree[2], p, pv;
   uint32_t tmem_base;
 };
 
@@ -72,8 +72,10 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int n_tiles = t_hi - t_lo + 1;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
-    mbar_init(&bars.s, 1); mbar_init(&bars.sfree, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1);
+      mbar_init(&bars.s[i], 1); mbar_init(&bars.sfree[i], 4);
+    }
     mbar_init(&bars.q, 1); mbar_init(&bars.p, 4); mbar_init(&bars.pv, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -117,9 +119,9 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int j = 0; j < 8; ++j) {
         const uint32_t qoff = ((j >> 2) * (Q_BYTES / 2) + (j & 3) * 32) >> 4;
         const uint32_t koff = ((j >> 2) * (KT_BYTES_ / 2) + (j & 3) * 32) >> 4;
-        umma_bf16_ws(tm + TM_S + (j & 1) * BN, dQ + qoff, dK + koff, idescS, j >= 2);
+        umma_bf16_ws(tm + TM_S + s * BN, dQ + qoff, dK + koff, idescS, j > 0);
       }
-      umma_commit_ws(&bars.s);
+      umma_commit_ws(&bars.s[s]);
     };
     mbar_wait(&bars.q, 0);
     mbar_wait(&bars.full[0], 0);
@@ -129,7 +131,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (t + 1 < n_tiles) {
         const int s1 = (t + 1) & 1;
         mbar_wait(&bars.full[s1], ((t + 1) >> 1) & 1);
-        mbar_wait(&bars.sfree, t & 1);  // the softmax warps have read S(t)
+        if (t + 1 >= 2) mbar_wait(&bars.sfree[s1], (((t + 1) >> 1) - 1) & 1);
         tc_fence_after();
         issue_s(t + 1);
       }
@@ -153,77 +155,78 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const int pos = i0 + row + shift;  // absolute key position of this query
     uint8_t* p_dst = smem + OFF_P + (row >> 3) * 1024 + (row & 7) * 16;
-    float m = -INFINITY, l = 0.f;
-    uint32_t r[32], r2[32];
-    float x[64];
+    float m = -INFINITY, l = 0.f;   // running max (log2 domain, scaled) and row sum
+    uint32_t r[32], r2[32];          // raw scores of keys 0..31 / 32..63 of the tile
     for (int t = 0; t < n_tiles; ++t) {
+      const int s = t & 1;
       const int j0 = (t_lo + t) * BN;
-      mbar_wait(&bars.s, t & 1);
+      mbar_wait(&bars.s[s], (t >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {  // two halves of 32 keys; each is the sum of the two partial accumulators
-        tmem_ld32(tlane + TM_S + hh * 32, r);
-        tmem_ld32(tlane + TM_S + BN + hh * 32, r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          x[hh * 32 + i] = (__uint_as_float(r[i]) + __uint_as_float(r2[i])) * a.scale_log2;
-      }
+      tmem_ld32(tlane + TM_S + s * BN, r);
+      tmem_ld32(tlane + TM_S + s * BN + 32, r2);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.sfree);
+      if (lane == 0) mbar_arrive(&bars.sfree[s]);
       // masks only on boundary tiles (CTA-uniform test)
       const bool need_mask = (j0 + BN - 1 > p_first) || (a.window > 0 && j0 < p_last - a.window + 1) ||
                              (j0 + BN > a.Tk);
       if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const int j = j0 + i;
-          const bool vis = (j <= pos) && (j < a.Tk) && (a.window <= 0 || pos - j < a.window);
-          x[i] = vis ? x[i] : -INFINITY;
+        for (int i = 0; i < 32; ++i) {
+          const int ja = j0 + i, jb = j0 + 32 + i;
+          const bool va = (ja <= pos) && (ja < a.Tk) && (a.window <= 0 || pos - ja < a.window);
+          const bool vb = (jb <= pos) && (jb < a.Tk) && (a.window <= 0 || pos - jb < a.window);
+          r[i] = va ? r[i] : 0xff800000u;   // -inf
+          r2[i] = vb ? r2[i] : 0xff800000u;
         }
       }
-      float mx = x[0];
+      float mx = fmaxf(__uint_as_float(r[0]), __uint_as_float(r2[0]));
 #pragma unroll
-      for (int i = 1; i < 64; ++i) mx = fmaxf(mx, x[i]);
+      for (int i = 1; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r2[i])));
+      mx *= a.scale_log2;  // scale > 0, so the max commutes with it
       // lazy rescale: the running max only moves when it would grow by more than 2^THRESHOLD
       const bool grow = mx > m + RESCALE_THRESHOLD;  // also true for the first finite max (m = -inf)
-      const float m_new = grow ? mx : m;
+      const float m_old = m;
+      m = grow ? mx : m;
+      const float m_eff = (m == -INFINITY) ? 0.f : m;
+      // p = exp2(score * scale - m): one packed FFMA per two keys, MUFU.EX2 each, packed row sum.  All of it
+      // happens BEFORE waiting for PV(t-1): only the store of P (single buffer) and the rare rescale of O
+      // depend on that MMA, so the exponentials overlap with it.
+      const float2 sc2 = make_float2(a.scale_log2, a.scale_log2), nm2 = make_float2(-m_eff, -m_eff);
+      float2 sum2 = make_float2(0.f, 0.f);
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const uint32_t* src = (i < 16) ? (r + 2 * i) : (r2 + 2 * (i - 16));
+        float2 v = __ffma2_rn(make_float2(__uint_as_float(src[0]), __uint_as_float(src[1])), sc2, nm2);
+        v.x = exp2f(v.x);
+        v.y = exp2f(v.y);
+        sum2 = __fadd2_rn(sum2, v);
+        w[i] = pack_bf16(v.x, v.y);
+      }
       if (t > 0) {
         mbar_wait(&bars.pv, (t - 1) & 1);  // P buffer free, O complete up to tile t-1
         tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
-          const float f = grow ? exp2f(m - m_new) : 1.f;  // exp2(-inf) = 0 wipes an all-masked prefix
+          const float f = grow ? exp2f(m_old - m) : 1.f;  // exp2(-inf) = 0 wipes an all-masked prefix
           l *= f;
+          uint32_t ro[32];
 #pragma unroll
           for (int c = 0; c < HD; c += 32) {
-            tmem_ld32(tlane + TM_O + c, r);
+            tmem_ld32(tlane + TM_O + c, ro);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-            tmem_st32(tlane + TM_O + c, r);
+            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * f);
+            tmem_st32(tlane + TM_O + c, ro);
           }
           tmem_st_wait();
         }
       }
-      m = m_new;
-      const float m_eff = (m == -INFINITY) ? 0.f : m;
-      float sum = 0.f;
+      l += sum2.x + sum2.y;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        x[i] = exp2f(x[i] - m_eff);
-        sum += x[i];
-      }
-      l += sum;
-#pragma unroll
-      for (int kg = 0; kg < 8; ++kg) {
-        uint4 w;
-        w.x = pack_bf16(x[kg * 8 + 0], x[kg * 8 + 1]);
-        w.y = pack_bf16(x[kg * 8 + 2], x[kg * 8 + 3]);
-        w.z = pack_bf16(x[kg * 8 + 4], x[kg * 8 + 5]);
-        w.w = pack_bf16(x[kg * 8 + 6], x[kg * 8 + 7]);
-        *reinterpret_cast<uint4*>(p_dst + kg * 128) = w;
-      }
+      for (int kg = 0; kg < 8; ++kg)
+        *reinterpret_cast<uint4*>(p_dst + kg * 128) = make_uint4(w[4 * kg], w[4 * kg + 1], w[4 * kg + 2], w[4 * kg + 3]);
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
