@@ -87,6 +87,56 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs p) {
   if (warp == 0) tmem_dealloc<64>(tmem);
 }
 
+// TS mode: A operand staged in TMEM by tcgen05.st (thread = row, word c = elements 2c, 2c+1), B in smem.
+__global__ void __launch_bounds__(128, 1) probe_ts_kernel(ProbeArgs p, const uint32_t* a_words /*[128][K/2]*/) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sB = smem;
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar_load, p.b_bytes);
+    bulk_g2s(sB, p.b_img, p.b_bytes, &bar_load);
+  }
+  const uint32_t row = warp * 32 + lane;
+  const uint32_t taddr = tmem + ((warp * 32u) << 16);
+  {
+    uint32_t r[32];
+    for (int i = 0; i < 32; ++i) r[i] = (i < (int)p.nk * 8) ? a_words[row * (p.nk * 8) + i] : 0u;
+    tmem_st32(taddr + 128, r);  // A lives at columns 128..159
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  mbar_wait(&bar_load, 0);
+  tc_fence_after();
+  if (warp == 0) {
+    for (uint32_t j = 0; j < p.nk; ++j) {
+      uint64_t db = umma_desc(smem_u32(sB) + p.b_off[j], p.b_lbo, p.b_sbo, p.b_layout);
+      umma_bf16_ts_ws(tmem, tmem + 128 + j * 8, db, p.idesc, j > 0 ? 1u : 0u);
+    }
+    umma_commit_ws(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (uint32_t c = 0; c < p.n; c += 8) {
+    uint32_t r[8];
+    tmem_ld8(taddr + c, r);
+    tmem_ld_wait();
+    for (int i = 0; i < 8; ++i) p.d[row * p.n + c + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 // ---------------------------------------------------------------------------
 static uint16_t f2bf(float f) {
   uint32_t u;
@@ -210,6 +260,45 @@ static int run(Lay la, bool swap_a, Lay lb, bool swap_b, int N, int K, bool neg_
   return bad == 0 && e == cudaSuccess;
 }
 
+static int run_ts(Lay lb, int N, int K) {
+  const int M = 128;
+  std::vector<float> A(M * K), B(N * K), ref(M * N);
+  srand(4321 + N + K);
+  for (auto& v : A) v = (float)((rand() % 7) - 3);
+  for (auto& v : B) v = (float)((rand() % 5) - 2);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc += A[m * K + k] * B[n * K + k];
+      ref[m * N + n] = acc;
+    }
+  Operand ob = build(lb, B, N, K, false);
+  std::vector<uint32_t> aw(M * K / 2);
+  for (int m = 0; m < M; ++m)
+    for (int c = 0; c < K / 2; ++c) aw[m * (K / 2) + c] = (uint32_t)f2bf(A[m * K + 2 * c]) | ((uint32_t)f2bf(A[m * K + 2 * c + 1]) << 16);
+  uint8_t* db; float* dd; uint32_t* da;
+  cudaMalloc(&db, 32768); cudaMalloc(&dd, M * N * 4); cudaMalloc(&da, aw.size() * 4);
+  cudaMemcpy(db, ob.img.data(), 32768, cudaMemcpyHostToDevice);
+  cudaMemcpy(da, aw.data(), aw.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dd, 0xff, M * N * 4);
+  ProbeArgs p{};
+  p.b_img = db; p.d = dd; p.b_bytes = 32768; p.b_lbo = ob.lbo; p.b_sbo = ob.sbo; p.b_layout = ob.layout;
+  p.idesc = umma_idesc_bf16(M, N, 0, ob.major); p.nk = K / 16; p.n = N;
+  memcpy(p.b_off, ob.off, sizeof(p.b_off));
+  cudaFuncSetAttribute(probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024);
+  probe_ts_kernel<<<1, 128, 65536 + 1024>>>(p, da);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<float> out(M * N);
+  cudaMemcpy(out.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
+  int bad = 0; double maxerr = 0;
+  for (int i = 0; i < M * N; ++i) { double er = fabs((double)out[i] - ref[i]); if (!(er <= 1e-3)) ++bad; if (er > maxerr || er != er) maxerr = er; }
+  printf("%-4s TS: A=TMEM B=%-8s N=%-3d K=%-3d bad=%d/%d maxerr=%g %s\n", (bad == 0 && e == cudaSuccess) ? "PASS" : "FAIL", lname(lb), N, K,
+         bad, M * N, maxerr, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(db); cudaFree(dd); cudaFree(da);
+  if (e != cudaSuccess) cudaDeviceReset();
+  return bad == 0;
+}
+
 // M = 64: which TMEM lanes receive which accumulator rows?  (lane_off = lane field of the D address)
 static void run_m64(int lane_off) {
   const int M = 64, N = 32, K = 64;
@@ -296,5 +385,9 @@ int main() {
   run(K_SW128, false, K_SW128, false, 32, 128, true, true);
   run_m64(0);
   run_m64(16);
+  run_ts(K_SW128, 64, 64);
+  run_ts(MN_SW128, 64, 64);
+  run_ts(MN_SW128, 128, 64);
+  run_ts(K_SW128, 64, 128);
   return 0;
 }
