@@ -12,10 +12,7 @@
 //   warps row softmax (one thread per query row, no shuffles), lazy rescale of O in TMEM,
 //         P -> bf16 -> shared (K-major core-matrix image)
 //   MMA   O += P V                   M128 N128 K64   (V: MN-major 128B-swizzled TMA tile)
-// The tensor pipe is in-order, shared by the two CTAs of an SM, and an MMA that accumulates onto the result of
-// the previous one pays the accumulate latency (~70 cycles at these tile sizes, more than its math), so the
-// eight K = 16 steps of S alternate between two TMEM accumulators that the softmax adds.  S(t+1) is issued as
-// soon as the softmax warps have pulled S(t) out of TMEM, i.e. before P(t) is ready.  The softmax is instruction-issue
+// S is double-buffered in TMEM so S(t+1) is issued before P(t) is ready.  The softmax is instruction-issue
 // bound (ncu: tensor and XU pipes ~50 % each, profiles/r01c_summary.md), so its inner loops use the packed
 // FP32x2 instructions of sm_100 (scale and max subtraction in one FFMA2, row sum in FADD2).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue.
@@ -38,13 +35,13 @@ constexpr uint32_t OFF_P = OFF_V + 2 * KT_BYTES_;
 constexpr uint32_t P_BYTES_ = BM * BN * 2;       // 16 KiB
 constexpr uint32_t DATA_BYTES = OFF_P + P_BYTES_;  // 112 KiB
 constexpr uint32_t SWA_SMEM = DATA_BYTES + 1024;   // barriers live in the alignment slack (or the tail)
-constexpr uint32_t TM_S = 0;      // 2 partial accumulators x 64 columns
+constexpr uint32_t TM_S = 0;      // 2 buffers x 64 columns
 constexpr uint32_t TM_O = 128;    // 128 columns
 constexpr uint32_t TM_COLS = 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: O is only rescaled when the row max grows by > 2^8
 
 struct Bars {
-  uint64_t full[2], empty[2], q, s, sfree, p, pv;
+  uint64_t full[2], empty[2], q, s[2], sfree[2], p, pv;
   uint32_t tmem_base;
 };
 
@@ -75,8 +72,10 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int n_tiles = t_hi - t_lo + 1;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1); }
-    mbar_init(&bars.s, 1); mbar_init(&bars.sfree, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1);
+      mbar_init(&bars.s[i], 1); mbar_init(&bars.sfree[i], 4);
+    }
     mbar_init(&bars.q, 1); mbar_init(&bars.p, 4); mbar_init(&bars.pv, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -120,9 +119,9 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int j = 0; j < 8; ++j) {
         const uint32_t qoff = ((j >> 2) * (Q_BYTES / 2) + (j & 3) * 32) >> 4;
         const uint32_t koff = ((j >> 2) * (KT_BYTES_ / 2) + (j & 3) * 32) >> 4;
-        umma_bf16_ws(tm + TM_S + (j & 1) * BN, dQ + qoff, dK + koff, idescS, j >= 2);
+        umma_bf16_ws(tm + TM_S + s * BN, dQ + qoff, dK + koff, idescS, j > 0);
       }
-      umma_commit_ws(&bars.s);
+      umma_commit_ws(&bars.s[s]);
     };
     mbar_wait(&bars.q, 0);
     mbar_wait(&bars.full[0], 0);
@@ -132,7 +131,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (t + 1 < n_tiles) {
         const int s1 = (t + 1) & 1;
         mbar_wait(&bars.full[s1], ((t + 1) >> 1) & 1);
-        mbar_wait(&bars.sfree, t & 1);  // the softmax warps have pulled S(t) out of TMEM
+        if (t + 1 >= 2) mbar_wait(&bars.sfree[s1], (((t + 1) >> 1) - 1) & 1);
         tc_fence_after();
         issue_s(t + 1);
       }
@@ -158,32 +157,17 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint8_t* p_dst = smem + OFF_P + (row >> 3) * 1024 + (row & 7) * 16;
     float m = -INFINITY, l = 0.f;   // running max (log2 domain, scaled) and row sum
     uint32_t r[32], r2[32];          // raw scores of keys 0..31 / 32..63 of the tile
-    uint32_t w[32];                  // second partial while loading; packed P afterwards
     for (int t = 0; t < n_tiles; ++t) {
+      const int s = t & 1;
       const int j0 = (t_lo + t) * BN;
-      mbar_wait(&bars.s, t & 1);
+      mbar_wait(&bars.s[s], (t >> 1) & 1);
       tc_fence_after();
-      tmem_ld32(tlane + TM_S, r);
-      tmem_ld32(tlane + TM_S + 32, r2);
-      tmem_ld32(tlane + TM_S + BN, w);
+      tmem_ld32(tlane + TM_S + s * BN, r);
+      tmem_ld32(tlane + TM_S + s * BN + 32, r2);
       tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float2 a2 = __fadd2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
-                                     make_float2(__uint_as_float(w[i]), __uint_as_float(w[i + 1])));
-        r[i] = __float_as_uint(a2.x); r[i + 1] = __float_as_uint(a2.y);
-      }
-      tmem_ld32(tlane + TM_S + BN + 32, w);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float2 a2 = __fadd2_rn(make_float2(__uint_as_float(r2[i]), __uint_as_float(r2[i + 1])),
-                                     make_float2(__uint_as_float(w[i]), __uint_as_float(w[i + 1])));
-        r2[i] = __float_as_uint(a2.x); r2[i + 1] = __float_as_uint(a2.y);
-      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.sfree);
+      if (lane == 0) mbar_arrive(&bars.sfree[s]);
       // masks only on boundary tiles (CTA-uniform test)
       const bool need_mask = (j0 + BN - 1 > p_first) || (a.window > 0 && j0 < p_last - a.window + 1) ||
                              (j0 + BN > a.Tk);
@@ -211,6 +195,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // depend on that MMA, so the exponentials overlap with it.
       const float2 sc2 = make_float2(a.scale_log2, a.scale_log2), nm2 = make_float2(-m_eff, -m_eff);
       float2 sum2 = make_float2(0.f, 0.f);
+      uint32_t w[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const uint32_t* src = (i < 16) ? (r + 2 * i) : (r2 + 2 * (i - 16));
