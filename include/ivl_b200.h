@@ -61,6 +61,13 @@ IVL_API const char* ivl_strerror(int code);
  *   scale <= 0 selects K^-0.5;  l2norm_qk != 0 normalises q,k rows in-kernel (eps 1e-6).
  *   workspace: ivl_gdn_chunk_workspace_bytes(B,T,H) bytes, 1024-byte aligned.
  * Only H*K*V = (any H)*128*256 is supported (the InfiniteVL shape); else IVL_ERR_BAD_SHAPE.
+ *
+ * Execution: two kernels, gdn_prep_kernel (parallel over chunks) and gdn_scan_kernel (the
+ * recurrence).  For T >= 2048 ivl_gdn_chunk_fwd runs them OVERLAPPED: the scan is launched on
+ * `stream`, prep on a library-owned second stream forked from and joined back to `stream` with
+ * events (legal inside a stream capture, so the call stays CUDA-graph safe); the scan follows
+ * per-chunk ready flags in the workspace.  Work submitted to `stream` after the call is ordered
+ * after both kernels.  Shorter inputs run prep then scan on `stream`.
  * ---------------------------------------------------------------------------------- */
 IVL_API size_t ivl_gdn_chunk_workspace_bytes(int B, int T, int H);
 
@@ -69,7 +76,9 @@ IVL_API int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const
                       int H, int K, int V, float scale, int l2norm_qk, void* workspace,
                       size_t workspace_bytes, void* stream);
 
-/* The two halves of the above, exposed so that the bench can time them separately. */
+/* The two halves of the above, exposed so that the bench can time them separately and so that a
+ * sequence-sharded caller can start prep before the previous rank's state has arrived.  prep must
+ * have been enqueued on `stream` (or be otherwise ordered) before scan. */
 IVL_API int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                        int B, int T, int H, float scale, int l2norm_qk, void* workspace,
                        size_t workspace_bytes, void* stream);

@@ -25,20 +25,24 @@ namespace {
 
 constexpr int PREP_THREADS = 256;  // 8 warps: warp w owns rows 16*(w>>1).. of the chunk and column half (w&1)
 constexpr int KH_LD = 136;  // bf16 elements per row: 272 B, rows shift by 16 B mod 128 -> conflict-free ldmatrix
-constexpr int V_LD = 264;
+constexpr int V_LD = 136;   // V is staged in two halves of 128 value columns
 constexpr int A_LD = 72;
 constexpr int L_LD = 68;   // fp32 row stride of L and of T = (I + L)^-1
 
+// 69.5 KiB, so that three CTAs are resident per SM (the kernel is a chain of short latency-bound
+// phases; occupancy is what hides them).  Buffers are reused as their contents die:
+//   qh : Qn rows                  -> T = (I + L)^-1 (fp32)        -> second half of V
+//   LA : L (fp32)                 -> Aw | Au (bf16 A operands)
 struct __align__(16) PrepSmem {
   __nv_bfloat16 kh[64 * KH_LD];
   __nv_bfloat16 qh[64 * KH_LD];
-  __nv_bfloat16 vb[64 * V_LD];
-  float L[64 * L_LD];  // strictly lower triangular, fp32
-  __nv_bfloat16 Aw[64 * A_LD];
-  __nv_bfloat16 Au[64 * A_LD];
+  __nv_bfloat16 vb[64 * V_LD];   // value columns 0..127
+  float LA[2 * 64 * A_LD / 2];   // 18432 B >= 64 * L_LD floats
   float G[64];
   float beta[64];
 };
+static_assert(sizeof(float) * 64 * L_LD <= sizeof(PrepSmem::LA), "L must fit");
+static_assert(sizeof(__nv_bfloat16) * 64 * V_LD <= sizeof(PrepSmem::qh), "V half must fit in the q tile");
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
                                         uint32_t& r3) {
@@ -110,22 +114,27 @@ __device__ __forceinline__ void norm_row_quarter(const uint4* raw, bool l2norm, 
 __device__ long long ivl_prep_trace[16 * 8];
 #define PTR(slot)                                                                     \
   do {                                                                                \
-    if (blockIdx.x >= 1000 && blockIdx.x < 1016 && blockIdx.y == 3 && threadIdx.x == 0) \
-      ivl_prep_trace[(blockIdx.x - 1000) * 8 + (slot)] = clock64();                   \
+    if (blockIdx.x >= 16000 && blockIdx.x < 16016 && threadIdx.x == 0)                \
+      ivl_prep_trace[(blockIdx.x - 16000) * 8 + (slot)] = clock64();                  \
   } while (0)
 #else
 #define PTR(slot) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(PREP_THREADS, 2)
+__global__ void __launch_bounds__(PREP_THREADS, 3)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
                 const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, int T, int H, float scale,
                 int l2norm, int prefetch_ahead) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
+  float* const sL = s.LA;                                                  // strictly lower triangular, fp32
+  __nv_bfloat16* const sAw = reinterpret_cast<__nv_bfloat16*>(s.LA);       // after the solve
+  __nv_bfloat16* const sAu = sAw + 64 * A_LD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c = blockIdx.x, h = blockIdx.y, b = blockIdx.z, NT = gridDim.x;
+  // CTAs are dispatched in linear block order: head fastest, then chunk, so the grid walks the sequence
+  // front to back over all heads and a concurrently running scan (gdn_scan.cu) can follow it.
+  const int c = blockIdx.x / H, h = blockIdx.x % H, b = blockIdx.z, NT = gridDim.x / H;
   const int t0 = c * GDN_C;
   const int valid = min(GDN_C, T - t0);
   const size_t tok0 = (size_t)b * T + t0;
@@ -144,12 +153,11 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     load_row_quarter(k + off, row < valid, rawk);
   }
   {
-    // Warm L2 for the CTA that will run on this SM slot one wave later (CTAs are dispatched in linear
-    // block order, chunk fastest): its q/k/v/g/beta lines then hit L2 instead of paying HBM latency
-    // at the head of a short CTA.
-    const long long ahead = (long long)c + (long long)NT * h + prefetch_ahead;
-    const int pc = (int)(ahead % NT), ph = (int)(ahead / NT);
-    if (ph < H) {
+    // Warm L2 for the CTA that will run on this SM slot one wave later: its q/k/v/g/beta lines then hit
+    // L2 instead of paying HBM latency at the head of a short CTA.
+    const long long ahead = (long long)blockIdx.x + prefetch_ahead;
+    const int pc = (int)(ahead / H), ph = (int)(ahead % H);
+    if (pc < NT) {
       const size_t ptok = (size_t)b * T + (size_t)pc * GDN_C;
       const int row = tid >> 2, qt = tid & 3;
       if (pc * GDN_C + row < T) {
@@ -164,8 +172,8 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       }
     }
   }
-  for (int i = tid; i < 64 * 32; i += PREP_THREADS) {
-    const int row = i >> 5, piece = i & 31;
+  for (int i = tid; i < 64 * 16; i += PREP_THREADS) {
+    const int row = i >> 4, piece = i & 15;
     __nv_bfloat16* dst = &s.vb[row * V_LD + piece * 8];
     if (row < valid)
       cp_async16(dst, v + ((tok0 + row) * H + h) * GDN_V + piece * 8);
@@ -173,7 +181,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = tid; i < 64 * L_LD; i += PREP_THREADS) s.L[i] = 0.f;
+  for (int i = tid; i < 64 * L_LD; i += PREP_THREADS) sL[i] = 0.f;
   if (warp == 0) {
     float g0 = (lane < valid) ? g[(tok0 + lane) * H + h] : 0.f;
     float g1 = (lane + 32 < valid) ? g[(tok0 + lane + 32) * H + h] : 0.f;
@@ -254,10 +262,10 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
         const float e00 = __expf(fminf(G0 - Gj0, 0.f)), e01 = __expf(fminf(G0 - Gj1, 0.f));
         const float e10 = __expf(fminf(G1 - Gj0, 0.f)), e11 = __expf(fminf(G1 - Gj1, 0.f));
         // strictly-lower entries of L; entries on/above the diagonal stay zero
-        if (i0 > j0) s.L[i0 * L_LD + j0] = be0 * ckk[lt][0] * e00;
-        if (i0 > j1) s.L[i0 * L_LD + j1] = be0 * ckk[lt][1] * e01;
-        if (i1 > j0) s.L[i1 * L_LD + j0] = be1 * ckk[lt][2] * e10;
-        if (i1 > j1) s.L[i1 * L_LD + j1] = be1 * ckk[lt][3] * e11;
+        if (i0 > j0) sL[i0 * L_LD + j0] = be0 * ckk[lt][0] * e00;
+        if (i0 > j1) sL[i0 * L_LD + j1] = be0 * ckk[lt][1] * e01;
+        if (i1 > j0) sL[i1 * L_LD + j0] = be1 * ckk[lt][2] * e10;
+        if (i1 > j1) sL[i1 * L_LD + j1] = be1 * ckk[lt][3] * e11;
         p00 = (i0 >= j0) ? cqk[lt][0] * e00 * scale : 0.f;
         p01 = (i0 >= j1) ? cqk[lt][1] * e01 * scale : 0.f;
         p10 = (i1 >= j0) ? cqk[lt][2] * e10 * scale : 0.f;
@@ -294,7 +302,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     for (int i = 0; i < 16; ++i) {
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < i; ++j) acc = fmaf(s.L[(base + i) * L_LD + base + j], x[j], acc);
+      for (int j = 0; j < i; ++j) acc = fmaf(sL[(base + i) * L_LD + base + j], x[j], acc);
       x[i] = ((i == col) ? 1.f : 0.f) - acc;
     }
 #pragma unroll
@@ -330,7 +338,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     const int nc = j * 16 + nh * 8;  // first of this warp's 8 columns
     for (int i = j + 1; i < 4; ++i) {
       float m[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int kb = j; kb < i; ++kb) tile_mma(m, s.L, i * 16, kb * 16, Tm, kb * 16, nc);
+      for (int kb = j; kb < i; ++kb) tile_mma(m, sL, i * 16, kb * 16, Tm, kb * 16, nc);
       // stage M_ij in tile (i, j) of T (not read by anyone else), then T_ij = -T_ii M_ij
       float* dst = Tm + (i * 16) * L_LD + nc;
       dst[gq * L_LD + 2 * tq] = m[0];
@@ -358,14 +366,25 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     for (int it = 0; it < 16; ++it) {
       const int i = rbase + 4 * it;
       const float tv = Tm[i * L_LD + cc];
-      s.Aw[i * A_LD + cc] = __float2bfloat16(tv * bw);
-      s.Au[i * A_LD + cc] = __float2bfloat16(tv * bu);
+      sAw[i * A_LD + cc] = __float2bfloat16(tv * bw);
+      sAu[i * A_LD + cc] = __float2bfloat16(tv * bu);
     }
   }
   __syncthreads();
   PTR(6);
+  // T is dead: fetch value columns 128..255 into its place while Wg and the first half of U are computed
+  __nv_bfloat16* const vb2 = s.qh;
+  for (int i = tid; i < 64 * 16; i += PREP_THREADS) {
+    const int row = i >> 4, piece = i & 15;
+    __nv_bfloat16* dst = &vb2[row * V_LD + piece * 8];
+    if (row < valid)
+      cp_async16(dst, v + ((tok0 + row) * H + h) * GDN_V + 128 + piece * 8);
+    else
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   // ---- stage 4: Wg = Aw Kn (negated, into rows 0..63 of the A1 image), U = Au V ------------
-  // warp (strip, half): key dims 64*half..+63 of Wg, value columns 128*half..+127 of U
+  // warp (strip, half): key dims 64*half..+63 of Wg; value columns 128*hv + 64*half..+63 of U in pass hv
   {
     const int i0 = r0 + gq, i1 = i0 + 8;
     float acc[8][4];
@@ -377,7 +396,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     for (int ks = 0; ks < 4; ++ks) {
       if (ks <= strip) {  // T is lower triangular
         uint32_t a[4];
-        ldsm_x4(smem_u32(&s.Aw[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
+        ldsm_x4(smem_u32(&sAw[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
         const int kk = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
         for (int ntp = 0; ntp < 4; ++ntp) {
@@ -396,8 +415,13 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(-acc[lt][2], -acc[lt][3]);
     }
 #pragma unroll
-    for (int hv = 0; hv < 2; ++hv) {  // two passes of 64 value columns
-      const int vbase = half * 128 + hv * 64;
+    for (int hv = 0; hv < 2; ++hv) {  // two passes of 64 value columns, one per staged half of V
+      const int vbase = hv * 128 + half * 64;
+      const __nv_bfloat16* vsrc = hv == 0 ? s.vb : vb2;
+      if (hv == 1) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -406,12 +430,12 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       for (int ks = 0; ks < 4; ++ks) {
         if (ks <= strip) {
           uint32_t a[4];
-          ldsm_x4(smem_u32(&s.Au[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
+          ldsm_x4(smem_u32(&sAu[(r0 + (lane & 15)) * A_LD + ks * 16 + (lane >> 4) * 8]), a[0], a[1], a[2], a[3]);
           const int kk = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
           for (int ntp = 0; ntp < 4; ++ntp) {
             uint32_t b0, b1, b2, b3;
-            ldsm_x4_t(smem_u32(&s.vb[kk * V_LD + vbase + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
+            ldsm_x4_t(smem_u32(&vsrc[kk * V_LD + half * 64 + ntp * 16 + (lane >> 4) * 8]), b0, b1, b2, b3);
             mma16816(acc[2 * ntp], a, b0, b1);
             mma16816(acc[2 * ntp + 1], a, b2, b3);
           }
@@ -427,6 +451,14 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     }
   }
   PTR(7);
+  // publish the chunk: every image store of this CTA happens-before the flag (bar.sync, then a gpu-scope
+  // fence by the publishing thread); the proxy fence orders them for the scan's bulk-copy (async proxy) reads
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ws.ready + ch), "r"(1u) : "memory");
+  }
 }
 
 }  // namespace
@@ -452,9 +484,9 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    resident = 2 * sms;
+    resident = 3 * sms;
   }
-  dim3 grid(gdn_num_chunks(T), H, B);
+  dim3 grid((unsigned)gdn_num_chunks(T) * (unsigned)H, 1, B);
   gdn_prep_kernel<<<grid, PREP_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
       static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, T, H, scale, l2norm,

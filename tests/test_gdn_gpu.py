@@ -116,6 +116,46 @@ def test_split_scan_is_bit_identical_at_full_size(ops):
     assert err_ratio(ro, o[:, T - tail:].float().cpu()) < TOL_O and err_ratio(rs, s.cpu()) < TOL_S
 
 
+@pytest.mark.parametrize("T,H", [(2048, 16), (4160, 4), (100, 2)])
+def test_overlapped_and_sliced_variants_are_bit_identical(ops, monkeypatch, T, H):
+    """ivl_gdn_chunk_fwd either runs prep then scan on the caller's stream or overlaps them on two streams
+    (the scan following prep's per-chunk ready flags), and the scan owns 32, 64 or 128 value columns per CTA.
+    The arithmetic per value column is the same in every form, so all of them must agree bit for bit, under
+    CUDA-graph replay too."""
+    q, k, v, g, beta, h0 = _cuda(gdn_inputs(T=T, H=H, seed=3))
+    ro, rs = gdn_chunk_ref(*(x.cpu() for x in (q, k, v, g, beta)), initial_state=h0.cpu())
+    outs = {}
+    for pipe in (0, 1):
+        for bv in (32, 64, 128):
+            monkeypatch.setenv("IVL_GDN_PIPE", str(pipe))
+            monkeypatch.setenv("IVL_GDN_BV", str(bv))
+            outs[(pipe, bv)] = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                                          use_qk_l2norm_in_kernel=True)
+    torch.cuda.synchronize()
+    o0, s0 = outs[(0, 32)]
+    assert err_ratio(ro, o0.float().cpu()) < TOL_O and err_ratio(rs, s0.cpu()) < TOL_S
+    for key, (o, s) in outs.items():
+        assert torch.equal(o, o0) and torch.equal(s, s0), key
+    # the overlapped form inside a captured graph: the second stream is forked from and joined to the capture
+    monkeypatch.setenv("IVL_GDN_PIPE", "1")
+    monkeypatch.setenv("IVL_GDN_BV", "64")
+    ops.gdn_workspace(1, T, H, q.device)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.gdn_workspace(1, T, H, q.device)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=side):
+            og, sg = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                                use_qk_l2norm_in_kernel=True)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):
+        og.zero_(); sg.zero_()
+        gr.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(og, o0) and torch.equal(sg, s0)
+
+
 def test_chunk_then_recurrent_streaming(ops):
     """Prefill 300 tokens with the chunk kernel, then decode 8 tokens one at a time in place."""
     q, k, v, g, beta, h0 = gdn_inputs(T=308, H=4, seed=51)
