@@ -47,6 +47,8 @@ extern "C" {
 /* Library identification; also the cheapest "does the .so load" check. */
 IVL_API int ivl_abi_version(void);
 IVL_API const char* ivl_strerror(int code);
+/* After IVL_ERR_LAUNCH: the CUDA runtime call that failed and its error text (per calling thread). */
+IVL_API const char* ivl_last_cuda_error(void);
 
 /* ------------------------------------------------------------------------------------
  * Gated DeltaNet, chunked prefill (T > 64 in the model, any T >= 1 here).

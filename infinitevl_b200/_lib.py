@@ -11,6 +11,7 @@ from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libivl_b200.so")
 
+IVL_ERR_LAUNCH = -5
 IVL_DTYPE_F32 = 0
 IVL_DTYPE_BF16 = 1
 
@@ -20,6 +21,7 @@ _lib = None
 SIGNATURES = {
     "ivl_abi_version": (c_int, []),
     "ivl_strerror": (c_char_p, [c_int]),
+    "ivl_last_cuda_error": (c_char_p, []),
     "ivl_gdn_chunk_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ivl_gdn_chunk_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
                           + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
@@ -63,5 +65,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
 
 def check(code: int, what: str) -> None:
     if code != 0:
-        msg = load().ivl_strerror(code).decode()
-        raise IvlError(f"{what} failed: {msg} (code {code})")
+        lib = load()
+        msg = lib.ivl_strerror(code).decode()
+        detail = lib.ivl_last_cuda_error().decode() if code == IVL_ERR_LAUNCH else ""
+        raise IvlError(f"{what} failed: {msg} (code {code})" + (f": {detail}" if detail else ""))

@@ -469,16 +469,28 @@ extern "C" __attribute__((visibility("default"))) int ivl_debug_read_prep_trace(
 }
 #endif
 
+// Loads the kernel and raises its shared-memory limit (once per device).  The overlapped chunk operator calls
+// this BEFORE it launches the scan: with lazy module loading the first launch of a kernel can block on the
+// kernels already running, and a running scan is waiting for this very kernel.
+cudaError_t configure_gdn_prep() {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!configured[dev]) {
+    e = cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  return cudaSuccess;
+}
+
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                             const GdnWorkspace& ws, int B, int T, int H, float scale, int l2norm,
                             cudaStream_t stream) {
-  static bool configured = false;
   const int smem = (int)sizeof(PrepSmem);
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = configure_gdn_prep()) return e;
   static int resident = 0;
   if (resident == 0) {
     int dev = 0, sms = 148;

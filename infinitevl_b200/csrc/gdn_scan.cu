@@ -381,11 +381,14 @@ template <int BV>
 cudaError_t launch_scan_variant(const GdnWorkspace& ws, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype,
                                 int B, int T, int H, cudaStream_t stream) {
   using C = ScanCfg<BV>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gdn_scan_kernel<BV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   dim3 grid(GDN_V / BV, H, B);
   gdn_scan_kernel<BV><<<grid, C::THREADS, C::SMEM, stream>>>(ws, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,
