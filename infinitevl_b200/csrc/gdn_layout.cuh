@@ -6,22 +6,30 @@
 // sm100.cuh).  The scan kernel then only issues 1-D bulk copies (TMA engine)
 // into its pipeline stages -- no layout work on the serial path.
 //
-//   blob[b][h][c] (BLOB_BYTES = 56 KiB, contiguous):
+//   blob[b][h][slot] (BLOB_BYTES = 56 KiB + 128 B, contiguous; slot = c mod ring):
 //     A1  image 32 KiB   K-major operand [-Wg ; Qg]  (128 rows x 128 k)
 //                        Wg = A (beta Kn exp(G)),  Qg = Qn exp(G) scale
 //     P   image  8 KiB   rows 64..127 of the K-major operand [0 ; P],  P = tril(Qn Kn^T * Gamma) * scale
 //     Kt  image 16 KiB   MN-major operand Kt^T (M = 128 key dims, K = 64 tokens), Kt = Kn exp(G_C - G)
-//                        (P and Kt are adjacent: the scan fetches them with one copy, A1 with another,
-//                         because their shared-memory slots are recycled at different times)
-//   ublob[b][h][c][s] (4 KiB each, s = V slice of 32 columns): U = A (beta V), laid out
+//     tail        128 B   fp32 gamma = exp(G_C), the whole-chunk decay, in the first 4 bytes
+//                        (P, Kt and the tail are adjacent: the scan fetches them with one copy, A1 with
+//                         another, because their shared-memory slots are recycled at different times;
+//                         gamma travels with the operands so that the scan never reads it before the
+//                         chunk is published)
+//   ublob[b][h][slot][s] (4 KiB each, s = V slice of 32 columns): U = A (beta V), laid out
 //                        [piece p of 8 columns][token][8] so that a thread owning a token
 //                        row reads four conflict-free 16-byte pieces.
-//   gamma[b][h][c]      fp32 exp(G_C), the whole-chunk decay.
 //   ready[b][h][c]      uint32 flag, zeroed by the host entry point before the launch and set to 1
 //                       (release, gpu scope) by the prep CTA once every image of the chunk is written.
 //                       The scan's copy warp polls it (acquire), so the two kernels can run
 //                       concurrently: prep walks the sequence front to back over all heads, the scan
 //                       follows a few chunks behind and finds the images still in L2.
+//   progress[b][h][8]   uint32, zeroed with the flags: number of chunks scan CTA s of the head has fully
+//                       consumed.  In the overlapped form the images live in a RING of `ring` chunk slots
+//                       per head: the prep CTA of chunk c waits until every scan CTA of its head has
+//                       consumed chunk c - ring before it overwrites the slot.  A ring of a few dozen
+//                       chunks stays resident in the 126 MB L2, so the images never travel to HBM.
+//                       Back to back (ring = number of chunks) nothing waits.
 //
 // K-major no-swizzle image of an [R rows][Kd] bf16 matrix: 8x8 "core matrices" of
 // 128 contiguous bytes (8 rows x 16 B); core (rg, kg) at rg * (Kd/8)*128 + kg * 128.
@@ -45,39 +53,49 @@ constexpr int GDN_NS = GDN_V / GDN_BV;  // U sub-slices per head
 constexpr uint32_t P_BYTES = 64 * 64 * 2;        // 8 KiB
 constexpr uint32_t A1_BYTES = 128 * 128 * 2;     // 32 KiB
 constexpr uint32_t KT_BYTES = 128 * 64 * 2;      // 16 KiB
-constexpr uint32_t BLOB_BYTES = P_BYTES + A1_BYTES + KT_BYTES;  // 56 KiB
+constexpr uint32_t TAIL_BYTES = 128;             // gamma (fp32) + padding
+constexpr uint32_t BLOB_BYTES = P_BYTES + A1_BYTES + KT_BYTES + TAIL_BYTES;  // 56 KiB + 128 B
 constexpr uint32_t UBLOB_BYTES = 64 * GDN_BV * 2;               // 4 KiB
 
 constexpr uint32_t BLOB_OFF_A1 = 0;
 constexpr uint32_t BLOB_OFF_P = A1_BYTES;
 constexpr uint32_t BLOB_OFF_KT = A1_BYTES + P_BYTES;
+constexpr uint32_t BLOB_OFF_TAIL = A1_BYTES + P_BYTES + KT_BYTES;
 
 struct GdnWorkspace {
-  uint8_t* blob;    // [B][H][NT][BLOB_BYTES]
-  uint8_t* ublob;   // [B][H][NT][NS][UBLOB_BYTES]
-  float* gamma;     // [B][H][NT]
-  uint32_t* ready;  // [B][H][NT]
+  uint8_t* blob;       // [B][H][ring][BLOB_BYTES]
+  uint8_t* ublob;      // [B][H][ring][NS][UBLOB_BYTES]
+  uint32_t* ready;     // [B][H][NT]
+  uint32_t* progress;  // [B][H][GDN_NS]
+  int ring;            // chunk slots per head (<= NT)
 };
 
 __host__ __device__ inline int gdn_num_chunks(int T) { return (T + GDN_C - 1) / GDN_C; }
 
+// flags + progress counters (one memset), rounded to 1 KiB; they sit at the FRONT of the workspace so that
+// their address does not depend on the ring length
+__host__ inline size_t gdn_sync_bytes(int B, int T, int H) {
+  size_t n = (size_t)B * H * (gdn_num_chunks(T) + GDN_NS) * sizeof(uint32_t);
+  return (n + 1023) / 1024 * 1024;
+}
+
+// Sized for the back-to-back form (one slot per chunk); the overlapped form uses a prefix of it.
 __host__ inline size_t gdn_workspace_bytes(int B, int T, int H) {
   size_t n = (size_t)B * H * gdn_num_chunks(T);
-  size_t gamma = (n * sizeof(float) + 1023) / 1024 * 1024;
-  return n * BLOB_BYTES + n * GDN_NS * UBLOB_BYTES + 2 * gamma;
+  return gdn_sync_bytes(B, T, H) + n * (BLOB_BYTES + GDN_NS * UBLOB_BYTES);
 }
 
-__host__ inline size_t gdn_ready_bytes(int B, int T, int H) {
-  return (size_t)B * H * gdn_num_chunks(T) * sizeof(uint32_t);
-}
-
-__host__ inline GdnWorkspace gdn_carve(void* ws, int B, int T, int H) {
-  size_t n = (size_t)B * H * gdn_num_chunks(T);
+// ring: chunk slots per head, clamped to [1, NT]
+__host__ inline GdnWorkspace gdn_carve(void* ws, int B, int T, int H, int ring) {
+  const int NT = gdn_num_chunks(T);
+  if (ring <= 0 || ring > NT) ring = NT;
+  size_t n = (size_t)B * H * ring;
   GdnWorkspace w;
-  w.blob = static_cast<uint8_t*>(ws);
-  w.ublob = w.blob + n * BLOB_BYTES;
-  w.gamma = reinterpret_cast<float*>(w.ublob + n * GDN_NS * UBLOB_BYTES);
-  w.ready = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(w.gamma) + (n * sizeof(float) + 1023) / 1024 * 1024);
+  w.ready = static_cast<uint32_t*>(ws);
+  w.progress = w.ready + (size_t)B * H * NT;
+  w.blob = static_cast<uint8_t*>(ws) + gdn_sync_bytes(B, T, H);
+  w.ublob = w.blob + n * BLOB_BYTES;   // n * 57472 keeps 128-byte alignment
+  w.ring = ring;
   return w;
 }
 

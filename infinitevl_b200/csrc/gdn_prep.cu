@@ -112,6 +112,13 @@ __device__ __forceinline__ void norm_row_quarter(const uint4* raw, bool l2norm, 
 
 #ifdef IVL_TRACE
 __device__ long long ivl_prep_trace[16 * 8];
+__device__ unsigned long long ivl_prep_wait[4];  // cycles waited on the ring, CTAs that waited, poll iterations
+__device__ unsigned long long ivl_prep_tl[16 * 2048 * 4];  // head 0, chunk c: globaltimer at CTA start, after the ring wait, at publish
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define PTR(slot)                                                                     \
   do {                                                                                \
     if (blockIdx.x >= 16000 && blockIdx.x < 16016 && threadIdx.x == 0)                \
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 3)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
                 const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, int T, int H, float scale,
-                int l2norm, int prefetch_ahead) {
+                int l2norm, int prefetch_ahead, int scan_ctas_per_head) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
   float* const sL = s.LA;                                                  // strictly lower triangular, fp32
@@ -138,10 +145,14 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   const int t0 = c * GDN_C;
   const int valid = min(GDN_C, T - t0);
   const size_t tok0 = (size_t)b * T + t0;
-  const size_t ch = ((size_t)b * H + h) * NT + c;  // chunk-head index
-  uint8_t* blob = ws.blob + ch * BLOB_BYTES;
-  uint8_t* ublob = ws.ublob + ch * (GDN_NS * UBLOB_BYTES);
+  const size_t ch = ((size_t)b * H + h) * NT + c;  // chunk-head index (ready flag)
+  const size_t slot = ((size_t)b * H + h) * ws.ring + (c % ws.ring);  // where its images live
+  uint8_t* blob = ws.blob + slot * BLOB_BYTES;
+  uint8_t* ublob = ws.ublob + slot * (GDN_NS * UBLOB_BYTES);
 
+#ifdef IVL_TRACE
+  if (tid == 0 && h < 16 && c < 2048) ivl_prep_tl[(h * 2048 + c) * 4 + 0] = gtime();
+#endif
   PTR(0);
   // ---- stage 0: issue every global load of the chunk up front (q, k rows into registers, V by cp.async,
   //      g / beta), then the chunk-local cumsum of g ------------------------------------------------
@@ -196,7 +207,41 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     s.beta[lane] = (lane < valid) ? __bfloat162float(beta[(tok0 + lane) * H + h]) : 0.f;
     s.beta[lane + 32] = (lane + 32 < valid) ? __bfloat162float(beta[(tok0 + lane + 32) * H + h]) : 0.f;
   }
+  if (warp == 1 && c >= ws.ring) {
+    // Ring hand-off (overlapped form only): the slot still holds chunk c - ring until every scan CTA of this
+    // head has consumed it.  CTAs are dispatched in chunk order, so everything the scan is waiting for is
+    // resident or done and this wait cannot deadlock; it is normally already satisfied.
+    const uint32_t need = (uint32_t)(c - ws.ring + 1);
+#ifdef IVL_TRACE
+    const long long tw0 = clock64();
+#endif
+    const uint32_t* prog = ws.progress + ((size_t)b * H + h) * GDN_NS;
+    long long spins = 0;
+    for (;;) {
+      uint32_t pv = 0xffffffffu;
+      // relaxed polls (an acquire load costs an L1 invalidate per iteration), one acquire fence at the end
+      if (lane < scan_ctas_per_head)
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pv) : "l"(prog + lane) : "memory");
+      if (__all_sync(0xffffffffu, pv >= need)) break;
+      // back off in proportion to the distance (a scan step is ~1.2 us): frequent polls of the one line the
+      // scan's copy warps keep writing were measured to slow the SCAN down by 2x
+      const uint32_t behind = need - __reduce_min_sync(0xffffffffu, pv);
+      __nanosleep(behind > 16 ? 16000 : behind * 1000);
+      if (++spins > (1ll << 23)) asm volatile("trap;");  // the scan is not running: fail loudly, do not hang
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#ifdef IVL_TRACE
+    if (lane == 0) {
+      atomicAdd(&ivl_prep_wait[0], (unsigned long long)(clock64() - tw0));
+      atomicAdd(&ivl_prep_wait[1], 1ull);
+      atomicAdd(&ivl_prep_wait[2], (unsigned long long)spins);
+    }
+#endif
+  }
   __syncthreads();
+#ifdef IVL_TRACE
+  if (tid == 0 && h < 16 && c < 2048) ivl_prep_tl[(h * 2048 + c) * 4 + 1] = gtime();
+#endif
   PTR(1);
 
   // ---- stage 1: normalise q, k rows; emit Qg and Kt images --------------------------------
@@ -212,7 +257,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
                      blob + BLOB_OFF_KT, [&](int p) {
                        return (uint32_t)((qt * 4 + p) * 1024 + (row >> 3) * 128 + (row & 7) * 16);
                      });
-    if (tid == 0) ws.gamma[ch] = __expf(Gc);
+    if (tid == 0) *reinterpret_cast<float*>(blob + BLOB_OFF_TAIL) = __expf(Gc);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -452,13 +497,14 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   }
   PTR(7);
   // publish the chunk: every image store of this CTA happens-before the flag (bar.sync, then a gpu-scope
-  // fence by the publishing thread); the proxy fence orders them for the scan's bulk-copy (async proxy) reads
+  // release by the publishing thread -- the split-K semaphore pattern).  The consumer pairs it with an acquire
+  // and a proxy fence before its bulk copies (async proxy) read the images.
   __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    asm volatile("fence.proxy.async;" ::: "memory");
+  if (tid == 0)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ws.ready + ch), "r"(1u) : "memory");
-  }
+#ifdef IVL_TRACE
+  if (tid == 0 && h < 16 && c < 2048) ivl_prep_tl[(h * 2048 + c) * 4 + 2] = gtime();
+#endif
 }
 
 }  // namespace
@@ -466,6 +512,14 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
 #ifdef IVL_TRACE
 extern "C" __attribute__((visibility("default"))) int ivl_debug_read_prep_trace(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, ivl_prep_trace, sizeof(long long) * n);
+}
+extern "C" __attribute__((visibility("default"))) int ivl_debug_read_prep_tl(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, ivl_prep_tl, sizeof(unsigned long long) * 16 * 2048 * 4);
+}
+extern "C" __attribute__((visibility("default"))) int ivl_debug_read_prep_wait(unsigned long long* host, int reset) {
+  int e = (int)cudaMemcpyFromSymbol(host, ivl_prep_wait, sizeof(unsigned long long) * 4);
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(ivl_prep_wait, z, sizeof(z)); }
+  return e;
 }
 #endif
 
@@ -486,9 +540,11 @@ cudaError_t configure_gdn_prep() {
   return cudaSuccess;
 }
 
+// scan_ctas_per_head: number of scan CTAs per head whose progress counters gate the ring (ignored when the
+// ring holds every chunk)
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                             const GdnWorkspace& ws, int B, int T, int H, float scale, int l2norm,
-                            cudaStream_t stream) {
+                            int scan_ctas_per_head, cudaStream_t stream) {
   const int smem = (int)sizeof(PrepSmem);
   if (cudaError_t e = configure_gdn_prep()) return e;
   static int resident = 0;
@@ -502,7 +558,7 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
   gdn_prep_kernel<<<grid, PREP_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
       static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, T, H, scale, l2norm,
-      resident);
+      resident, scan_ctas_per_head);
   return cudaGetLastError();
 }
 

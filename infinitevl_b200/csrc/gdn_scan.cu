@@ -36,7 +36,7 @@ namespace {
 //
 // Shared memory: two operand rings that are recycled at different points of a step --
 //   A ring  (NA slots of 32 KiB): [-Wg ; Qg], free as soon as MMA-A has retired (early in the step)
-//   K ring  (NK slots): [8 KiB of zeros | P | Kt | U slice], free after MMA-C (end of the step)
+//   K ring  (NK slots): [8 KiB of zeros | P | Kt | gamma | U slice], free after MMA-C (end of the step)
 // -- so a two-slot K ring still gives the A operand more than a full step of prefetch distance.
 template <int BV>
 struct ScanCfg {
@@ -50,8 +50,9 @@ struct ScanCfg {
   static constexpr uint32_t KS_OFF_Z = 0;                      // rows 0..63 of the [0 ; P] operand, zeroed once
   static constexpr uint32_t KS_OFF_P = P_BYTES;                // P | Kt land here with one copy
   static constexpr uint32_t KS_OFF_KT = 2 * P_BYTES;
-  static constexpr uint32_t KS_OFF_U = 2 * P_BYTES + KT_BYTES;
-  static constexpr uint32_t KSLOT = KS_OFF_U + U_BYTES;
+  static constexpr uint32_t KS_OFF_TAIL = 2 * P_BYTES + KT_BYTES;   // gamma of the chunk (first 4 bytes)
+  static constexpr uint32_t KS_OFF_U = KS_OFF_TAIL + TAIL_BYTES;
+  static constexpr uint32_t KSLOT = KS_OFF_U + U_BYTES + (1024 - TAIL_BYTES);
   static constexpr uint32_t OFF_A = 0;
   static constexpr uint32_t OFF_K = NA * A1_BYTES;
   static constexpr uint32_t SB_BYTES = 128 * BV * 2;           // bf16 shadow of S, MN-major B operand
@@ -71,6 +72,8 @@ struct ScanCfg {
 // Developer-only timeline probe (compiled in with -DIVL_TRACE by tools/trace_scan.py; never in the product build)
 #ifdef IVL_TRACE
 __device__ long long ivl_trace_buf[64 * 16];
+__device__ unsigned long long ivl_scan_wait[4];  // copy-warp cycles spent waiting for ready flags, polls, spins
+__device__ unsigned long long ivl_scan_tl[16 * 2048 * 4];  // head 0: globaltimer when the copy warp of slice s issued chunk c
 #define TR(slot)                                                                                         \
   do {                                                                                                   \
     if (tr_on && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && c >= 1000 && c < 1064)               \
@@ -99,9 +102,9 @@ __device__ __forceinline__ void store_row_bf16(uint8_t* base, uint32_t piece_str
   }
 }
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -115,10 +118,11 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
   Bars& bars = *reinterpret_cast<Bars*>(smem + C::OFF_BARS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const size_t ch0 = ((size_t)b * H + h) * NT;
-  const uint8_t* blob = ws.blob + ch0 * BLOB_BYTES;
-  const uint8_t* ublob = ws.ublob + (ch0 * GDN_NS + slice * C::NCG) * UBLOB_BYTES;
-  const float* gamma = ws.gamma + ch0;
+  const size_t ch0 = ((size_t)b * H + h) * NT;         // first ready flag of this head
+  const size_t slot0 = ((size_t)b * H + h) * ws.ring;  // first image slot of this head; chunk c lives in c % ring
+  const int ring = ws.ring;
+  const uint8_t* blob = ws.blob + slot0 * BLOB_BYTES;
+  const uint8_t* ublob = ws.ublob + (slot0 * GDN_NS + slice * C::NCG) * UBLOB_BYTES;
 
   if (tid == 0) {
     for (int s = 0; s < 3; ++s) {
@@ -156,13 +160,17 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
     // Chunk c may be fetched once gdn_prep_kernel has published it (ws.ready, see gdn_layout.cuh).  The
     // 32 lanes look at 32 flags at a time, so a scan that runs behind prep polls once per 32 chunks.
     const uint32_t* ready = ws.ready + ch0;
+    uint32_t* progress = ws.progress + ((size_t)b * H + h) * GDN_NS + slice;
     int known = 0;  // chunks [0, known) are published
     for (int c = 0; c < NT; ++c) {
       if (c >= known) {
         long long spins = 0;
+#ifdef IVL_TRACE
+        const long long tw0 = clock64();
+#endif
         do {
           const int idx = known + lane;
-          const uint32_t f = (idx < NT) ? ld_acquire_gpu(ready + idx) : 0u;
+          const uint32_t f = (idx < NT) ? ld_relaxed_gpu(ready + idx) : 0u;
           const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
           known += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
           if (c >= known) {
@@ -170,18 +178,42 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
             if (++spins > (1ll << 24)) asm volatile("trap;");  // prep never ran: fail loudly instead of hanging
           }
         } while (c >= known);
+        // relaxed polls, then one acquire fence (pairs with prep's release) and the generic -> async proxy fence
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
+#ifdef IVL_TRACE
+        if (lane == 0) {
+          atomicAdd(&ivl_scan_wait[0], (unsigned long long)(clock64() - tw0));
+          atomicAdd(&ivl_scan_wait[1], 1ull);
+          atomicAdd(&ivl_scan_wait[2], (unsigned long long)spins);
+        }
+#endif
       }
       const int sa = c % C::NA, sk = c % C::NK;
+      const size_t cs = (size_t)(c % ring);  // image slot of chunk c
+#ifdef IVL_TRACE
+      if (lane == 0 && h < 16 && c < 2048 && slice < 4) {
+        unsigned long long tg;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tg));
+        ivl_scan_tl[(h * 2048 + c) * 4 + slice] = tg;
+      }
+#endif
       if (c >= C::NA) mbar_wait(&bars.emptyA[sa], (c / C::NA - 1) & 1);
       mbar_arrive_expect_tx_ws(&bars.fullA[sa], A1_BYTES);
-      bulk_g2s_ws(smem + C::OFF_A + sa * A1_BYTES, blob + (size_t)c * BLOB_BYTES + BLOB_OFF_A1, A1_BYTES,
-                  &bars.fullA[sa]);
-      if (c >= C::NK) mbar_wait(&bars.emptyK[sk], (c / C::NK - 1) & 1);
+      bulk_g2s_ws(smem + C::OFF_A + sa * A1_BYTES, blob + cs * BLOB_BYTES + BLOB_OFF_A1, A1_BYTES, &bars.fullA[sa]);
+      if (c >= C::NK) {
+        mbar_wait(&bars.emptyK[sk], (c / C::NK - 1) & 1);
+        // every MMA that read chunk c - NK has retired (the A slot of that chunk was released even earlier), so
+        // its image slot may be overwritten: tell prep (the ring hand-off of gdn_layout.cuh)
+        // (relaxed is enough: the copies out of that slot have COMPLETED -- this warp saw their mbarrier -- and
+        //  a release here would make the copy warp wait for its own outstanding bulk copies every chunk)
+        if (lane == 0 && ring < NT)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(c - C::NK + 1)) : "memory");
+      }
       uint8_t* ks = smem + C::OFF_K + sk * C::KSLOT;
-      mbar_arrive_expect_tx_ws(&bars.fullK[sk], P_BYTES + KT_BYTES + C::U_BYTES);
-      bulk_g2s_ws(ks + C::KS_OFF_P, blob + (size_t)c * BLOB_BYTES + BLOB_OFF_P, P_BYTES + KT_BYTES, &bars.fullK[sk]);
-      bulk_g2s_ws(ks + C::KS_OFF_U, ublob + (size_t)c * (GDN_NS * UBLOB_BYTES), C::U_BYTES, &bars.fullK[sk]);
+      mbar_arrive_expect_tx_ws(&bars.fullK[sk], P_BYTES + KT_BYTES + TAIL_BYTES + C::U_BYTES);
+      bulk_g2s_ws(ks + C::KS_OFF_P, blob + cs * BLOB_BYTES + BLOB_OFF_P, P_BYTES + KT_BYTES + TAIL_BYTES, &bars.fullK[sk]);
+      bulk_g2s_ws(ks + C::KS_OFF_U, ublob + cs * (GDN_NS * UBLOB_BYTES), C::U_BYTES, &bars.fullK[sk]);
     }
   } else if (warp <= C::NCG) {
     // ------------------------------- MMA issuers (one warp per chain) -----------------
@@ -272,7 +304,7 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
       mbar_wait(&bars.fullK[0], 0);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sb);
-      const float g0 = __ldg(gamma);
+      const float g0 = *reinterpret_cast<const float*>(smem + C::OFF_K + C::KS_OFF_TAIL);  // slot 0 has landed
 #pragma unroll
       for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(x[i] * g0);
       tmem_st32(tlane + C::TM_S, r);
@@ -284,7 +316,6 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
 
     for (int c = 0; c < NT; ++c) {
       const int sk = c % C::NK, buf = c & 1;
-      const float gnext = (c + 1 < NT) ? __ldg(gamma + c + 1) : 1.f;
       if (is_vn) {
         // v_new = U - Wg S   (A1 holds -Wg, so the accumulator is added)
         // (the K slot of chunk c was awaited in the S hand-over of chunk c-1)
@@ -316,9 +347,11 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
       }
       // state hand-over: S_{c+1} is complete once MMA-B has retired.  While waiting for it, make sure the
       // next chunk's operands have landed (off the critical path here, and it spares the MMA warp a wait).
+      float gnext = 1.f;
       if (c + 1 < NT) {
         mbar_wait(&bars.fullA[(c + 1) % C::NA], ((c + 1) / C::NA) & 1);
         mbar_wait(&bars.fullK[(c + 1) % C::NK], ((c + 1) / C::NK) & 1);
+        gnext = *reinterpret_cast<const float*>(smem + C::OFF_K + ((c + 1) % C::NK) * C::KSLOT + C::KS_OFF_TAIL);
       }
       mbar_wait(bar_s, c & 1);
       tc_fence_after();
@@ -412,6 +445,14 @@ cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const void* h0, int h0_dtype
 #ifdef IVL_TRACE
 extern "C" __attribute__((visibility("default"))) int ivl_debug_read_trace(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, ivl_trace_buf, sizeof(long long) * n);
+}
+extern "C" __attribute__((visibility("default"))) int ivl_debug_read_scan_tl(unsigned long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, ivl_scan_tl, sizeof(unsigned long long) * 16 * 2048 * 4);
+}
+extern "C" __attribute__((visibility("default"))) int ivl_debug_read_scan_wait(unsigned long long* host, int reset) {
+  int e = (int)cudaMemcpyFromSymbol(host, ivl_scan_wait, sizeof(unsigned long long) * 4);
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(ivl_scan_wait, z, sizeof(z)); }
+  return e;
 }
 #endif
 

@@ -119,26 +119,36 @@ def test_split_scan_is_bit_identical_at_full_size(ops):
 @pytest.mark.parametrize("T,H", [(2048, 16), (4160, 4), (100, 2)])
 def test_overlapped_and_sliced_variants_are_bit_identical(ops, monkeypatch, T, H):
     """ivl_gdn_chunk_fwd either runs prep then scan on the caller's stream or overlaps them on two streams
-    (the scan following prep's per-chunk ready flags), and the scan owns 32, 64 or 128 value columns per CTA.
-    The arithmetic per value column is the same in every form, so all of them must agree bit for bit, under
-    CUDA-graph replay too."""
-    q, k, v, g, beta, h0 = _cuda(gdn_inputs(T=T, H=H, seed=3))
-    ro, rs = gdn_chunk_ref(*(x.cpu() for x in (q, k, v, g, beta)), initial_state=h0.cpu())
-    outs = {}
-    for pipe in (0, 1):
-        for bv in (32, 64, 128):
-            monkeypatch.setenv("IVL_GDN_PIPE", str(pipe))
-            monkeypatch.setenv("IVL_GDN_BV", str(bv))
-            outs[(pipe, bv)] = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
-                                                          use_qk_l2norm_in_kernel=True)
-    torch.cuda.synchronize()
-    o0, s0 = outs[(0, 32)]
-    assert err_ratio(ro, o0.float().cpu()) < TOL_O and err_ratio(rs, s0.cpu()) < TOL_S
-    for key, (o, s) in outs.items():
-        assert torch.equal(o, o0) and torch.equal(s, s0), key
+    (the scan following prep's per-chunk ready flags, prep following the scan's progress through a ring of
+    image slots), and the scan owns 32, 64 or 128 value columns per CTA.  The arithmetic per value column is
+    the same in every form, so all of them must agree bit for bit, under CUDA-graph replay too.  Every form
+    gets fresh inputs in the same (cached) workspace, so an image or gamma read before it was published, or a
+    ring slot overwritten too early, shows up as a mismatch."""
+    seed = 3
+    for pipe, bv, ring in ((1, 64, 32), (1, 128, 8), (1, 32, 9), (0, 64, 0), (0, 128, 0), (1, 64, 8)):
+        seed += 1
+        q, k, v, g, beta, h0 = _cuda(gdn_inputs(T=T, H=H, seed=seed))
+        monkeypatch.setenv("IVL_GDN_PIPE", "0")
+        monkeypatch.setenv("IVL_GDN_BV", "32")
+        o0, s0 = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                            use_qk_l2norm_in_kernel=True)
+        if seed == 4:
+            ro, rs = gdn_chunk_ref(*(x.cpu() for x in (q, k, v, g, beta)), initial_state=h0.cpu())
+            assert err_ratio(ro, o0.float().cpu()) < TOL_O and err_ratio(rs, s0.cpu()) < TOL_S
+        # poison the workspace images with another problem's data before the form under test runs
+        q2, k2, v2, g2, beta2, _ = _cuda(gdn_inputs(T=T, H=H, seed=seed + 100))
+        ops.chunk_gated_delta_rule(q2, k2, v2, g2, beta2, output_final_state=True, use_qk_l2norm_in_kernel=True)
+        monkeypatch.setenv("IVL_GDN_PIPE", str(pipe))
+        monkeypatch.setenv("IVL_GDN_BV", str(bv))
+        monkeypatch.setenv("IVL_GDN_RING", str(ring))
+        o, s = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                          use_qk_l2norm_in_kernel=True)
+        torch.cuda.synchronize()
+        assert torch.equal(o, o0) and torch.equal(s, s0), (pipe, bv, ring)
     # the overlapped form inside a captured graph: the second stream is forked from and joined to the capture
     monkeypatch.setenv("IVL_GDN_PIPE", "1")
     monkeypatch.setenv("IVL_GDN_BV", "64")
+    monkeypatch.setenv("IVL_GDN_RING", "16")
     ops.gdn_workspace(1, T, H, q.device)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
