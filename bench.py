@@ -31,9 +31,10 @@ H, K, V = 16, 128, 256
 HQ, HKV, D, WINDOW = 16, 2, 128, 8192
 GDN_BYTES_PER_TOKEN = 24672          # q,k,v,g,beta read + o written, per token per layer
 GDN_STATE_BYTES = 2 * H * K * V * 4  # h0 read + hT written, per sequence per layer
-# dram__bytes_read.sum + dram__bytes_write.sum of gdn_prep_kernel + gdn_scan_kernel at T = 131072, one launch each,
-# from the committed ncu capture (profiles/); refreshed whenever the kernels change
-GDN_DRAM_TRAFFIC_NCU = 10.99e9
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE overlapped ivl_gdn_chunk_fwd call at T = 131072 (prep + scan
+# running concurrently), from the committed ncu range-replay capture profiles/r01e_range_overlapped.csv
+# (5 407 097 088 read + 4 011 054 080 written); refreshed whenever the kernels change
+GDN_DRAM_TRAFFIC_NCU = 9418151168
 
 
 def swa_flops(T, Tk_prefix=0):
@@ -288,9 +289,9 @@ def run_ours(args):
                 "kernel": "gdn_chunk = gdn_prep_kernel + gdn_scan_kernel (one GDN layer; "
                           + ("overlapped on two streams, timed as one operator call" if world == 1 else "back to back") + ")",
                 "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": GDN_DRAM_TRAFFIC_NCU if T_local == 131072 else None,
-                "traffic_note": "ncu dram bytes of the two kernels profiled back to back (ncu serialises kernels, so the "
-                                "overlapped form cannot be profiled); see profiles/",
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": GDN_DRAM_TRAFFIC_NCU if (T_local == 131072 and world == 1) else None,
+                "traffic_note": "ncu --replay-mode range over one overlapped operator call (kernel replay would serialise "
+                                "the two kernels); back to back the two kernels move 6.46 + 4.03 GB; see profiles/r01e_summary.md",
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg_bytes}
         kernels = {"gdn_layer_ms": round(t_layer, 4), "gdn_prep_alone_ms": round(t_prep, 4),
                    "gdn_scan_alone_ms": round(t_scan, 4)}
