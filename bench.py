@@ -190,15 +190,17 @@ class HotPath:
                 self.gdn_fwd(self.h0)
                 n += 2
                 continue
-            # sequence-sharded: prep does not depend on the incoming state, so it runs while the state of
-            # the previous rank is still in flight
+            # sequence-sharded: prep does not depend on the incoming state, so it runs while the state of the
+            # previous rank's segment is still in flight, then the scan has the GPU to itself.  (Receiving first and
+            # running the overlapped operator was measured slower at N = 2: 89.5 vs 80.4 ms per step -- the
+            # send/recv rendezvous then sits on the critical path of both ranks at every layer.)
             self.gdn_prep()
             h0 = self.h0
-            if self.world > 1 and self.rank > 0:
+            if self.rank > 0:
                 dist.recv(self.state_in, src=self.rank - 1)
                 h0 = self.state_in
             self.gdn_scan(h0)
-            if self.world > 1 and self.rank < self.world - 1:
+            if self.rank < self.world - 1:
                 dist.send(self.ht, dst=self.rank + 1)
             n += 2
         self.launches_per_step = n
@@ -304,12 +306,10 @@ def run_ours(args):
                 kernels["swa_frac_of_bf16_sustained"] = round(kernels["swa_tflops"] / peaks["bf16_tflops_sustained"], 4)
 
     # ---- end-to-end through the public operator API with HOST buffers ---------------------------
-    e2e = None
     decode = None
-    if world == 1:
-        e2e = run_e2e(hp, args)
-        if hp.has_swa:
-            decode = run_decode(dev, peaks)
+    e2e = run_e2e(hp, args, world, dev)
+    if world == 1 and hp.has_swa:
+        decode = run_decode(dev, peaks)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -383,9 +383,11 @@ def run_decode(dev, peaks, context=524288, steps=50):
                     "one CUDA graph; state size is independent of the context length"}
 
 
-def run_e2e(hp, args):
-    """Same step, but the step's inputs start in pinned host memory and the result is read back."""
-    T = hp.T
+def run_e2e(hp, args, world=1, dev=None):
+    """Same step, but the step's inputs start in pinned host memory and the result is read back
+    (every rank copies its own token range; max over ranks)."""
+    import torch.distributed as dist
+    T = hp.T * world
     host = {}
     names = ["q", "k", "v", "g", "beta"] + (["sq", "sk", "sv"] if hp.has_swa else [])
     for n in names:
@@ -400,18 +402,26 @@ def run_e2e(hp, args):
         hp.step()
         out_host.copy_(hp.o, non_blocking=True)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     e2e_step()
-    torch.cuda.synchronize()
+    barrier()
     steps = max(1, min(args.steps, 3))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
         e2e_step()
     b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / steps
-    return {"value": round(T / (ms * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": round(ms, 3), "steps": steps,
+    barrier()
+    ms_t = torch.tensor([a.elapsed_time(b) / steps], device=hp.dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = ms_t.item()
+    return {"value": round(T / (ms * 1e-3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d * world,
+            "d2h_bytes_per_step": d2h * world, "ms_per_step": round(ms, 3), "steps": steps,
             "api": "infinitevl_b200 C ABI (ivl_gdn_chunk_fwd" + (", ivl_swa_fwd" if hp.has_swa else "") + ") with pinned host buffers"}
 
 
