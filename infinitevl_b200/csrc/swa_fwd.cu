@@ -17,6 +17,9 @@
 // FP32x2 instructions of sm_100 (scale and max subtraction in one FFMA2, row sum in FADD2).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue.
 #include <cuda.h>
+#include <stdlib.h>
+
+#include <initializer_list>
 
 #include "sm100.cuh"
 
@@ -38,10 +41,17 @@ constexpr uint32_t SWA_SMEM = DATA_BYTES + 1024;   // barriers live in the align
 constexpr uint32_t TM_S = 0;      // 2 buffers x 64 columns
 constexpr uint32_t TM_O = 128;    // 128 columns
 constexpr uint32_t TM_COLS = 256;
+// Measured (tools/exp_swa_poly.py, B200 under its 1000 W cap): alone and hot, POLY = 3 is 6 % faster than 0
+// (8.24 vs 8.79 ms at 128K); inside the bench step the extra FMA work lowers the sustained clock (1597-1635 vs
+// 1650-1672 MHz) and the step does not get faster (150.9 / 151.4 vs 150.3 / 150.2 ms), so the default stays 0.
+constexpr int SWA_POLY_DEFAULT = 0;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: O is only rescaled when the row max grows by > 2^8
 
 struct Bars {
-  uint64_t full[2], empty[2], q, s[2], sfree[2], p, pv;
+  // K and V tiles travel in separate two-slot rings: a K slot is free as soon as S = Q K^T of its tile has
+  // retired (before that tile's softmax even starts), a V slot only after O += P V, so the K tile of tile t+2 is
+  // already in flight while tile t is still in the softmax
+  uint64_t fullK[2], emptyK[2], fullV[2], emptyV[2], q, s[2], sfree[2], p, pv;
   uint32_t tmem_base;
 };
 
@@ -53,6 +63,28 @@ struct SwaArgs {
   float scale_log2;            // softmax scale * log2(e)
 };
 
+// 2^x for a pair of values on the FMA pipe instead of the XU pipe (two MUFU.EX2): Cody-Waite range reduction
+// with the round-to-nearest magic constant, a degree-3 minimax polynomial on [-0.5, 0.5] (relative error 7.7e-5,
+// far below the bf16 rounding P gets anyway) and the integer part added to the exponent field.  x <= ~8 here
+// (lazy rescaling); masked scores (-inf) are clamped and come out as 2^-125 instead of 0, which no sum notices.
+__device__ __forceinline__ float2 exp2_fma_pair(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));        // 1.5 * 2^23: integer in the low bits
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);                  // x - round(x)
+  float2 p = __ffma2_rn(make_float2(0.05508868f, 0.05508868f), f, make_float2(0.24260405f, 0.24260405f));
+  p = __ffma2_rn(p, f, make_float2(0.69327623f, 0.69327623f));
+  p = __ffma2_rn(p, f, make_float2(0.99992895f, 0.99992895f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+
+// POLY: of every 8 pairs of exponentials, POLY are computed on the FMA pipe (exp2_fma_pair), the rest by MUFU.EX2.
+// With two CTAs per SM the two softmax warps that share a scheduler are XU-bound in their exponential phase
+// (64 MUFU x 8 issue cycles per tile and warp); moving part of them to the half-idle FMA pipe balances the two.
+template <int POLY>
 __global__ void __launch_bounds__(SWA_THREADS, 2)
 swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, SwaArgs a) {
@@ -73,7 +105,8 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars.full[i], 1); mbar_init(&bars.empty[i], 1);
+      mbar_init(&bars.fullK[i], 1); mbar_init(&bars.emptyK[i], 1);
+      mbar_init(&bars.fullV[i], 1); mbar_init(&bars.emptyV[i], 1);
       mbar_init(&bars.s[i], 1); mbar_init(&bars.sfree[i], 4);
     }
     mbar_init(&bars.q, 1); mbar_init(&bars.p, 4); mbar_init(&bars.pv, 1);
@@ -91,18 +124,31 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_arrive_expect_tx_ws(&bars.q, Q_BYTES);
     tma_load_4d_ws(smem + OFF_Q, &tmQ, 0, h, i0, b, &bars.q);
     tma_load_4d_ws(smem + OFF_Q + Q_BYTES / 2, &tmQ, 64, h, i0, b, &bars.q);
-    for (int t = 0; t < n_tiles; ++t) {
+    // order of the copies = order in which their slots come free: K(t) [after S(t-2)], then V(t-1) [after PV(t-3)]
+    auto load_k = [&](int t) {
       const int s = t & 1;
-      if (t >= 2) mbar_wait(&bars.empty[s], ((t >> 1) - 1) & 1);
+      if (t >= 2) mbar_wait(&bars.emptyK[s], ((t >> 1) - 1) & 1);
       const int j0 = (t_lo + t) * BN;
       uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
+      mbar_arrive_expect_tx_ws(&bars.fullK[s], KT_BYTES_);
+      tma_load_4d_ws(kd, &tmK, 0, hk, j0, b, &bars.fullK[s]);
+      tma_load_4d_ws(kd + KT_BYTES_ / 2, &tmK, 64, hk, j0, b, &bars.fullK[s]);
+    };
+    auto load_v = [&](int t) {
+      const int s = t & 1;
+      if (t >= 2) mbar_wait(&bars.emptyV[s], ((t >> 1) - 1) & 1);
+      const int j0 = (t_lo + t) * BN;
       uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
-      mbar_arrive_expect_tx_ws(&bars.full[s], 2 * KT_BYTES_);
-      tma_load_4d_ws(kd, &tmK, 0, hk, j0, b, &bars.full[s]);
-      tma_load_4d_ws(kd + KT_BYTES_ / 2, &tmK, 64, hk, j0, b, &bars.full[s]);
-      tma_load_4d_ws(vd, &tmV, 0, hk, j0, b, &bars.full[s]);
-      tma_load_4d_ws(vd + KT_BYTES_ / 2, &tmV, 64, hk, j0, b, &bars.full[s]);
+      mbar_arrive_expect_tx_ws(&bars.fullV[s], KT_BYTES_);
+      tma_load_4d_ws(vd, &tmV, 0, hk, j0, b, &bars.fullV[s]);
+      tma_load_4d_ws(vd + KT_BYTES_ / 2, &tmV, 64, hk, j0, b, &bars.fullV[s]);
+    };
+    load_k(0);
+    for (int t = 1; t < n_tiles; ++t) {
+      load_k(t);
+      load_v(t - 1);
     }
+    load_v(n_tiles - 1);
   } else if (warp == 1) {
     // ---------------------------------- MMA issuer --------------------------------------
     // All 32 lanes run converged; the elected lane issues (umma_*_ws) so descriptors stay in uniform registers.
@@ -122,20 +168,22 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         umma_bf16_ws(tm + TM_S + s * BN, dQ + qoff, dK + koff, idescS, j > 0);
       }
       umma_commit_ws(&bars.s[s]);
+      umma_commit_ws(&bars.emptyK[s]);
     };
     mbar_wait(&bars.q, 0);
-    mbar_wait(&bars.full[0], 0);
+    mbar_wait(&bars.fullK[0], 0);
     tc_fence_after();
     issue_s(0);
     for (int t = 0; t < n_tiles; ++t) {
       if (t + 1 < n_tiles) {
         const int s1 = (t + 1) & 1;
-        mbar_wait(&bars.full[s1], ((t + 1) >> 1) & 1);
+        mbar_wait(&bars.fullK[s1], ((t + 1) >> 1) & 1);
         if (t + 1 >= 2) mbar_wait(&bars.sfree[s1], (((t + 1) >> 1) - 1) & 1);
         tc_fence_after();
         issue_s(t + 1);
       }
       mbar_wait(&bars.p, t & 1);
+      mbar_wait(&bars.fullV[t & 1], (t >> 1) & 1);
       tc_fence_after();
       {
         const int s = t & 1;
@@ -145,7 +193,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 0; j < BN / 16; ++j)
           umma_bf16_ws(tm + TM_O, dP + j * 16, dV + j * 128, idescO, (t > 0 || j > 0) ? 1u : 0u);
         umma_commit_ws(&bars.pv);
-        umma_commit_ws(&bars.empty[s]);
+        umma_commit_ws(&bars.emptyV[s]);
       }
     }
   } else {
@@ -200,8 +248,12 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int i = 0; i < 32; ++i) {
         const uint32_t* src = (i < 16) ? (r + 2 * i) : (r2 + 2 * (i - 16));
         float2 v = __ffma2_rn(make_float2(__uint_as_float(src[0]), __uint_as_float(src[1])), sc2, nm2);
-        v.x = exp2f(v.x);
-        v.y = exp2f(v.y);
+        if ((i & 7) < POLY) {
+          v = exp2_fma_pair(v);
+        } else {
+          v.x = exp2f(v.x);
+          v.y = exp2f(v.y);
+        }
         sum2 = __fadd2_rn(sum2, v);
         w[i] = pack_bf16(v.x, v.y);
       }
@@ -300,10 +352,18 @@ bool make_map(CUtensorMap* m, const void* ptr, int B, int T, int Hn, long long s
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
                            int window, float scale, cudaStream_t stream) {
+  // IVL_SWA_POLY (developer knob): pairs out of 8 whose exponentials run on the FMA pipe
+  int poly = SWA_POLY_DEFAULT;
+  if (const char* e = getenv("IVL_SWA_POLY")) poly = atoi(e);
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, SwaArgs) =
+      poly <= 0 ? swa_fwd_kernel<0> : poly <= 2 ? swa_fwd_kernel<2> : poly == 3 ? swa_fwd_kernel<3>
+      : poly == 4 ? swa_fwd_kernel<4> : swa_fwd_kernel<5>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(swa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWA_SMEM);
-    if (e != cudaSuccess) return e;
+    for (auto f : {swa_fwd_kernel<0>, swa_fwd_kernel<2>, swa_fwd_kernel<3>, swa_fwd_kernel<4>, swa_fwd_kernel<5>}) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SWA_SMEM);
+      if (e != cudaSuccess) return e;
+    }
     configured = true;
   }
   CUtensorMap tq, tk, tv;
@@ -317,7 +377,7 @@ cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, co
   a.window = (window > 0 && Tk > window) ? window : 0;  // HF glue passes the window only when key_len > W
   a.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(Hq, (Tq + BM - 1) / BM, B);
-  swa_fwd_kernel<<<grid, SWA_THREADS, SWA_SMEM, stream>>>(tq, tk, tv, a);
+  kern<<<grid, SWA_THREADS, SWA_SMEM, stream>>>(tq, tk, tv, a);
   return cudaGetLastError();
 }
 
