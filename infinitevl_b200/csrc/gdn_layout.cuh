@@ -6,12 +6,12 @@
 // sm100.cuh).  The scan kernel then only issues 1-D bulk copies (TMA engine)
 // into its pipeline stages -- no layout work on the serial path.
 //
-//   blob[b][h][slot] (BLOB_BYTES = 56 KiB + 128 B, contiguous; slot = c mod ring):
+//   blob[b][h][slot] (BLOB_BYTES = 57 KiB, contiguous; slot = c mod ring):
 //     A1  image 32 KiB   K-major operand [-Wg ; Qg]  (128 rows x 128 k)
 //                        Wg = A (beta Kn exp(G)),  Qg = Qn exp(G) scale
 //     P   image  8 KiB   rows 64..127 of the K-major operand [0 ; P],  P = tril(Qn Kn^T * Gamma) * scale
 //     Kt  image 16 KiB   MN-major operand Kt^T (M = 128 key dims, K = 64 tokens), Kt = Kn exp(G_C - G)
-//     tail        128 B   fp32 gamma = exp(G_C), the whole-chunk decay, in the first 4 bytes
+//     tail        1 KiB   fp32 gamma = exp(G_C), the whole-chunk decay, in the first 4 bytes (128 B are copied)
 //                        (P, Kt and the tail are adjacent: the scan fetches them with one copy, A1 with
 //                         another, because their shared-memory slots are recycled at different times;
 //                         gamma travels with the operands so that the scan never reads it before the
@@ -53,8 +53,9 @@ constexpr int GDN_NS = GDN_V / GDN_BV;  // U sub-slices per head
 constexpr uint32_t P_BYTES = 64 * 64 * 2;        // 8 KiB
 constexpr uint32_t A1_BYTES = 128 * 128 * 2;     // 32 KiB
 constexpr uint32_t KT_BYTES = 128 * 64 * 2;      // 16 KiB
-constexpr uint32_t TAIL_BYTES = 128;             // gamma (fp32) + padding
-constexpr uint32_t BLOB_BYTES = P_BYTES + A1_BYTES + KT_BYTES + TAIL_BYTES;  // 56 KiB + 128 B
+constexpr uint32_t TAIL_BYTES = 128;             // gamma (fp32) + padding: what the scan copies
+constexpr uint32_t TAIL_STRIDE = 1024;           // what the blob reserves, so that blobs stay 1 KiB aligned
+constexpr uint32_t BLOB_BYTES = P_BYTES + A1_BYTES + KT_BYTES + TAIL_STRIDE;  // 57 KiB
 constexpr uint32_t UBLOB_BYTES = 64 * GDN_BV * 2;               // 4 KiB
 
 constexpr uint32_t BLOB_OFF_A1 = 0;
@@ -94,7 +95,7 @@ __host__ inline GdnWorkspace gdn_carve(void* ws, int B, int T, int H, int ring) 
   w.ready = static_cast<uint32_t*>(ws);
   w.progress = w.ready + (size_t)B * H * NT;
   w.blob = static_cast<uint8_t*>(ws) + gdn_sync_bytes(B, T, H);
-  w.ublob = w.blob + n * BLOB_BYTES;   // n * 57472 keeps 128-byte alignment
+  w.ublob = w.blob + n * BLOB_BYTES;
   w.ring = ring;
   return w;
 }

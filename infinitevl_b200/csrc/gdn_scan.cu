@@ -17,6 +17,8 @@
 //   epi    O = D1[64:128] -> bf16 -> global;  S -> bf16 shadow, gamma_{c+1} S -> TMEM
 // Warp roles: warp 0 copies (and follows the prep kernel's per-chunk ready flags), warp 1 MMA
 // issuer, warps 2.. epilogue: one warp per (TMEM lane quadrant = warp % 4, 32-column group).
+#include <stdlib.h>
+
 #include "gdn_layout.cuh"
 #include "sm100.cuh"
 
@@ -102,9 +104,9 @@ __device__ __forceinline__ void store_row_bf16(uint8_t* base, uint32_t piece_str
   }
 }
 
-__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -170,7 +172,7 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
 #endif
         do {
           const int idx = known + lane;
-          const uint32_t f = (idx < NT) ? ld_relaxed_gpu(ready + idx) : 0u;
+          const uint32_t f = (idx < NT) ? ld_acquire_gpu(ready + idx) : 0u;
           const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
           known += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
           if (c >= known) {
@@ -178,8 +180,9 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
             if (++spins > (1ll << 24)) asm volatile("trap;");  // prep never ran: fail loudly instead of hanging
           }
         } while (c >= known);
-        // relaxed polls, then one acquire fence (pairs with prep's release) and the generic -> async proxy fence
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        // every lane acquired its own flag (pairs with prep's release; the ballot orders the lanes), then the
+        // generic -> async proxy fence.  (A gpu-scope FENCE here instead would also wait for this warp's
+        // outstanding bulk copies at every poll.)
         asm volatile("fence.proxy.async;" ::: "memory");
 #ifdef IVL_TRACE
         if (lane == 0) {
@@ -424,6 +427,19 @@ cudaError_t launch_scan_variant(const GdnWorkspace& ws, const void* h0, int h0_d
     configured[dev] = true;
   }
   dim3 grid(GDN_V / BV, H, B);
+  // Developer knob IVL_GDN_CLUSTER=2: launch the CTAs of a head as clusters of two, i.e. on the two SMs of one TPC
+  // (the kernel uses no cluster feature; this only controls placement next to the concurrently running prep).
+  const char* cl = getenv("IVL_GDN_CLUSTER");
+  if (cl && atoi(cl) == 2 && (GDN_V / BV) % 2 == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gdn_scan_kernel<BV>, ws, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht, ht_dtype, T,
+                              H, gdn_num_chunks(T));
+  }
   gdn_scan_kernel<BV><<<grid, C::THREADS, C::SMEM, stream>>>(ws, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,
                                                              ht_dtype, T, H, gdn_num_chunks(T));
   return cudaGetLastError();

@@ -39,12 +39,12 @@ def test_version_and_strerror(lib):
 
 
 def test_workspace_size_formula(lib):
-    # per (b, h, chunk): 56 KiB + 128 B operand blob + 8 x 4 KiB U slices + a 4 B ready flag;
+    # per (b, h, chunk): 57 KiB operand blob (56 KiB of images + gamma) + 8 x 4 KiB U slices + a 4 B ready flag;
     # per (b, h): 8 progress counters; flags + counters rounded to 1 KiB
     for B, T, H in ((1, 64, 16), (1, 65, 16), (2, 1000, 3), (1, 131072, 16)):
         nt = (T + 63) // 64
         n = B * H * nt
-        want = n * (57344 + 128 + 8 * 4096) + ((n + B * H * 8) * 4 + 1023) // 1024 * 1024
+        want = n * (57344 + 1024 + 8 * 4096) + ((n + B * H * 8) * 4 + 1023) // 1024 * 1024
         assert lib.ivl_gdn_chunk_workspace_bytes(B, T, H) == want
     assert lib.ivl_gdn_chunk_workspace_bytes(0, 64, 16) == 0
 
