@@ -17,8 +17,6 @@
 //   epi    O = D1[64:128] -> bf16 -> global;  S -> bf16 shadow, gamma_{c+1} S -> TMEM
 // Warp roles: warp 0 copies (and follows the prep kernel's per-chunk ready flags), warp 1 MMA
 // issuer, warps 2.. epilogue: one warp per (TMEM lane quadrant = warp % 4, 32-column group).
-#include <stdlib.h>
-
 #include "gdn_layout.cuh"
 #include "sm100.cuh"
 
@@ -427,19 +425,6 @@ cudaError_t launch_scan_variant(const GdnWorkspace& ws, const void* h0, int h0_d
     configured[dev] = true;
   }
   dim3 grid(GDN_V / BV, H, B);
-  // Developer knob IVL_GDN_CLUSTER=2: launch the CTAs of a head as clusters of two, i.e. on the two SMs of one TPC
-  // (the kernel uses no cluster feature; this only controls placement next to the concurrently running prep).
-  const char* cl = getenv("IVL_GDN_CLUSTER");
-  if (cl && atoi(cl) == 2 && (GDN_V / BV) % 2 == 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gdn_scan_kernel<BV>, ws, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht, ht_dtype, T,
-                              H, gdn_num_chunks(T));
-  }
   gdn_scan_kernel<BV><<<grid, C::THREADS, C::SMEM, stream>>>(ws, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,
                                                              ht_dtype, T, H, gdn_num_chunks(T));
   return cudaGetLastError();

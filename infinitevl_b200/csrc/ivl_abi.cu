@@ -207,7 +207,7 @@ int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const float* 
   IVL_CUDA(ivl::launch_gdn_scan(ws, h0, h0_dtype, o, ht, ht_dtype, B, T, H, bv, st));
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, B, T, H, default_scale(scale, ivl::GDN_K), l2norm_qk,
-                                env_int("IVL_GDN_NOWAIT", 0) ? 0 : ivl::GDN_V / bv, fj->aux));
+                                ivl::GDN_V / bv, fj->aux));
   IVL_CUDA(cudaEventRecord(fj->join, fj->aux));
   IVL_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   return IVL_OK;
