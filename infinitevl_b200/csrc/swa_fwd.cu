@@ -10,9 +10,11 @@
 // overlaps the other's MMAs.  Per 64-key tile:
 //   MMA   S = Q K^T                  M128 N64 K128   (Q, K: K-major 128B-swizzled TMA tiles)
 //   warps row softmax (one thread per query row, no shuffles), lazy rescale of O in TMEM,
-//         P -> bf16 -> shared (K-major core-matrix image)
-//   MMA   O += P V                   M128 N128 K64   (V: MN-major 128B-swizzled TMA tile)
-// S is double-buffered in TMEM so S(t+1) is issued before P(t) is ready.  The softmax is instruction-issue
+//         P -> bf16 -> TMEM, over the first 32 columns of the S buffer it was computed from
+//   MMA   O += P V                   M128 N128 K64   (P: TMEM A operand; V: MN-major 128B-swizzled TMA tile)
+// S is double-buffered in TMEM so S(t+1) is issued before P(t) is ready; S(t+2) reuses the buffer of S(t) / P(t)
+// and is issued after PV(t), which the tensor pipe executes in order.  P never touches shared memory: the
+// kernel was at the shared-memory port's limit (operand reads + TMA fills + 16 KB of P stores per tile).  The softmax is instruction-issue
 // bound (ncu: tensor and XU pipes ~50 % each, profiles/r01c_summary.md), so its inner loops use the packed
 // FP32x2 instructions of sm_100 (scale and max subtraction in one FFMA2, row sum in FADD2).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue.
@@ -34,9 +36,7 @@ constexpr uint32_t KT_BYTES_ = BN * HD * 2;      // 16 KiB: 2 panels [64][64]
 constexpr uint32_t OFF_Q = 0;
 constexpr uint32_t OFF_K = Q_BYTES;              // 2 stages
 constexpr uint32_t OFF_V = OFF_K + 2 * KT_BYTES_;
-constexpr uint32_t OFF_P = OFF_V + 2 * KT_BYTES_;
-constexpr uint32_t P_BYTES_ = BM * BN * 2;       // 16 KiB
-constexpr uint32_t DATA_BYTES = OFF_P + P_BYTES_;  // 112 KiB
+constexpr uint32_t DATA_BYTES = OFF_V + 2 * KT_BYTES_;  // 96 KiB
 constexpr uint32_t SWA_SMEM = DATA_BYTES + 1024;   // barriers live in the alignment slack (or the tail)
 constexpr uint32_t TM_S = 0;      // 2 buffers x 64 columns
 constexpr uint32_t TM_O = 128;    // 128 columns
@@ -157,7 +157,6 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t sb = smem_u32(smem);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint64_t dQ = umma_desc(sb + OFF_Q, 16, 1024, SWZ_128B);
-    const uint64_t dP = umma_desc(sb + OFF_P, 128, 1024, SWZ_NONE);
     auto issue_s = [&](int t) {
       const int s = t & 1;
       const uint64_t dK = umma_desc(sb + OFF_K + s * KT_BYTES_, 16, 1024, SWZ_128B);
@@ -191,7 +190,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint64_t dV = umma_desc(sb + OFF_V + s * KT_BYTES_, KT_BYTES_ / 2, 1024, SWZ_128B);
 #pragma unroll
         for (int j = 0; j < BN / 16; ++j)
-          umma_bf16_ws(tm + TM_O, dP + j * 16, dV + j * 128, idescO, (t > 0 || j > 0) ? 1u : 0u);
+          umma_bf16_ts_ws(tm + TM_O, tm + TM_S + s * BN + j * 8, dV + j * 128, idescO, (t > 0 || j > 0) ? 1u : 0u);
         umma_commit_ws(&bars.pv);
         umma_commit_ws(&bars.emptyV[s]);
       }
@@ -202,7 +201,6 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int row = quad * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const int pos = i0 + row + shift;  // absolute key position of this query
-    uint8_t* p_dst = smem + OFF_P + (row >> 3) * 1024 + (row & 7) * 16;
     float m = -INFINITY, l = 0.f;   // running max (log2 domain, scaled) and row sum
     uint32_t r[32], r2[32];          // raw scores of keys 0..31 / 32..63 of the tile
     for (int t = 0; t < n_tiles; ++t) {
@@ -257,30 +255,30 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         sum2 = __fadd2_rn(sum2, v);
         w[i] = pack_bf16(v.x, v.y);
       }
-      if (t > 0) {
-        mbar_wait(&bars.pv, (t - 1) & 1);  // P buffer free, O complete up to tile t-1
+      if (__any_sync(0xffffffffu, grow) && t > 0) {
+        mbar_wait(&bars.pv, (t - 1) & 1);  // O complete up to tile t-1 (only the rare rescale needs it)
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
-          const float f = grow ? exp2f(m_old - m) : 1.f;  // exp2(-inf) = 0 wipes an all-masked prefix
-          l *= f;
-          uint32_t ro[32];
+        const float f = grow ? exp2f(m_old - m) : 1.f;  // exp2(-inf) = 0 wipes an all-masked prefix
+        l *= f;
+        uint32_t ro[32];
 #pragma unroll
-          for (int c = 0; c < HD; c += 32) {
-            tmem_ld32(tlane + TM_O + c, ro);
-            tmem_ld_wait();
+        for (int c = 0; c < HD; c += 32) {
+          tmem_ld32(tlane + TM_O + c, ro);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * f);
-            tmem_st32(tlane + TM_O + c, ro);
-          }
-          tmem_st_wait();
+          for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * f);
+          tmem_st32(tlane + TM_O + c, ro);
         }
       }
       l += sum2.x + sum2.y;
-#pragma unroll
-      for (int kg = 0; kg < 8; ++kg)
-        *reinterpret_cast<uint4*>(p_dst + kg * 128) = make_uint4(w[4 * kg], w[4 * kg + 1], w[4 * kg + 2], w[4 * kg + 3]);
-      fence_async_smem();
+      // P(t) as a TMEM A operand: lane = query row, word i = keys 2i, 2i+1, over the S buffer this warp has
+      // already read (its other 32 columns stay dead until S(t+2) overwrites the buffer)
+      tmem_st32(tlane + TM_S + s * BN, w);
+      tmem_st_wait();
       tc_fence_before();
+      // Stay within one phase of the PV barrier (a parity wait cannot tell phase n from phase n - 2): PV(t-1)
+      // was issued a whole tile ago, so this is normally free, and PV(t) cannot retire before the arrival below.
+      if (t > 0) mbar_wait(&bars.pv, (t - 1) & 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.p);
     }
