@@ -78,6 +78,19 @@ IVL_API int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const
                       int H, int K, int V, float scale, int l2norm_qk, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Packed variable-length batch: the reference's `cu_seqlens` form (fla/ops/gated_delta_rule/chunk.py:211-214,
+ * 355-369: B = 1, sequences concatenated on the token axis, one initial / final state per sequence).  One launch
+ * pair for the whole batch.  The caller cuts every sequence into chunks of 64 tokens (the last one may be
+ * short; empty sequences have no chunk) and passes three DEVICE arrays:
+ *   chunk_tok0[num_chunks], chunk_valid[num_chunks]   first token / token count of each chunk,
+ *   seq_chunk_begin[num_seqs + 1]                      chunk range of each sequence.
+ *   h0, ht: [num_seqs, H, 128, 256];  workspace: ivl_gdn_chunk_workspace_bytes(1, 64 * num_chunks, H). */
+IVL_API int ivl_gdn_chunk_fwd_varlen(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                             const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H,
+                             int K, int V, float scale, int l2norm_qk, const int32_t* chunk_tok0,
+                             const int32_t* chunk_valid, int num_chunks, const int32_t* seq_chunk_begin,
+                             int num_seqs, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The two halves of the above, exposed so that the bench can time them separately and so that a
  * sequence-sharded caller can start prep before the previous rank's state has arrived.  prep must
  * have been enqueued on `stream` (or be otherwise ordered) before scan. */

@@ -63,6 +63,15 @@ constexpr uint32_t BLOB_OFF_P = A1_BYTES;
 constexpr uint32_t BLOB_OFF_KT = A1_BYTES + P_BYTES;
 constexpr uint32_t BLOB_OFF_TAIL = A1_BYTES + P_BYTES + KT_BYTES;
 
+// Packed variable-length batch (cu_seqlens of the reference operator): the flattened token axis is cut into
+// chunks per SEQUENCE (a chunk never straddles two sequences; the last chunk of a sequence may be short).
+// All three tables live in device memory; null pointers mean the dense [B, T] case.
+struct GdnVarlen {
+  const int* chunk_tok0;       // [num_chunks]  first token of the chunk on the flattened axis
+  const int* chunk_valid;      // [num_chunks]  tokens in the chunk (1..64)
+  const int* seq_chunk_begin;  // [N + 1]       chunks of sequence n are seq_chunk_begin[n] .. seq_chunk_begin[n+1]-1
+};
+
 struct GdnWorkspace {
   uint8_t* blob;       // [B][H][ring][BLOB_BYTES]
   uint8_t* ublob;      // [B][H][ring][NS][UBLOB_BYTES]

@@ -131,7 +131,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 __global__ void __launch_bounds__(PREP_THREADS, 3)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
-                const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, int T, int H, float scale,
+                const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, GdnVarlen vl, int T, int H, float scale,
                 int l2norm, int prefetch_ahead, int scan_ctas_per_head) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
@@ -142,8 +142,9 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   // CTAs are dispatched in linear block order: head fastest, then chunk, so the grid walks the sequence
   // front to back over all heads and a concurrently running scan (gdn_scan.cu) can follow it.
   const int c = blockIdx.x / H, h = blockIdx.x % H, b = blockIdx.z, NT = gridDim.x / H;
-  const int t0 = c * GDN_C;
-  const int valid = min(GDN_C, T - t0);
+  const bool varlen = vl.chunk_tok0 != nullptr;  // packed sequences: chunk geometry comes from the tables
+  const int t0 = varlen ? __ldg(vl.chunk_tok0 + c) : c * GDN_C;
+  const int valid = varlen ? __ldg(vl.chunk_valid + c) : min(GDN_C, T - t0);
   const size_t tok0 = (size_t)b * T + t0;
   const size_t ch = ((size_t)b * H + h) * NT + c;  // chunk-head index (ready flag)
   const size_t slot = ((size_t)b * H + h) * ws.ring + (c % ws.ring);  // where its images live
@@ -169,9 +170,10 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     const long long ahead = (long long)blockIdx.x + prefetch_ahead;
     const int pc = (int)(ahead / H), ph = (int)(ahead % H);
     if (pc < NT) {
-      const size_t ptok = (size_t)b * T + (size_t)pc * GDN_C;
+      const int pt0 = varlen ? __ldg(vl.chunk_tok0 + pc) : pc * GDN_C;
+      const size_t ptok = (size_t)b * T + (size_t)pt0;
       const int row = tid >> 2, qt = tid & 3;
-      if (pc * GDN_C + row < T) {
+      if (pt0 + row < T) {
         const size_t poff = ((ptok + row) * H + ph) * GDN_K + qt * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q + poff));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(k + poff));
@@ -542,9 +544,10 @@ cudaError_t configure_gdn_prep() {
 
 // scan_ctas_per_head: number of scan CTAs per head whose progress counters gate the ring (ignored when the
 // ring holds every chunk)
+// vl.chunk_tok0 != nullptr: packed variable-length batch (B must be 1) of num_chunks chunks
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
-                            const GdnWorkspace& ws, int B, int T, int H, float scale, int l2norm,
-                            int scan_ctas_per_head, cudaStream_t stream) {
+                            const GdnWorkspace& ws, const GdnVarlen& vl, int num_chunks, int B, int T, int H,
+                            float scale, int l2norm, int scan_ctas_per_head, cudaStream_t stream) {
   const int smem = (int)sizeof(PrepSmem);
   if (cudaError_t e = configure_gdn_prep()) return e;
   static int resident = 0;
@@ -554,10 +557,10 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     resident = 3 * sms;
   }
-  dim3 grid((unsigned)gdn_num_chunks(T) * (unsigned)H, 1, B);
+  dim3 grid((unsigned)num_chunks * (unsigned)H, 1, B);
   gdn_prep_kernel<<<grid, PREP_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
-      static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, T, H, scale, l2norm,
+      static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, vl, T, H, scale, l2norm,
       resident, scan_ctas_per_head);
   return cudaGetLastError();
 }

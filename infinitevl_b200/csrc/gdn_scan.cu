@@ -110,17 +110,39 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 
 template <int BV>
 __global__ void __launch_bounds__(ScanCfg<BV>::THREADS, 1)
-gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv_bfloat16* __restrict__ o,
-                void* __restrict__ ht, int ht_dtype, int T, int H, int NT) {
+gdn_scan_kernel(GdnWorkspace ws, GdnVarlen vl, const void* __restrict__ h0, int h0_dtype,
+                __nv_bfloat16* __restrict__ o, void* __restrict__ ht, int ht_dtype, int T, int H, int NTROW) {
   using C = ScanCfg<BV>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Bars& bars = *reinterpret_cast<Bars*>(smem + C::OFF_BARS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slice = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const size_t ch0 = ((size_t)b * H + h) * NT;         // first ready flag of this head
-  const size_t slot0 = ((size_t)b * H + h) * ws.ring;  // first image slot of this head; chunk c lives in c % ring
+  const int slice = blockIdx.x, h = blockIdx.y;
+  // Dense: blockIdx.z = batch row b, which owns chunks 0 .. NTROW-1 of workspace row (b, h).
+  // Packed (vl): blockIdx.z = sequence n of the single flattened row; its chunks are cb .. cb+NT-1 of row (0, h).
+  const bool varlen = vl.chunk_tok0 != nullptr;
+  const int b = varlen ? 0 : blockIdx.z;
+  const int seq = blockIdx.z;                           // index of the initial / final state
+  const int cb = varlen ? __ldg(vl.seq_chunk_begin + seq) : 0;
+  const int NT = varlen ? __ldg(vl.seq_chunk_begin + seq + 1) - cb : NTROW;   // chunks this CTA scans
+  const size_t ch0 = ((size_t)b * H + h) * NTROW + cb;  // ready flag of this CTA's first chunk
+  const size_t slot0 = ((size_t)b * H + h) * ws.ring;   // first image slot of the row; chunk c lives in c % ring
   const int ring = ws.ring;
+  if (NT <= 0) {
+    // empty sequence: the final state is the initial state
+    if (ht != nullptr) {
+      const size_t base = ((size_t)seq * H + h) * GDN_K * GDN_V;
+      for (int i = tid; i < GDN_K * BV; i += C::THREADS) {
+        const size_t off = base + (size_t)(i / BV) * GDN_V + slice * BV + (i % BV);
+        const float x = h0 == nullptr ? 0.f
+                        : (h0_dtype == 0 ? static_cast<const float*>(h0)[off]
+                                         : __bfloat162float(static_cast<const __nv_bfloat16*>(h0)[off]));
+        if (ht_dtype == 0) static_cast<float*>(ht)[off] = x;
+        else static_cast<__nv_bfloat16*>(ht)[off] = __float2bfloat16(x);
+      }
+    }
+    return;
+  }
   const uint8_t* blob = ws.blob + slot0 * BLOB_BYTES;
   const uint8_t* ublob = ws.ublob + (slot0 * GDN_NS + slice * C::NCG) * UBLOB_BYTES;
 
@@ -191,7 +213,7 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
 #endif
       }
       const int sa = c % C::NA, sk = c % C::NK;
-      const size_t cs = (size_t)(c % ring);  // image slot of chunk c
+      const size_t cs = (size_t)((cb + c) % ring);  // image slot of chunk c
 #ifdef IVL_TRACE
       if (lane == 0 && h < 16 && c < 2048 && slice < 4) {
         unsigned long long tg;
@@ -208,7 +230,7 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
         // its image slot may be overwritten: tell prep (the ring hand-off of gdn_layout.cuh)
         // (relaxed is enough: the copies out of that slot have COMPLETED -- this warp saw their mbarrier -- and
         //  a release here would make the copy warp wait for its own outstanding bulk copies every chunk)
-        if (lane == 0 && ring < NT)
+        if (lane == 0 && ring < NTROW)
           asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(c - C::NK + 1)) : "memory");
       }
       uint8_t* ks = smem + C::OFF_K + sk * C::KSLOT;
@@ -277,7 +299,7 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
 
     // initial state: S_0 -> bf16 shadow, gamma_0 S_0 -> TMEM
     {
-      const size_t soff = (((size_t)b * H + h) * GDN_K + row) * GDN_V + col0;
+      const size_t soff = (((size_t)seq * H + h) * GDN_K + row) * GDN_V + col0;
       if (h0 == nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = 0.f;
@@ -377,7 +399,7 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
         if (lane == 0) mbar_arrive(bar_vnst);   // MMA-B of the next chunk may accumulate
         if (quad == 0) TR(11);
       } else if (ht != nullptr) {
-        const size_t soff = (((size_t)b * H + h) * GDN_K + row) * GDN_V + col0;
+        const size_t soff = (((size_t)seq * H + h) * GDN_K + row) * GDN_V + col0;
         if (ht_dtype == 0) {
           float4* p = reinterpret_cast<float4*>(static_cast<float*>(ht) + soff);
 #pragma unroll
@@ -397,7 +419,8 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
         if (quad == 2) TR(12);
         tmem_ld32(tlane + C::TM_D1 + buf * 32, r);
         tmem_ld_wait();  // D1[buf] is free again once this warp's next sb arrival is observed by the MMA warp
-        const int t = c * GDN_C + tok;
+        const int t = varlen ? (tok < __ldg(vl.chunk_valid + cb + c) ? __ldg(vl.chunk_tok0 + cb + c) + tok : T)
+                             : c * GDN_C + tok;
         if (t < T) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]);
@@ -412,8 +435,8 @@ gdn_scan_kernel(GdnWorkspace ws, const void* __restrict__ h0, int h0_dtype, __nv
 }
 
 template <int BV>
-cudaError_t launch_scan_variant(const GdnWorkspace& ws, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype,
-                                int B, int T, int H, cudaStream_t stream) {
+cudaError_t launch_scan_variant(const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, const void* h0,
+                                int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, cudaStream_t stream) {
   using C = ScanCfg<BV>;
   static bool configured[64] = {};
   int dev = 0;
@@ -424,21 +447,22 @@ cudaError_t launch_scan_variant(const GdnWorkspace& ws, const void* h0, int h0_d
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  dim3 grid(GDN_V / BV, H, B);
-  gdn_scan_kernel<BV><<<grid, C::THREADS, C::SMEM, stream>>>(ws, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,
-                                                             ht_dtype, T, H, gdn_num_chunks(T));
+  dim3 grid(GDN_V / BV, H, nseq);
+  gdn_scan_kernel<BV><<<grid, C::THREADS, C::SMEM, stream>>>(ws, vl, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,
+                                                             ht_dtype, T, H, ntrow);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-// bv: value columns per CTA (32, 64 or 128)
-cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype,
-                            int B, int T, int H, int bv, cudaStream_t stream) {
+// bv: value columns per CTA (32, 64 or 128).  ntrow: chunks per workspace row; nseq: batch rows (dense) or
+// sequences of the packed batch (vl tables set).
+cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, const void* h0,
+                            int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int bv, cudaStream_t stream) {
   switch (bv) {
-    case 32: return launch_scan_variant<32>(ws, h0, h0_dtype, o, ht, ht_dtype, B, T, H, stream);
-    case 64: return launch_scan_variant<64>(ws, h0, h0_dtype, o, ht, ht_dtype, B, T, H, stream);
-    case 128: return launch_scan_variant<128>(ws, h0, h0_dtype, o, ht, ht_dtype, B, T, H, stream);
+    case 32: return launch_scan_variant<32>(ws, vl, ntrow, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, stream);
+    case 64: return launch_scan_variant<64>(ws, vl, ntrow, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, stream);
+    case 128: return launch_scan_variant<128>(ws, vl, ntrow, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, stream);
     default: return cudaErrorInvalidValue;
   }
 }

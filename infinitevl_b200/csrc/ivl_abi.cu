@@ -10,11 +10,11 @@
 
 namespace ivl {
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
-                            const GdnWorkspace& ws, int B, int T, int H, float scale, int l2norm,
-                            int scan_ctas_per_head, cudaStream_t stream);
+                            const GdnWorkspace& ws, const GdnVarlen& vl, int num_chunks, int B, int T, int H,
+                            float scale, int l2norm, int scan_ctas_per_head, cudaStream_t stream);
 cudaError_t configure_gdn_prep();
-cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype,
-                            int B, int T, int H, int bv, cudaStream_t stream);
+cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, const void* h0,
+                            int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int bv, cudaStream_t stream);
 cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, const float* g, const void* beta,
                                  const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H,
                                  float scale, int l2norm, cudaStream_t stream);
@@ -138,7 +138,8 @@ int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float*
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, /*ring=*/0);  // one slot per chunk
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T, H), st));
-  IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, B, T, H, default_scale(scale, ivl::GDN_K), l2norm_qk, 0, st));
+  IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, T, H,
+                                default_scale(scale, ivl::GDN_K), l2norm_qk, 0, st));
   return IVL_OK;
 }
 
@@ -150,15 +151,25 @@ int ivl_gdn_chunk_scan(const void* h0, int h0_dtype, void* o, void* ht, int ht_d
   if (workspace_bytes < ivl::gdn_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
     return IVL_ERR_WORKSPACE;
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, /*ring=*/0);
-  IVL_CUDA(ivl::launch_gdn_scan(ws, h0, h0_dtype, o, ht, ht_dtype, B, T, H, scan_bv(32),
-                                static_cast<cudaStream_t>(stream)));
+  IVL_CUDA(ivl::launch_gdn_scan(ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, h0, h0_dtype, o, ht, ht_dtype, T, H,
+                                scan_bv(32), static_cast<cudaStream_t>(stream)));
   return IVL_OK;
 }
 
-int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const float* g, const void* beta, const void* h0,
-                      int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H, int K, int V, float scale,
-                      int l2norm_qk, void* workspace, size_t workspace_bytes, void* stream) {
-  if (int e = check_gdn_shape(B, T, H, K, V)) return e;
+namespace {
+// Shared body of the dense and the packed (variable-length) chunk operator.  nseq: batch rows (dense) or sequences
+// (packed, B = 1); num_chunks: chunks per workspace row.
+int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float* g, const void* beta, const void* h0,
+                       int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H, float scale, int l2norm_qk,
+                       const ivl::GdnVarlen& vl, int num_chunks, int nseq, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (!q || !k || !v || !g || !beta || !o || !workspace) return IVL_ERR_NULL;
+  if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
+  const int T_ws = num_chunks * ivl::GDN_C;   // the workspace is sized by chunks
+  if (workspace_bytes < ivl::gdn_workspace_bytes(B, T_ws, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
+    return IVL_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float sc = default_scale(scale, ivl::GDN_K);
   // The first call on a device runs the two kernels back to back: a first launch may have to load the kernel
   // or grow the context's local-memory pool, both of which wait for running kernels -- and in the overlapped
   // form the running scan waits for prep.  (Not needed under stream capture: nothing runs at capture time.)
@@ -166,51 +177,70 @@ int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const float* 
   int dev = 0;
   IVL_CUDA(cudaGetDevice(&dev));
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  IVL_CUDA(cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &cap));
+  IVL_CUDA(cudaStreamIsCapturing(st, &cap));
   const bool first = dev >= 0 && dev < 64 && !warmed[dev] && cap == cudaStreamCaptureStatusNone;
   if (first) warmed[dev] = true;
   // Profilers and sanitizers (ncu, compute-sanitizer: their injection library is mapped into the process) and
   // CUDA_LAUNCH_BLOCKING=1 run one kernel at a time; a scan that waits for a prep that cannot start would only
   // hit its time-out trap, so those runs get the back-to-back form unless IVL_GDN_PIPE is set explicitly.
   const bool serialised = tool_attached() || env_int("CUDA_LAUNCH_BLOCKING", 0) != 0;
-  const int overlap_default = (T >= 2048 && !serialised) ? 1 : 0;
+  const int overlap_default = (num_chunks >= 32 && !serialised) ? 1 : 0;
   if (first || env_int("IVL_GDN_PIPE", overlap_default) == 0) {
-    if (int e = ivl_gdn_chunk_prep(q, k, v, g, beta, B, T, H, scale, l2norm_qk, workspace, workspace_bytes, stream))
-      return e;
-    return ivl_gdn_chunk_scan(h0, h0_dtype, o, ht, ht_dtype, B, T, H, workspace, workspace_bytes, stream);
+    ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
+    IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, st));
+    IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
+    return IVL_OK;
   }
   // Overlapped form.  The scan goes first, on the caller's stream, with 64-column slices: its few CTAs (64 at
   // B = 1, H = 16) take their SMs and then follow the ready flags; prep runs on the second stream on the SMs
   // that are left and publishes chunk after chunk, so the operand images are consumed while they are still
   // in L2.  At 128K tokens both sides then take ~2.3 ms (scan alone on 64 SMs 2.32 ms, prep alone on 84 SMs
   // 1.34 x 148 / 84 = 2.37 ms), against 1.34 + 1.59 ms back to back.
-  if (!q || !k || !v || !g || !beta || !o || !workspace) return IVL_ERR_NULL;
-  if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
-  if (workspace_bytes < ivl::gdn_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
-    return IVL_ERR_WORKSPACE;
   ForkJoin* fj = fork_join();
   if (!fj) { cuda_failed(cudaGetLastError(), "fork_join stream/event creation"); return IVL_ERR_LAUNCH; }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   // IVL_GDN_RING = n (experimental, default off) keeps the images in a ring of n chunk slots per head and makes
   // prep wait for the scan's progress before it reuses a slot.  A ring of 16 chunks (22 MB) stays in L2 and
   // cuts the operator's DRAM traffic from 9.4 GB to 4.2 GB at 128K tokens (ncu range replay), but prep needs
   // ~16 chunks in flight to keep its pace, so the two kernels then wait on each other (5 ms instead of 2.4 ms);
   // rings long enough not to stall (>= 512 chunks) no longer fit the L2.  See profiles/r01e_summary.md.
+  // (Dense single-row batches only: the progress counters are per head.)
   const int bv = scan_bv(64);
-  int ring = env_int("IVL_GDN_RING", 0);
+  int ring = (vl.chunk_tok0 == nullptr && B == 1) ? env_int("IVL_GDN_RING", 0) : 0;
   if (ring > 0 && ring < 8) ring = 8;
-  ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, ring);
+  ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, ring);
   IVL_CUDA(ivl::configure_gdn_prep());  // prep must be loaded before a scan that waits for it is running
-  IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T, H), st));
+  IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
   IVL_CUDA(cudaEventRecord(fj->fork, st));
   IVL_CUDA(cudaStreamWaitEvent(fj->aux, fj->fork, 0));
-  IVL_CUDA(ivl::launch_gdn_scan(ws, h0, h0_dtype, o, ht, ht_dtype, B, T, H, bv, st));
+  IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, bv, st));
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
-  IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, B, T, H, default_scale(scale, ivl::GDN_K), l2norm_qk,
-                                ivl::GDN_V / bv, fj->aux));
+  IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv, fj->aux));
   IVL_CUDA(cudaEventRecord(fj->join, fj->aux));
   IVL_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   return IVL_OK;
+}
+}  // namespace
+
+int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const float* g, const void* beta, const void* h0,
+                      int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H, int K, int V, float scale,
+                      int l2norm_qk, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_gdn_shape(B, T, H, K, V)) return e;
+  return gdn_chunk_fwd_impl(q, k, v, g, beta, h0, h0_dtype, o, ht, ht_dtype, B, T, H, scale, l2norm_qk, ivl::GdnVarlen{},
+                            ivl::gdn_num_chunks(T), B, workspace, workspace_bytes, stream);
+}
+
+int ivl_gdn_chunk_fwd_varlen(const void* q, const void* k, const void* v, const float* g, const void* beta,
+                             const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int K, int V,
+                             float scale, int l2norm_qk, const int32_t* chunk_tok0, const int32_t* chunk_valid,
+                             int num_chunks, const int32_t* seq_chunk_begin, int num_seqs, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (int e = check_gdn_shape(1, T, H, K, V)) return e;
+  if (num_chunks <= 0 || num_seqs <= 0 || num_seqs > 65535) return IVL_ERR_BAD_SHAPE;
+  if (!chunk_tok0 || !chunk_valid || !seq_chunk_begin) return IVL_ERR_NULL;
+  ivl::GdnVarlen vl{chunk_tok0, chunk_valid, seq_chunk_begin};
+  return gdn_chunk_fwd_impl(q, k, v, g, beta, h0, h0_dtype, o, ht, ht_dtype, 1, T, H, scale, l2norm_qk, vl, num_chunks,
+                            num_seqs, workspace, workspace_bytes, stream);
 }
 
 int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, const float* g, const void* beta,

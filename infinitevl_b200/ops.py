@@ -113,6 +113,9 @@ def _gated_delta_rule(runner, q, k, v, g, beta, scale, initial_state, output_fin
     bounds = [int(x) for x in cu_seqlens.tolist()]
     N = len(bounds) - 1
     ht = torch.empty(N, H, K, V, dtype=torch.float32, device=q.device) if output_final_state else None
+    if runner is _run_chunk:
+        _run_chunk_varlen(q, k, v, g, beta, scale, initial_state, ht, o, l2norm, bounds)
+        return o, ht
     for n in range(N):
         s, e = bounds[n], bounds[n + 1]
         if e <= s:
@@ -123,6 +126,44 @@ def _gated_delta_rule(runner, q, k, v, g, beta, scale, initial_state, output_fin
                None if initial_state is None else initial_state[n:n + 1],
                None if ht is None else ht[n:n + 1], o[:, s:e], l2norm)
     return o, ht
+
+
+def varlen_chunk_tables(bounds, device):
+    """The chunk geometry of a packed batch, as the C ABI wants it (include/ivl_b200.h,
+    ivl_gdn_chunk_fwd_varlen): sequences are cut into 64-token chunks that never straddle a
+    boundary -- the reference's prepare_chunk_indices (fla/ops/gated_delta_rule/chunk.py:211-214)."""
+    tok0, valid, begin = [], [], [0]
+    for n in range(len(bounds) - 1):
+        s, e = bounds[n], bounds[n + 1]
+        for t in range(s, e, 64):
+            tok0.append(t)
+            valid.append(min(64, e - t))
+        begin.append(len(tok0))
+    as_dev = lambda x: torch.tensor(x, dtype=torch.int32).to(device, non_blocking=False)
+    return as_dev(tok0), as_dev(valid), as_dev(begin), len(tok0)
+
+
+def _run_chunk_varlen(q, k, v, g, beta, scale, h0, ht, o, l2norm, bounds):
+    """One launch pair for the whole packed batch."""
+    lib = _lib.load()
+    _, T, H, K = q.shape
+    V = v.shape[-1]
+    N = len(bounds) - 1
+    tok0, valid, begin, num_chunks = varlen_chunk_tables(bounds, q.device)
+    if bounds[-1] < T:
+        o[:, bounds[-1]:].zero_()  # tokens past the last sequence belong to nobody
+    if num_chunks == 0:
+        if ht is not None:
+            ht.copy_(h0.to(ht.dtype) if h0 is not None else torch.zeros_like(ht))
+        return
+    ws = gdn_workspace(1, 64 * num_chunks, H, q.device)
+    code = lib.ivl_gdn_chunk_fwd_varlen(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(),
+        _ptr(h0), _dtype_code(h0) if h0 is not None else 0, o.data_ptr(),
+        _ptr(ht), _dtype_code(ht) if ht is not None else 0,
+        T, H, K, V, float(scale), int(l2norm), tok0.data_ptr(), valid.data_ptr(), num_chunks, begin.data_ptr(), N,
+        ws.data_ptr(), ws.numel(), _stream_ptr(q.device))
+    _lib.check(code, "ivl_gdn_chunk_fwd_varlen")
 
 
 @torch.no_grad()

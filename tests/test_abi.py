@@ -74,3 +74,18 @@ def test_ops_refuse_cpu_tensors():
     g = torch.zeros(1, 64, 1)
     with pytest.raises(_lib.IvlError):
         ops.chunk_gated_delta_rule(q, q, v, g, g.bfloat16())
+
+
+def test_varlen_chunk_tables_host_logic():
+    """Chunk geometry of a packed batch (the host side of ivl_gdn_chunk_fwd_varlen): 64-token chunks that never
+    straddle a sequence boundary, none for empty sequences -- fla's prepare_chunk_indices
+    (fla/ops/gated_delta_rule/chunk.py:211-214) in the layout the C ABI takes."""
+    from infinitevl_b200.ops import varlen_chunk_tables
+    bounds = [0, 0, 1, 64, 129, 129, 400]
+    tok0, valid, begin, n = varlen_chunk_tables(bounds, "cpu")
+    assert n == 9
+    assert tok0.tolist() == [0, 1, 64, 128, 129, 193, 257, 321, 385]
+    assert valid.tolist() == [1, 63, 64, 1, 64, 64, 64, 64, 15]
+    assert begin.tolist() == [0, 0, 1, 2, 4, 4, 9]
+    assert int(valid.sum()) == bounds[-1]
+    assert all(t.dtype.is_floating_point is False and t.element_size() == 4 for t in (tok0, valid, begin))

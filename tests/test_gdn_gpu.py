@@ -200,6 +200,39 @@ def test_varlen_cu_seqlens(ops):
         assert err_ratio(ro, o[:, a:b].float().cpu()) < TOL_O and err_ratio(rs, s[n:n + 1].cpu()) < TOL_S
 
 
+@pytest.mark.parametrize("pipe", ["0", "1"])
+def test_varlen_is_one_launch_and_matches_per_sequence_calls(ops, monkeypatch, pipe):
+    """The packed form (ivl_gdn_chunk_fwd_varlen: one prep + one scan launch for the whole batch, chunks cut per
+    sequence) must reproduce, bit for bit, the dense operator run on every sequence separately -- including
+    empty sequences, one-token sequences, lengths around the chunk size and a tail nobody owns."""
+    lens = [0, 1, 63, 64, 65, 200, 0, 2500, 130]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)))
+    T = int(cu[-1]) + 7          # 7 trailing tokens that belong to no sequence
+    H = 4
+    q, k, v, g, beta, _ = _cuda(gdn_inputs(T=T, H=H, seed=101))
+    h0 = torch.randn(len(lens), H, 128, 256, generator=torch.Generator().manual_seed(2)).cuda()
+    monkeypatch.setenv("IVL_GDN_PIPE", pipe)
+    o, s = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                      cu_seqlens=cu.cuda(), use_qk_l2norm_in_kernel=True)
+    torch.cuda.synchronize()
+    assert s.shape == (len(lens), H, 128, 256)
+    assert torch.count_nonzero(o[:, int(cu[-1]):]) == 0
+    monkeypatch.setenv("IVL_GDN_PIPE", "0")
+    for n, L in enumerate(lens):
+        a, b = int(cu[n]), int(cu[n + 1])
+        if L == 0:
+            assert torch.equal(s[n], h0[n])
+            continue
+        on, sn = ops.chunk_gated_delta_rule(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b],
+                                            initial_state=h0[n:n + 1], output_final_state=True,
+                                            use_qk_l2norm_in_kernel=True)
+        assert torch.equal(o[:, a:b], on) and torch.equal(s[n:n + 1], sn), (n, L)
+    # and against the oracle for one of them
+    a, b = int(cu[7]), int(cu[8])
+    ro, rs = gdn_chunk_ref(*(x[:, a:b].cpu() for x in (q, k, v, g, beta)), initial_state=h0[7:8].cpu())
+    assert err_ratio(ro, o[:, a:b].float().cpu()) < TOL_O and err_ratio(rs, s[7:8].cpu()) < TOL_S
+
+
 def test_reference_error_behaviour(ops):
     q, k, v, g, beta, h0 = _cuda(gdn_inputs(T=64, H=2, seed=71))
     with pytest.raises(AssertionError):  # fla/ops/gated_delta_rule/chunk.py:352
