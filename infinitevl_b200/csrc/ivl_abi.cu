@@ -5,6 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "../../include/ivl_b200.h"
 #include "gdn_layout.cuh"
 
@@ -85,17 +89,20 @@ inline bool tool_attached() {
   return cached == 1;
 }
 
-// Second stream + fork/join events of the overlapped chunk operator, one set per device, created on first use
-// (event record / wait across streams is also how a capturing stream forks, so the operator stays graph-safe).
+// Second stream + fork/join events of the overlapped chunk operator, one set per (device, caller stream), created
+// on first use (event record / wait across streams is also how a capturing stream forks, so the operator stays
+// graph-safe).  Callers on different streams -- or different host threads -- never share a set.
 struct ForkJoin {
   cudaStream_t aux = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-inline ForkJoin* fork_join() {
-  static ForkJoin fj[64];
+inline ForkJoin* fork_join(cudaStream_t caller) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, ForkJoin> sets;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  ForkJoin& f = fj[dev];
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  ForkJoin& f = sets[std::make_pair(dev, caller)];
   if (!f.aux) {
     if (cudaStreamCreateWithFlags(&f.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -197,7 +204,7 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   // that are left and publishes chunk after chunk, so the operand images are consumed while they are still
   // in L2.  At 128K tokens both sides then take ~2.3 ms (scan alone on 64 SMs 2.32 ms, prep alone on 84 SMs
   // 1.34 x 148 / 84 = 2.37 ms), against 1.34 + 1.59 ms back to back.
-  ForkJoin* fj = fork_join();
+  ForkJoin* fj = fork_join(st);
   if (!fj) { cuda_failed(cudaGetLastError(), "fork_join stream/event creation"); return IVL_ERR_LAUNCH; }
   // IVL_GDN_RING = n (experimental, default off) keeps the images in a ring of n chunk slots per head and makes
   // prep wait for the scan's progress before it reuses a slot.  A ring of 16 chunks (22 MB) stays in L2 and
