@@ -56,14 +56,41 @@ __global__ void mrope_kernel(__nv_bfloat16* __restrict__ x, long long sb, long l
 
 // ---------------------------------------------------------------------------------------------
 // Decode attention: one new token per sequence against the cached window.  HBM-bound (reads the
-// K/V window once: 2 * Hkv * Tk * 128 * 2 bytes), so it is a split-KV CUDA-core kernel: CTA =
-// (128-key slice, kv-head, batch) serving all `group` q-heads of that kv-head, followed by a
-// log-sum-exp combine.  Replaces the flash-attn call for q_len == 1 (std:1092-1108) -- and the O(W)
-// cache roll stays in the cache class.
+// K/V window once: 2 * Hkv * Tk * 128 * 2 bytes), so it is a split-KV kernel: CTA = (128-key slice,
+// kv-head, batch) serving all `group` q-heads of that kv-head, followed by a log-sum-exp combine.
+// The slice is staged with cp.async and both products run on warp-level tensor-core MMAs (the 8
+// q-heads of a kv-head are the -- half empty -- M = 16 rows of an m16n8k16 tile): scores = Q K^T
+// with the four warps splitting the keys, O = P V with the warps splitting the head dim.  (The first
+// version did these with scalar FMAs over shared memory and took ~20 us per layer for 8.4 MB.)
+// Replaces the flash-attn call for q_len == 1 (std:1092-1108) -- the O(W) cache roll stays in the
+// cache class.
 // ---------------------------------------------------------------------------------------------
 constexpr int DEC_KEYS = 128;     // keys per CTA
 constexpr int DEC_MAXG = 8;       // q-heads per kv-head supported
-constexpr int DEC_LD = 136;       // padded smem row (bf16 elements)
+constexpr int DEC_LD = 136;       // padded smem row (bf16 elements): 272 B, conflict-free ldmatrix
+
+struct DecSmem {
+  __nv_bfloat16 k[DEC_KEYS * DEC_LD];
+  __nv_bfloat16 v[DEC_KEYS * DEC_LD];
+  __nv_bfloat16 q[16 * DEC_LD];     // rows >= group are zero
+  __nv_bfloat16 p[16 * DEC_LD];     // probabilities, bf16 (as in the prefill kernel)
+  float red_m[DEC_MAXG][4], red_l[DEC_MAXG][4];
+};
+
+__device__ __forceinline__ void dec_ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void dec_ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void dec_mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __global__ void __launch_bounds__(128)
 swa_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, long long k_sb,
@@ -71,99 +98,114 @@ swa_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
                           long long v_st, long long v_sh, float* __restrict__ part, int Tk, int Hq, int group,
                           int first_key, float scale_log2) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  __nv_bfloat16* sk = reinterpret_cast<__nv_bfloat16*>(dsm);              // [128][136]
-  __nv_bfloat16* sv = sk + DEC_KEYS * DEC_LD;                             // [128][136]
-  float* sq = reinterpret_cast<float*>(sv + DEC_KEYS * DEC_LD);           // [8][128]
-  float* sp = sq + DEC_MAXG * 128;                                        // [8][128]
-  __shared__ float red[DEC_MAXG][4];
+  DecSmem& s = *reinterpret_cast<DecSmem*>(dsm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;   // mma fragment coordinates: row (= q-head) and column pair
   const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z, nsplit = gridDim.x;
   const int j0 = first_key + split * DEC_KEYS;
   const int nk = min(DEC_KEYS, Tk - j0);
-  // stage K and V slices (coalesced 16-byte copies) and the group's queries
+  // stage the K and V slices (16-byte async copies, rows past the end zeroed) and the group's queries
   for (int i = tid; i < DEC_KEYS * 16; i += 128) {
     const int r = i >> 4, c = i & 15;
-    uint4 kk = make_uint4(0, 0, 0, 0), vv = kk;
+    __nv_bfloat16* kd = s.k + r * DEC_LD + c * 8;
+    __nv_bfloat16* vd = s.v + r * DEC_LD + c * 8;
     if (r < nk) {
-      kk = __ldg(reinterpret_cast<const uint4*>(k + b * k_sb + (long long)(j0 + r) * k_st + hk * k_sh) + c);
-      vv = __ldg(reinterpret_cast<const uint4*>(v + b * v_sb + (long long)(j0 + r) * v_st + hk * v_sh) + c);
-    }
-    *reinterpret_cast<uint4*>(sk + r * DEC_LD + c * 8) = kk;
-    *reinterpret_cast<uint4*>(sv + r * DEC_LD + c * 8) = vv;
-  }
-  for (int i = tid; i < group * 128; i += 128)
-    sq[i] = __bfloat162float(q[((long long)b * Hq + hk * group) * 128 + i]) * scale_log2;
-  __syncthreads();
-  // scores: thread = key
-  float sc[DEC_MAXG];
-#pragma unroll
-  for (int g = 0; g < DEC_MAXG; ++g) sc[g] = 0.f;
-  {
-    const __nv_bfloat16* kr = sk + tid * DEC_LD;
-#pragma unroll 4
-    for (int c = 0; c < 16; ++c) {
-      const uint4 u = *reinterpret_cast<const uint4*>(kr + c * 8);
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
-      float kf[8];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { kf[2 * e] = bf16_lo(w[e]); kf[2 * e + 1] = bf16_hi(w[e]); }
-#pragma unroll
-      for (int g = 0; g < DEC_MAXG; ++g) {
-        if (g < group) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sc[g] = fmaf(kf[e], sq[g * 128 + c * 8 + e], sc[g]);
-        }
-      }
+      const __nv_bfloat16* kg = k + b * k_sb + (long long)(j0 + r) * k_st + hk * k_sh + c * 8;
+      const __nv_bfloat16* vg = v + b * v_sb + (long long)(j0 + r) * v_st + hk * v_sh + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(kd)), "l"(kg));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(vd)), "l"(vg));
+    } else {
+      *reinterpret_cast<uint4*>(kd) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(vd) = make_uint4(0, 0, 0, 0);
     }
   }
-  const bool valid = tid < nk;
-  float mloc[DEC_MAXG], lloc[DEC_MAXG];
-#pragma unroll
-  for (int g = 0; g < DEC_MAXG; ++g) {
-    float x = valid ? sc[g] : -INFINITY;
-    float m = x;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if (lane == 0) red[g][warp] = m;
-    mloc[g] = x;
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < 16 * 16; i += 128) {
+    const int r = i >> 4, c = i & 15;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (r < group) u = __ldg(reinterpret_cast<const uint4*>(q + ((long long)b * Hq + hk * group + r) * 128) + c);
+    *reinterpret_cast<uint4*>(s.q + r * DEC_LD + c * 8) = u;
+    *reinterpret_cast<uint4*>(s.p + r * DEC_LD + c * 8) = make_uint4(0, 0, 0, 0);
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+
+  // ---- scores: warp w owns keys 32w .. 32w+31 (four n-tiles of 8 keys) ----
+  float sc[4][4];
 #pragma unroll
-  for (int g = 0; g < DEC_MAXG; ++g) {
-    const float m = fmaxf(fmaxf(red[g][0], red[g][1]), fmaxf(red[g][2], red[g][3]));
-    const float p = (m == -INFINITY) ? 0.f : exp2f(mloc[g] - m);
-    sp[g * 128 + tid] = p;
-    float l = p;
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) l += __shfl_xor_sync(0xffffffffu, l, d);
-    mloc[g] = m;
-    lloc[g] = l;
+    for (int e = 0; e < 4; ++e) sc[i][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    uint32_t a[4];
+    dec_ldsm_x4(smem_u32(s.q + (lane & 15) * DEC_LD + ks * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
+#pragma unroll
+    for (int ntp = 0; ntp < 2; ++ntp) {
+      uint32_t b0, b1, b2, b3;
+      const int n = warp * 32 + ntp * 16 + (lane & 7) + (lane >> 4) * 8, kk = ks * 16 + ((lane >> 3) & 1) * 8;
+      dec_ldsm_x4(smem_u32(s.k + n * DEC_LD + kk), b0, b1, b2, b3);
+      dec_mma16816(sc[2 * ntp], a, b0, b1);
+      dec_mma16816(sc[2 * ntp + 1], a, b2, b3);
+    }
   }
-  __syncthreads();  // sp complete; red[] about to be reused for the sums
+  // this thread holds, for q-head gq (accumulator rows gq; rows gq + 8 are padding), keys 32w + 8nt + 2tq + {0,1}
+  float m = -INFINITY;
 #pragma unroll
-  for (int g = 0; g < DEC_MAXG; ++g)
-    if (lane == 0) red[g][warp] = lloc[g];
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = warp * 32 + nt * 8 + 2 * tq + e;
+      const float x = key < nk ? sc[nt][e] * scale_log2 : -INFINITY;
+      sc[nt][e] = x;
+      m = fmaxf(m, x);
+    }
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  if (tq == 0) s.red_m[gq][warp] = m;
   __syncthreads();
-  // PV: thread = output dim
-  float acc[DEC_MAXG];
+  m = fmaxf(fmaxf(s.red_m[gq][0], s.red_m[gq][1]), fmaxf(s.red_m[gq][2], s.red_m[gq][3]));
+  float l = 0.f;
 #pragma unroll
-  for (int g = 0; g < DEC_MAXG; ++g) acc[g] = 0.f;
-  for (int r = 0; r < nk; ++r) {
-    const float vv = __bfloat162float(sv[r * DEC_LD + tid]);
+  for (int nt = 0; nt < 4; ++nt) {
+    const float p0 = (m == -INFINITY) ? 0.f : exp2f(sc[nt][0] - m);
+    const float p1 = (m == -INFINITY) ? 0.f : exp2f(sc[nt][1] - m);
+    l += p0 + p1;
+    *reinterpret_cast<uint32_t*>(s.p + gq * DEC_LD + warp * 32 + nt * 8 + 2 * tq) = pack_bf16(p0, p1);
+  }
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  if (tq == 0) s.red_l[gq][warp] = l;
+  __syncthreads();
+
+  // ---- O = P V: warp w owns head dims 32w .. 32w+31 (four n-tiles of 8 dims), all 128 keys ----
+  float acc[4][4];
 #pragma unroll
-    for (int g = 0; g < DEC_MAXG; ++g)
-      if (g < group) acc[g] = fmaf(sp[g * 128 + r], vv, acc[g]);
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    uint32_t a[4];
+    dec_ldsm_x4(smem_u32(s.p + (lane & 15) * DEC_LD + ks * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
+    const int kk = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int ntp = 0; ntp < 2; ++ntp) {
+      uint32_t b0, b1, b2, b3;
+      dec_ldsm_x4_t(smem_u32(s.v + kk * DEC_LD + warp * 32 + ntp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+      dec_mma16816(acc[2 * ntp], a, b0, b1);
+      dec_mma16816(acc[2 * ntp + 1], a, b2, b3);
+    }
   }
   // partial record per (b, q-head, split): [m, l, o[128]]
+  if (gq < group) {
+    float* rec = part + (((long long)b * Hq + hk * group + gq) * nsplit + split) * 130;
 #pragma unroll
-  for (int g = 0; g < DEC_MAXG; ++g) {
-    if (g < group) {
-      float* rec = part + (((long long)b * Hq + hk * group + g) * nsplit + split) * 130;
-      rec[2 + tid] = acc[g];
-      if (tid == 0) {
-        rec[0] = mloc[g];
-        rec[1] = red[g][0] + red[g][1] + red[g][2] + red[g][3];
-      }
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<float2*>(rec + 2 + warp * 32 + nt * 8 + 2 * tq) = make_float2(acc[nt][0], acc[nt][1]);
+    if (warp == 0 && tq == 0) {
+      rec[0] = m;
+      rec[1] = s.red_l[gq][0] + s.red_l[gq][1] + s.red_l[gq][2] + s.red_l[gq][3];
     }
   }
 }
@@ -197,7 +239,7 @@ cudaError_t launch_swa_decode(const void* q, const void* k, const long long* ks,
                               void* o, int B, int Tk, int Hq, int Hkv, int window, float scale, void* workspace,
                               cudaStream_t stream) {
   static bool configured = false;
-  const int smem = 2 * DEC_KEYS * DEC_LD * 2 + 2 * DEC_MAXG * 128 * 4;
+  const int smem = (int)sizeof(DecSmem);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(swa_decode_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;

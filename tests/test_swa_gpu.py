@@ -37,6 +37,18 @@ def test_swa_matches_oracle(swa, Tq, Tk, window):
     assert err_ratio(ref, out.float().cpu()) < 5e-3
 
 
+@pytest.mark.parametrize("B,Hq,Hkv,Tk,window", [(2, 16, 2, 777, None), (1, 8, 2, 8400, 8192), (3, 2, 2, 130, 64),
+                                                (1, 16, 16, 129, None), (2, 16, 2, 8191, 8192)])
+def test_swa_decode_step_matches_oracle(swa, B, Hq, Hkv, Tk, window):
+    """q_len == 1 goes through the split-KV decode kernels (tensor-core partials + log-sum-exp combine): group
+    sizes 8 / 4 / 1, batches, a window that cuts the cache, slices with a ragged tail."""
+    q, k, v = _qkv(B, Hq, Hkv, 1, Tk, seed=B * 1000 + Tk)
+    ref = swa_attention_ref(q, k, v, window=window)
+    out = swa.swa_attention(q.cuda(), k.cuda(), v.cuda(), window=window)
+    assert out.shape == (B, 1, Hq, 128) and torch.isfinite(out).all()
+    assert err_ratio(ref, out.float().cpu()) < 5e-3
+
+
 def test_swa_batch_heads_and_peaky_scores(swa):
     """B = 2, MHA-like grouping 4:4, and large-magnitude scores (exercises the lazy rescale path)."""
     q, k, v = _qkv(2, 4, 4, 300, 300, seed=3, scale=3.0)
