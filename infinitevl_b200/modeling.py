@@ -372,9 +372,32 @@ class HybridTextConfig:
         self.head_dim = self.hidden_size // self.num_attention_heads
 
 
+def normalize_position_ids(position_ids, cache_position, batch_size):
+    """Position-id normalisation of InfiniteVLTextModel.forward (std:1512-1525): None -> the cache positions on all
+    three M-RoPE rows; [B, T] -> the same row three times; [4, B, T] (the packed FA2 form) -> text positions
+    (row 0) split from the three M-RoPE rows.  Returns (mrope_position_ids [3, B, T], text_position_ids | None).
+
+    The reference uses the text row to build block-diagonal masks for packed sequences; the sliding-window kernel
+    here is causal over the whole row, so a text row that restarts inside a sequence is refused, not ignored."""
+    text_position_ids = None
+    if position_ids is None:
+        position_ids = cache_position.view(1, 1, -1).expand(3, batch_size, -1)
+    elif position_ids.dim() == 2:
+        position_ids = position_ids[None].expand(3, position_ids.shape[0], -1)
+    if position_ids.dim() == 3 and position_ids.shape[0] == 4:
+        text_position_ids = position_ids[0]
+        position_ids = position_ids[1:]
+        if text_position_ids.shape[-1] > 1 and bool((text_position_ids[:, 1:] <= text_position_ids[:, :-1]).any()):
+            raise NotImplementedError("packed sequences (text position ids restart inside the row) need "
+                                      "block-diagonal attention, which the B200 SWA kernel does not implement")
+    if position_ids.dim() != 3 or position_ids.shape[0] != 3:
+        raise ValueError(f"position_ids must be [B, T], [3, B, T] or [4, B, T], got {tuple(position_ids.shape)}")
+    return position_ids, text_position_ids
+
+
 class HybridDecoder(nn.Module):
     """The decoder stack of InfiniteVLTextModel without embeddings / lm_head (std:1455-1591): what the hot
-    path lives in.  forward(inputs_embeds [B,T,hidden], position_ids [3,B,T] or [B,T]) -> hidden states."""
+    path lives in.  forward(inputs_embeds [B,T,hidden], position_ids [3,B,T], [4,B,T] or [B,T]) -> hidden states."""
 
     def __init__(self, config, mixers_only: bool = False):
         super().__init__()
@@ -395,10 +418,7 @@ class HybridDecoder(nn.Module):
         if cache_position is None:
             past = past_key_values.get_seq_length() if past_key_values is not None else 0
             cache_position = torch.arange(past, past + T, device=inputs_embeds.device)
-        if position_ids is None:
-            position_ids = cache_position.view(1, 1, -1).expand(3, B, -1)
-        elif position_ids.dim() == 2:
-            position_ids = position_ids[None].expand(3, -1, -1)
+        position_ids, _ = normalize_position_ids(position_ids, cache_position, B)
         cos, sin = self.rotary_emb(inputs_embeds, position_ids)
         cos, sin = mrope_select(cos, sin, self.config.rope_scaling["mrope_section"])
         h = inputs_embeds

@@ -99,3 +99,25 @@ def test_cache_container_and_demo_clone_protocol():
         else:
             nbytes += 2 * (l.recurrent_state.numel() + l.conv_state_q.numel() + l.conv_state_k.numel() + l.conv_state_v.numel())
     assert nbytes == 27 * (16 * 128 * 256 * 2 + (2048 + 2048 + 4096) * 4 * 2) + 9 * 2 * 2 * 8191 * 128 * 2
+
+
+def test_position_id_normalisation_matches_reference_rules():
+    """InfiniteVLTextModel.forward (std:1512-1525): default positions from cache_position, 2-D ids broadcast to the
+    three M-RoPE rows, the 4-row packed form split into text row + M-RoPE rows; restarts are refused."""
+    import pytest
+    from infinitevl_b200.modeling import normalize_position_ids
+    cp = torch.arange(5, 9)
+    p, t = normalize_position_ids(None, cp, 2)
+    assert p.shape == (3, 2, 4) and t is None and torch.equal(p[1, 1], cp)
+    ids = torch.arange(8).view(2, 4)
+    p, t = normalize_position_ids(ids, cp, 2)
+    assert p.shape == (3, 2, 4) and torch.equal(p[2], ids)
+    four = torch.stack([ids, ids + 1, ids + 2, ids + 3])
+    p, t = normalize_position_ids(four, cp, 2)
+    assert torch.equal(t, ids) and torch.equal(p, four[1:])
+    packed = four.clone()
+    packed[0, 0] = torch.tensor([0, 1, 0, 1])
+    with pytest.raises(NotImplementedError):
+        normalize_position_ids(packed, cp, 2)
+    with pytest.raises(ValueError):
+        normalize_position_ids(torch.zeros(2, 2, 4, dtype=torch.long), cp, 2)
