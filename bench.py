@@ -334,6 +334,69 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def gdn_mixer_core_decode(dev, steps=50):
+    """Everything between the input projections and o_proj of the 27 GDN mixers for one decode token (conv steps,
+    gates, recurrence, gated norm, cache updates): the kernel-by-kernel chain against the one-launch fused step
+    (ivl_gdn_decode_step), each as one CUDA graph of 27 layers."""
+    from infinitevl_b200 import _lib, modeling, ops
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(8)
+    rnd = lambda *shape: (torch.randn(*shape, generator=gen) * 0.5).bfloat16().to(dev)
+    xq, xk, xv, a, b, gate = rnd(1, 1, H * K), rnd(1, 1, H * K), rnd(1, 1, H * V), rnd(1, 1, H), rnd(1, 1, H), rnd(1, 1, H * V)
+    wq, wk, wv, nw = rnd(H * K, 1, 4), rnd(H * K, 1, 4), rnd(H * V, 1, 4), torch.ones(V, dtype=torch.bfloat16, device=dev)
+    A_log = torch.zeros(H, device=dev)
+    dt_bias = torch.zeros(H, device=dev)
+    layers = [dict(cq=rnd(1, H * K, 4), ck=rnd(1, H * K, 4), cv=rnd(1, H * V, 4), st=rnd(1, H, K, V),
+                   cq2=rnd(1, H * K, 4), ck2=rnd(1, H * K, 4), cv2=rnd(1, H * V, 4)) for _ in range(N_GDN_LAYERS)]
+    out = torch.empty(1, 1, H * V, dtype=torch.bfloat16, device=dev)
+
+    def chain():
+        for L in layers:
+            q, _ = modeling.short_conv_silu(xq, wq, L["cq"], True, cache_out=L["cq2"])
+            k, _ = modeling.short_conv_silu(xk, wk, L["ck"], True, cache_out=L["ck2"])
+            v, _ = modeling.short_conv_silu(xv, wv, L["cv"], True, cache_out=L["cv2"])
+            L["cq"].copy_(L["cq2"]); L["ck"].copy_(L["ck2"]); L["cv"].copy_(L["cv2"])   # the cache's "set"
+            g, beta = modeling.gdn_gates(a, b, A_log, dt_bias)
+            o, _ = ops.fused_recurrent_gated_delta_rule(q.view(1, 1, H, K), k.view(1, 1, H, K), v.view(1, 1, H, V), g, beta,
+                                                        initial_state=L["st"], output_final_state=True,
+                                                        use_qk_l2norm_in_kernel=True, state_out=L["st"])
+            modeling.rmsnorm_gated(o, gate.view(1, 1, H, V), nw)
+
+    def fused():
+        st = torch.cuda.current_stream().cuda_stream
+        for L in layers:
+            _lib.check(lib.ivl_gdn_decode_step(
+                xq.data_ptr(), xk.data_ptr(), xv.data_ptr(), a.data_ptr(), b.data_ptr(), gate.data_ptr(), wq.data_ptr(),
+                wk.data_ptr(), wv.data_ptr(), A_log.data_ptr(), dt_bias.data_ptr(), nw.data_ptr(), L["cq"].data_ptr(),
+                L["ck"].data_ptr(), L["cv"].data_ptr(), L["st"].data_ptr(), 1, out.data_ptr(), 1, H, K, V, 0.0, 1e-5, st),
+                "ivl_gdn_decode_step")
+
+    res = {}
+    for name, fn in (("kernel_chain_ms", chain), ("fused_ms", fused)):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = round(e0.elapsed_time(e1) / steps, 4)
+    res["what"] = ("27 GDN mixers, one decode token, projections excluded: 3 conv steps + cache copies + gates + "
+                   "recurrence + gated norm per layer (10 launches) vs ivl_gdn_decode_step (1 launch)")
+    return res
+
+
 def run_decode(dev, peaks, context=524288, steps=50):
     """Decode step of the hot path (BASELINE.json config 3): after a 512K-token context the state is constant
     size -- 27 DeltaNet states (bf16, as the reference caches them) and 9 full 8191-token K/V windows -- so one
@@ -376,7 +439,8 @@ def run_decode(dev, peaks, context=524288, steps=50):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
     alg = N_GDN_LAYERS * 2 * H * K * V * 2 + N_SWA_LAYERS * 2 * HKV * WINDOW * D * 2
-    return {"step_ms": round(ms, 4), "context_tokens": context, "launches_per_step": N_GDN_LAYERS + 2 * N_SWA_LAYERS,
+    core = gdn_mixer_core_decode(dev)
+    return {"step_ms": round(ms, 4), "gdn_mixer_core": core, "context_tokens": context, "launches_per_step": N_GDN_LAYERS + 2 * N_SWA_LAYERS,
             "algorithmic_bytes": alg, "achieved_gbs": round(alg / (ms * 1e-3) / 1e9, 1),
             "hbm_frac": round(alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
             "what": "27x GDN token recurrence (bf16 state in place) + 9x SWA split-KV decode over an 8192-key window, "

@@ -101,6 +101,26 @@ IVL_API int ivl_gdn_chunk_scan(const void* h0, int h0_dtype, void* o, void* ht, 
                        int H, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Gated DeltaNet, ONE decode step of the whole mixer core in one launch: everything between the input
+ * projections and o_proj of GatedDeltaNet.forward for q_len == 1 (std:1263-1342): the three
+ * ShortConvolution steps (fla/modules/convolution.py:224-293), the gate math (std:1293-1294), the
+ * recurrence (fused_recurrent_gated_delta_rule, std:1310-1320) and FusedRMSNormGated (std:1338).
+ *   q_in,k_in [B,H*128], v_in [B,H*256]  bf16 outputs of q_proj/k_proj/v_proj for the new token
+ *   a_in,b_in [B,H] bf16 (a_proj, b_proj);  gate_in [B,H*256] bf16 (g_proj)
+ *   conv_weight_* [D,1,4] bf16;  A_log, dt_bias fp32 [H];  norm_weight bf16 [256]
+ *   conv_state_* [B,D,4] bf16 and state [B,H,128,256] (state_dtype) are UPDATED IN PLACE
+ *   out [B,H*256] bf16: the normalised, gated mixer output (input of o_proj)
+ * Bit-identical to the chain ivl_short_conv_fwd x3 + ivl_gdn_gate_fwd + ivl_gdn_recurrent_fwd +
+ * ivl_rmsnorm_gated_fwd on the same inputs.  Requires num_key_value_heads == num_heads.
+ * ---------------------------------------------------------------------------------- */
+IVL_API int ivl_gdn_decode_step(const void* q_in, const void* k_in, const void* v_in, const void* a_in,
+                        const void* b_in, const void* gate_in, const void* conv_weight_q,
+                        const void* conv_weight_k, const void* conv_weight_v, const float* A_log,
+                        const float* dt_bias, const void* norm_weight, void* conv_state_q,
+                        void* conv_state_k, void* conv_state_v, void* state, int state_dtype, void* out,
+                        int B, int H, int K, int V, float scale, float norm_eps, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Gated DeltaNet, token recurrence (decode and q_len <= 64, std:1230).
  * Replaces fused_recurrent_gated_delta_rule -- fla/ops/gated_delta_rule/fused_recurrent.py:218-335,
  * called from std:1310-1320.  Same tensors as above; exact fp32 recurrence.

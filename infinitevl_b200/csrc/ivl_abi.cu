@@ -19,6 +19,11 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
 cudaError_t configure_gdn_prep();
 cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, const void* h0,
                             int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int bv, cudaStream_t stream);
+cudaError_t launch_gdn_decode_step(const void* q_in, const void* k_in, const void* v_in, const void* a_in,
+                                   const void* b_in, const void* gate_in, const void* wq, const void* wk,
+                                   const void* wv, const float* A_log, const float* dt_bias, const void* norm_w,
+                                   void* conv_q, void* conv_k, void* conv_v, void* state, int state_dtype, void* out,
+                                   int B, int H, float scale, float eps, cudaStream_t stream);
 cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, const float* g, const void* beta,
                                  const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H,
                                  float scale, int l2norm, cudaStream_t stream);
@@ -259,6 +264,23 @@ int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, const flo
   cudaError_t e = ivl::launch_gdn_recurrent(q, k, v, g, beta, h0, h0 ? h0_dtype : 0, o, ht, ht ? ht_dtype : 0, B, T, H,
                                             default_scale(scale, K), l2norm_qk, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_gdn_decode_step(const void* q_in, const void* k_in, const void* v_in, const void* a_in, const void* b_in,
+                        const void* gate_in, const void* conv_weight_q, const void* conv_weight_k,
+                        const void* conv_weight_v, const float* A_log, const float* dt_bias, const void* norm_weight,
+                        void* conv_state_q, void* conv_state_k, void* conv_state_v, void* state, int state_dtype,
+                        void* out, int B, int H, int K, int V, float scale, float norm_eps, void* stream) {
+  if (int e = check_gdn_shape(B, 1, H, K, V)) return e;
+  if (!q_in || !k_in || !v_in || !a_in || !b_in || !gate_in || !conv_weight_q || !conv_weight_k || !conv_weight_v ||
+      !A_log || !dt_bias || !norm_weight || !conv_state_q || !conv_state_k || !conv_state_v || !state || !out)
+    return IVL_ERR_NULL;
+  if (bad_dtype(state_dtype)) return IVL_ERR_DTYPE;
+  IVL_CUDA(ivl::launch_gdn_decode_step(q_in, k_in, v_in, a_in, b_in, gate_in, conv_weight_q, conv_weight_k,
+                                       conv_weight_v, A_log, dt_bias, norm_weight, conv_state_q, conv_state_k,
+                                       conv_state_v, state, state_dtype, out, B, H, default_scale(scale, K), norm_eps,
+                                       static_cast<cudaStream_t>(stream)));
+  return IVL_OK;
 }
 
 int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides, const void* v,

@@ -13,6 +13,7 @@ row f-1 of SURVEY.md section 8, not built yet.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -230,6 +231,9 @@ class GatedDeltaNet(nn.Module):
             (prev_q, prev_k, prev_v), recurrent_state = past_key_values.update(
                 layer_idx=self.layer_idx, key_states=None, value_states=None, conv_state=None, recurrent_state=None,
                 cache_kwargs={"op": "get", "cache_position": cache_position})
+        if q_len == 1 and self._fused_decode_ok(prev_q, prev_k, prev_v, recurrent_state):
+            return self._decode_step(hidden_states, past_key_values, cache_position, prev_q, prev_k, prev_v,
+                                     recurrent_state), None
         q, new_q = self.q_conv1d(self.q_proj(hidden_states), cache=prev_q, output_final_state=use_cache)
         k, new_k = self.k_conv1d(self.k_proj(hidden_states), cache=prev_k, output_final_state=use_cache)
         v, new_v = self.v_conv1d(self.v_proj(hidden_states), cache=prev_v, output_final_state=use_cache)
@@ -248,6 +252,46 @@ class GatedDeltaNet(nn.Module):
         o = self.o_norm(o, gate)
         o = self.o_proj(o.reshape(B, q_len, self.num_heads * self.head_v_dim))
         return o, None
+
+
+    # -- single-token decode: the whole mixer core in one launch (ivl_gdn_decode_step) -------------------------
+    def _fused_decode_ok(self, prev_q, prev_k, prev_v, state) -> bool:
+        """The fused step updates the cache buffers in place, so it needs a started cache whose conv tails are
+        bf16 (the cache dtype of a bf16 model); anything else takes the kernel-by-kernel path."""
+        if os.environ.get("IVL_GDN_FUSED_DECODE", "1") == "0":
+            return False
+        ts = (prev_q, prev_k, prev_v, state)
+        return (all(t is not None and t.is_cuda and t.is_contiguous() for t in ts)
+                and all(t.dtype == torch.bfloat16 for t in ts[:3]) and state.dtype in (torch.bfloat16, torch.float32)
+                and self.num_key_value_heads == self.num_heads and self.q_proj.weight.dtype == torch.bfloat16)
+
+    def _decode_step(self, hidden_states, past_key_values, cache_position, conv_q, conv_k, conv_v, state):
+        B = hidden_states.shape[0]
+        H = self.num_heads
+        xq, xk, xv = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+        a, b, gate = self.a_proj(hidden_states), self.b_proj(hidden_states), self.g_proj(hidden_states)
+        f32 = getattr(self, "_gate_params_f32", None)
+        if f32 is None or f32[0].device != xq.device:
+            # fp32 copies of the two per-head gate parameters, made once (inference weights do not change)
+            f32 = (self.A_log.detach().float().contiguous(), self.dt_bias.detach().float().contiguous())
+            self._gate_params_f32 = f32
+        out = torch.empty(B, 1, H * self.head_v_dim, dtype=torch.bfloat16, device=xq.device)
+        wq, wk, wv = (m.weight for m in (self.q_conv1d, self.k_conv1d, self.v_conv1d))
+        nw = self.o_norm.weight
+        tensors = [xq, xk, xv, a, b, gate, wq, wk, wv, nw]
+        assert all(t.dtype == torch.bfloat16 and t.is_contiguous() for t in tensors)
+        code = _lib.load().ivl_gdn_decode_step(
+            xq.data_ptr(), xk.data_ptr(), xv.data_ptr(), a.data_ptr(), b.data_ptr(), gate.data_ptr(),
+            wq.data_ptr(), wk.data_ptr(), wv.data_ptr(), f32[0].data_ptr(), f32[1].data_ptr(), nw.data_ptr(),
+            conv_q.data_ptr(), conv_k.data_ptr(), conv_v.data_ptr(), state.data_ptr(),
+            _lib.IVL_DTYPE_F32 if state.dtype == torch.float32 else _lib.IVL_DTYPE_BF16, out.data_ptr(),
+            B, H, self.head_k_dim, self.head_v_dim, float(self.head_k_dim ** -0.5), float(self.norm_eps), _stream(xq))
+        _lib.check(code, "ivl_gdn_decode_step")
+        # the buffers were updated in place; "set" with the same tensors only advances the cache's bookkeeping
+        past_key_values.update(layer_idx=self.layer_idx, key_states=None, value_states=None,
+                               conv_state=(conv_q, conv_k, conv_v), recurrent_state=state,
+                               cache_kwargs={"op": "set", "delta_len": 1, "cache_position": cache_position})
+        return self.o_proj(out)
 
 
 class InfiniteVLSelfAttention(nn.Module):

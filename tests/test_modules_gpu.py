@@ -130,6 +130,32 @@ def test_gated_deltanet_mixer_and_streaming(M):
     assert err_ratio(rconv[2], lin.conv_state_v.float().cpu()) < 1e-2
 
 
+@pytest.mark.parametrize("B,cache_dtype", [(1, torch.bfloat16), (3, torch.bfloat16)])
+def test_fused_decode_step_is_bit_identical_to_the_kernel_chain(M, monkeypatch, B, cache_dtype):
+    """q_len == 1 with a started cache runs the whole mixer core in one launch (ivl_gdn_decode_step: conv steps,
+    gates, recurrence, gated norm, caches updated in place).  It repeats the arithmetic of the kernel-by-kernel
+    path operation for operation, so outputs and cache contents must be equal bit for bit over many steps."""
+    cfg = M.HybridTextConfig(num_hidden_layers=4)
+    mod = _init(M.GatedDeltaNet(cfg, 1), 31).bfloat16().cuda()
+    x = torch.randn(B, 140, 2048, generator=gen(32)).bfloat16().cuda()
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("IVL_GDN_FUSED_DECODE", fused)
+        cache = M.StaticCachePrealloc(config=cfg, batch_size=B, device="cuda", dtype=cache_dtype)
+        outs = [mod(x[:, :100], past_key_values=cache, cache_position=torch.arange(0, 100, device="cuda"))[0]]
+        for t in range(100, 140):
+            outs.append(mod(x[:, t:t + 1], past_key_values=cache, cache_position=torch.arange(t, t + 1, device="cuda"))[0])
+        lin = cache.layers[1]
+        assert lin.seq_len == 140
+        res[fused] = (torch.cat(outs, 1), lin.recurrent_state.clone(), lin.conv_state_q.clone(),
+                      lin.conv_state_k.clone(), lin.conv_state_v.clone())
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
+    # and the streamed result is the same function as the one-shot forward (different chunking: tolerance)
+    full, _ = mod(x)
+    assert err_ratio(full.float().cpu(), res["1"][0].float().cpu()) < 1.5e-2
+
+
 def test_self_attention_mixer_with_cache(M):
     cfg = M.HybridTextConfig(num_hidden_layers=4, sliding_window=256)
     mod = _init(M.InfiniteVLSelfAttention(cfg, 0), 21).bfloat16().cuda()

@@ -5,7 +5,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CS = os.path.join(ROOT, "infinitevl_b200", "csrc")
 out = "/tmp/libivl_trace.so"
-srcs = [os.path.join(CS, f) for f in ("ivl_abi.cu", "gdn_prep.cu", "gdn_scan.cu", "gdn_recurrent.cu", "gdn_fused.cu", "swa_fwd.cu", "swa_misc.cu")]
+srcs = [os.path.join(CS, f) for f in ("ivl_abi.cu", "gdn_prep.cu", "gdn_scan.cu", "gdn_recurrent.cu", "gdn_decode.cu", "gdn_fused.cu", "swa_fwd.cu", "swa_misc.cu")]
 subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC",
                 "--expt-relaxed-constexpr", "-DIVL_BUILDING_DLL", "-DIVL_TRACE", "-shared", "-I", os.path.join(ROOT, "include"), "-o", out] + srcs, check=True)
 lib = ctypes.CDLL(out)
