@@ -505,7 +505,7 @@ def run_e2e(hp, args, world=1, dev=None):
 
     loop(2)
     barrier()
-    steps = max(2, min(args.steps, 4))
+    steps = max(4, min(2 * args.steps, 10))   # the feeder is a two-deep pipeline: enough steps to amortise its fill
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     loop(steps)
