@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(128, 1) probe_ts_kernel(ProbeArgs p, const uin
   }
   const uint32_t row = warp * 32 + lane;
   const uint32_t taddr = tmem + ((warp * 32u) << 16);
-  {
+  for (uint32_t c0 = 0; c0 < p.nk * 8; c0 += 32) {  // A lives at columns 128.. (8 words = 16 k per MMA)
     uint32_t r[32];
-    for (int i = 0; i < 32; ++i) r[i] = (i < (int)p.nk * 8) ? a_words[row * (p.nk * 8) + i] : 0u;
-    tmem_st32(taddr + 128, r);  // A lives at columns 128..159
+    for (int i = 0; i < 32; ++i) r[i] = (c0 + i < p.nk * 8) ? a_words[row * (p.nk * 8) + c0 + i] : 0u;
+    tmem_st32(taddr + 128 + c0, r);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -389,5 +389,10 @@ int main() {
   run_ts(MN_SW128, 64, 64);
   run_ts(MN_SW128, 128, 64);
   run_ts(K_SW128, 64, 128);
+  // operand forms of the planned transposed scan: the state shadow / v_new as TMEM A
+  // operands against the images gdn_prep.cu already writes, used as B operands
+  run_ts(K_NONE, 128, 128);   // D1^T = S^T . [-W;Q]^T : B = the K-major no-swizzle [-W;Q] image (N = its 128 rows)
+  run_ts(MN_NONE, 128, 64);   // S^T += Vn^T . K~      : B = the MN-major no-swizzle K~ image (N = 128 key dims)
+  run_ts(K_NONE, 64, 64);     // O^T  = Vn^T . P^T     : B = the K-major no-swizzle P image (N = 64 tokens)
   return 0;
 }
