@@ -197,7 +197,15 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   // hit its time-out trap, so those runs get the back-to-back form unless IVL_GDN_PIPE is set explicitly.
   const bool serialised = tool_attached() || env_int("CUDA_LAUNCH_BLOCKING", 0) != 0;
   const int overlap_default = (num_chunks >= 32 && !serialised) ? 1 : 0;
-  if (first || env_int("IVL_GDN_PIPE", overlap_default) == 0) {
+  // The overlapped form needs the scan's CTAs resident AND at least half of the SMs left for prep: scan CTAs
+  // that fill the GPU would spin on flags that prep could then never publish.  Big batches take wider slices
+  // or, failing that, the back-to-back form.
+  int sms = 0;
+  IVL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int bv_overlap = scan_bv(64);
+  if ((long long)nseq * H * (ivl::GDN_V / bv_overlap) > sms / 2) bv_overlap = 128;
+  const bool fits = (long long)nseq * H * (ivl::GDN_V / bv_overlap) <= sms / 2;
+  if (first || !fits || env_int("IVL_GDN_PIPE", overlap_default) == 0) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
     IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, st));
@@ -211,15 +219,13 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   // 1.34 x 148 / 84 = 2.37 ms), against 1.34 + 1.59 ms back to back.
   ForkJoin* fj = fork_join(st);
   if (!fj) { cuda_failed(cudaGetLastError(), "fork_join stream/event creation"); return IVL_ERR_LAUNCH; }
-  // IVL_GDN_RING = n (experimental, default off) keeps the images in a ring of n chunk slots per head and makes
-  // prep wait for the scan's progress before it reuses a slot.  A ring of 16 chunks (22 MB) stays in L2 and
-  // cuts the operator's DRAM traffic from 9.4 GB to 4.2 GB at 128K tokens (ncu range replay), but prep needs
-  // ~16 chunks in flight to keep its pace, so the two kernels then wait on each other (5 ms instead of 2.4 ms);
-  // rings long enough not to stall (>= 512 chunks) no longer fit the L2.  See profiles/r01e_summary.md.
-  // (Dense single-row batches only: the progress counters are per head.)
-  const int bv = scan_bv(64);
-  int ring = (vl.chunk_tok0 == nullptr && B == 1) ? env_int("IVL_GDN_RING", 0) : 0;
-  if (ring > 0 && ring < 8) ring = 8;
+  // The image ring (gdn_layout.cuh: prep reuses a short ring of chunk slots and waits for the scan's progress)
+  // stays disabled: it does keep the images in L2 (4.2 GB instead of 9.4 GB of DRAM traffic at 128K tokens with a
+  // 16-chunk ring, ncu range replay) but prep needs ~16 chunks in flight, so the kernels then wait on each other
+  // (5 ms instead of 2.4 ms), and a randomised soak (tools/soak_gdn.py) found a rare hang with back-to-back calls.
+  // The device code paths are kept for the next prep design; ring == chunks per row makes them inert.
+  const int bv = bv_overlap;
+  const int ring = 0;
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, ring);
   IVL_CUDA(ivl::configure_gdn_prep());  // prep must be loaded before a scan that waits for it is running
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));

@@ -119,11 +119,10 @@ def test_split_scan_is_bit_identical_at_full_size(ops):
 @pytest.mark.parametrize("T,H", [(2048, 16), (4160, 4), (100, 2)])
 def test_overlapped_and_sliced_variants_are_bit_identical(ops, monkeypatch, T, H):
     """ivl_gdn_chunk_fwd either runs prep then scan on the caller's stream or overlaps them on two streams
-    (the scan following prep's per-chunk ready flags, prep following the scan's progress through a ring of
-    image slots), and the scan owns 32, 64 or 128 value columns per CTA.  The arithmetic per value column is
+    (the scan following prep's per-chunk ready flags), and the scan owns 32, 64 or 128 value columns per CTA.  The arithmetic per value column is
     the same in every form, so all of them must agree bit for bit, under CUDA-graph replay too.  Every form
-    gets fresh inputs in the same (cached) workspace, so an image or gamma read before it was published, or a
-    ring slot overwritten too early, shows up as a mismatch."""
+    gets fresh inputs in the same (cached) workspace, so an image or gamma read before it was published shows up
+    as a mismatch."""
     seed = 3
     for pipe, bv, ring in ((1, 64, 32), (1, 128, 8), (1, 32, 9), (0, 64, 0), (0, 128, 0), (1, 64, 8)):
         seed += 1
@@ -198,6 +197,27 @@ def test_varlen_cu_seqlens(ops):
             continue
         ro, rs = gdn_chunk_ref(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], initial_state=h0[n:n + 1])
         assert err_ratio(ro, o[:, a:b].float().cpu()) < TOL_O and err_ratio(rs, s[n:n + 1].cpu()) < TOL_S
+
+
+def test_big_batches_do_not_starve_prep(ops, monkeypatch):
+    """In the overlapped form the scan's CTAs spin on flags prep has to publish, so they must never fill the GPU:
+    a batch whose scan would need more than half of the SMs takes wider slices or the back-to-back form.
+    (B = 5, H = 16 would be 320 scan CTAs at 64 columns: without the guard this call never returns.)"""
+    B, T, H = 5, 2112, 16
+    monkeypatch.setenv("IVL_GDN_PIPE", "1")
+    q, k, v, g, beta, _ = gdn_inputs(T=T, H=H, seed=77)
+    q, k, v, g, beta = (x.repeat(B, *([1] * (x.dim() - 1))).cuda() for x in (q, k, v, g, beta))
+    v = v * torch.linspace(0.5, 1.5, B, device="cuda").view(B, 1, 1, 1).to(v.dtype)   # rows differ
+    h0 = torch.randn(B, H, 128, 256, generator=torch.Generator().manual_seed(3)).cuda()
+    o, s = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                      use_qk_l2norm_in_kernel=True)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("IVL_GDN_PIPE", "0")
+    for b in (0, B - 1):
+        ob, sb = ops.chunk_gated_delta_rule(q[b:b + 1], k[b:b + 1], v[b:b + 1], g[b:b + 1], beta[b:b + 1],
+                                            initial_state=h0[b:b + 1], output_final_state=True,
+                                            use_qk_l2norm_in_kernel=True)
+        assert torch.equal(o[b:b + 1], ob) and torch.equal(s[b:b + 1], sb)
 
 
 @pytest.mark.parametrize("pipe", ["0", "1"])
