@@ -8,15 +8,16 @@
 //  ops/common/chunk_o.py:32-114,456-497) without ever materialising the per-chunk
 // states h[B,NT,H,K,V] (2.15 GB per layer at 128K tokens in the reference).
 //
-// Per chunk c (operands are the images written by gdn_prep.cu, loaded with 1-D bulk
-// TMA copies through two mbarrier rings):
-//   MMA-A  D1 = [-Wg ; Qg] . bf16(S)            M128 N=BV K128  (tcgen05, accum in TMEM)
+// Per chunk c and 32-column chain of the CTA (operands are the images written by gdn_prep.cu,
+// loaded with 1-D bulk TMA copies through two mbarrier rings shared by the chains):
+//   MMA-A  D1 = [-Wg ; Qg] . bf16(S)            M128 N32 K128   (tcgen05, accum in TMEM)
 //   epi    Vn = U + D1[0:64]      -> bf16 -> shared (MN-major B operand)
-//   MMA-B  S  = gamma S + Kt^T . Vn             M128 N=BV K64   (gamma pre-applied in TMEM)
-//   MMA-C  D1[64:128] += P . Vn                 M128 N=BV K64   (rows 0..63 of the A operand are zero)
+//   MMA-B  S  = gamma S + Kt^T . Vn             M128 N32 K64    (gamma pre-applied in TMEM)
+//   MMA-C  D1[64:128] += P . Vn                 M128 N32 K64    (rows 0..63 of the A operand are zero)
 //   epi    O = D1[64:128] -> bf16 -> global;  S -> bf16 shadow, gamma_{c+1} S -> TMEM
-// Warp roles: warp 0 copies (and follows the prep kernel's per-chunk ready flags), warp 1 MMA
-// issuer, warps 2.. epilogue: one warp per (TMEM lane quadrant = warp % 4, 32-column group).
+// Warp roles: warp 0 copies (and follows the prep kernel's per-chunk ready flags), warps 1..BV/32 issue the
+// MMAs of one chain each, then four epilogue warps per chain (TMEM lane quadrant = warp % 4).
+// Packed variable-length batches (GdnVarlen tables) run one CTA group per sequence over that sequence's chunks.
 #include "gdn_layout.cuh"
 #include "sm100.cuh"
 
@@ -31,8 +32,8 @@ namespace {
 // shadow / v_new buffers -- that share one copy of the operand rings.  While one chain waits on its
 // MMA -> epilogue -> MMA round trip the others use the tensor pipe and the shared-memory ports.  (One wide
 // N = BV chain was measured at 1079 / 1742 ns per chunk for BV = 64 / 128 against 767 ns for BV = 32:
-// every dependent N = 128 MMA costs ~210 cycles and the shadow store alone 256.)  BV = 128 leaves
-// 116 SMs free at B = 1, which is what lets gdn_prep_kernel run concurrently (ivl_gdn_chunk_fwd).
+// every dependent N = 128 MMA costs ~210 cycles and the shadow store alone 256.)  BV = 64 leaves
+// 84 SMs free at B = 1, H = 16, which is what lets gdn_prep_kernel run concurrently (ivl_gdn_chunk_fwd).
 //
 // Shared memory: two operand rings that are recycled at different points of a step --
 //   A ring  (NA slots of 32 KiB): [-Wg ; Qg], free as soon as MMA-A has retired (early in the step)
