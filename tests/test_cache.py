@@ -121,3 +121,20 @@ def test_position_id_normalisation_matches_reference_rules():
         normalize_position_ids(packed, cp, 2)
     with pytest.raises(ValueError):
         normalize_position_ids(torch.zeros(2, 2, 4, dtype=torch.long), cp, 2)
+
+
+def test_demo_import_alias_resolves_to_the_b200_caches():
+    """demo_streaming_inference.py:36-44 imports the cache classes from a module named modeling_qwen2_5_vl;
+    infinitevl_b200/compat on sys.path provides it."""
+    import importlib
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "infinitevl_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        mod = importlib.import_module("modeling_qwen2_5_vl")
+        assert mod.StaticCachePrealloc is StaticCachePrealloc
+        assert mod.StaticSlidingWindowLayerPrealloc is StaticSlidingWindowLayerPrealloc
+        assert mod.StaticLinearLayerPrealloc is StaticLinearLayerPrealloc
+    finally:
+        sys.path.remove(compat)
+        sys.modules.pop("modeling_qwen2_5_vl", None)
