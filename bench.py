@@ -32,9 +32,10 @@ HQ, HKV, D, WINDOW = 16, 2, 128, 8192
 GDN_BYTES_PER_TOKEN = 24672          # q,k,v,g,beta read + o written, per token per layer
 GDN_STATE_BYTES = 2 * H * K * V * 4  # h0 read + hT written, per sequence per layer
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE overlapped ivl_gdn_chunk_fwd call at T = 131072 (prep + scan
-# running concurrently), from the committed ncu range-replay capture profiles/r01e_range_overlapped.csv
-# (5 407 097 088 read + 4 011 054 080 written); refreshed whenever the kernels change
-GDN_DRAM_TRAFFIC_NCU = 9418151168
+# running concurrently), from the committed ncu range-replay capture profiles/r01h_range_overlapped.csv
+# (6 972 059 904 read + 4 007 053 568 written; an earlier build of the same design measured 9.42 GB -- how much of
+# the image traffic hits L2 depends on how far prep runs ahead); refreshed whenever the kernels change
+GDN_DRAM_TRAFFIC_NCU = 10979113472
 
 
 def swa_flops(T, Tk_prefix=0):
