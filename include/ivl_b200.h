@@ -4,7 +4,8 @@
  * One shared library (libivl_b200.so), plain pointers and sizes, no C++ or
  * torch types.  Every entry point
  *   - runs asynchronously on the CUDA stream passed in (a cudaStream_t cast to void*),
- *   - never allocates, never synchronises, never throws,
+ *   - never allocates device memory, never synchronises, never throws (ivl_gdn_chunk_fwd creates one helper
+ *     stream and two events per caller stream the first time it overlaps its kernels, nothing afterwards),
  *   - returns IVL_OK or a negative IVL_ERR_* code (ivl_strerror() names it),
  * so it is safe inside CUDA-graph capture (the reference demo captures the whole
  * forward, inference_examples/demo_streaming_inference.py:473-486).
