@@ -222,7 +222,9 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   // The image ring (gdn_layout.cuh: prep reuses a short ring of chunk slots and waits for the scan's progress)
   // stays disabled: it does keep the images in L2 (4.2 GB instead of 9.4 GB of DRAM traffic at 128K tokens with a
   // 16-chunk ring, ncu range replay) but prep needs ~16 chunks in flight, so the kernels then wait on each other
-  // (5 ms instead of 2.4 ms), and a randomised soak (tools/soak_gdn.py) found a rare hang with back-to-back calls.
+  // (5 ms instead of 2.4 ms), and a randomised soak (tools/soak_gdn.py) found a hang with back-to-back calls: prep
+  // CTAs become resident before the scan's (which need a whole SM each), and once every SM holds a prep CTA that
+  // waits for scan progress the scan can never start.  A ring needs the scan's residency established first.
   // The device code paths are kept for the next prep design; ring == chunks per row makes them inert.
   const int bv = bv_overlap;
   const int ring = 0;
