@@ -109,7 +109,11 @@ inline ForkJoin* fork_join(cudaStream_t caller) {
   std::lock_guard<std::mutex> lock(mu);
   ForkJoin& f = sets[std::make_pair(dev, caller)];
   if (!f.aux) {
-    if (cudaStreamCreateWithFlags(&f.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    // lowest priority: when SMs come free, the block scheduler should place the scan's few whole-SM CTAs (caller's
+    // stream) before prep's many small ones, so that the scan is resident early and the two really overlap
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&f.aux, cudaStreamNonBlocking, least) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
