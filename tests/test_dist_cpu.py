@@ -1,4 +1,4 @@
-"""CPU (gloo, world_size 2) test of the sequence-chunk hand-off logic in infinitevl_b200/dist.py:
+"""CPU (gloo, world_size 2 and 4) test of the sequence-chunk hand-off logic in infinitevl_b200/dist.py:
 the product's cache classes + send/recv protocol + wavefront loop, with the oracle standing in for the
 CUDA mixers.  The rank-concatenated output must equal the single-process run."""
 import os
@@ -110,11 +110,12 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_hand_off_equals_single_process():
+@pytest.mark.parametrize("world", [2, 4])   # 4: middle ranks both receive and send
+def test_hand_off_equals_single_process(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
