@@ -5,7 +5,9 @@
  * torch types.  Every entry point
  *   - runs asynchronously on the CUDA stream passed in (a cudaStream_t cast to void*),
  *   - never allocates device memory, never synchronises, never throws (ivl_gdn_chunk_fwd creates one helper
- *     stream and two events per caller stream the first time it overlaps its kernels, nothing afterwards),
+ *     stream and two events per caller stream the first time it overlaps its kernels -- or ivl_stream_init does,
+ *     ahead of time -- and nothing afterwards; ivl_stream_release frees them),
+ *   - returns IVL_ERR_ARCH on a device that is not sm_100 (the kernels exist for sm_100a only),
  *   - returns IVL_OK or a negative IVL_ERR_* code (ivl_strerror() names it),
  * so it is safe inside CUDA-graph capture (the reference demo captures the whole
  * forward, inference_examples/demo_streaming_inference.py:473-486).
@@ -50,6 +52,14 @@ IVL_API int ivl_abi_version(void);
 IVL_API const char* ivl_strerror(int code);
 /* After IVL_ERR_LAUNCH: the CUDA runtime call that failed and its error text (per calling thread). */
 IVL_API const char* ivl_last_cuda_error(void);
+
+/* Optional: create, ahead of time, the helper stream and the two events ivl_gdn_chunk_fwd uses when it overlaps its
+ * two kernels for calls issued on `stream` of the current device (otherwise created lazily by the first such call;
+ * both are legal during stream capture).  ivl_stream_release destroys them again: call it before destroying a
+ * stream that has been used with this library (the set is keyed by the stream handle), with no call in flight.
+ * Replaces nothing in the reference (its Triton launches own no streams); part of the drop-in's resource contract. */
+IVL_API int ivl_stream_init(void* stream);
+IVL_API int ivl_stream_release(void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Gated DeltaNet, chunked prefill (T > 64 in the model, any T >= 1 here).

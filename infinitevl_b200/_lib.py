@@ -22,6 +22,8 @@ SIGNATURES = {
     "ivl_abi_version": (c_int, []),
     "ivl_strerror": (c_char_p, [c_int]),
     "ivl_last_cuda_error": (c_char_p, []),
+    "ivl_stream_init": (c_int, [c_void_p]),
+    "ivl_stream_release": (c_int, [c_void_p]),
     "ivl_gdn_chunk_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ivl_gdn_chunk_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
                           + [c_float, c_int, c_void_p, c_size_t, c_void_p]),

@@ -16,6 +16,8 @@
 //
 // This kernel is throughput work (32K independent CTAs at 128K tokens); it uses the
 // warp-level mma.sync path.  The latency-critical scan uses tcgen05 (gdn_scan.cu).
+#include <atomic>
+
 #include "gdn_layout.cuh"
 #include "sm100.cuh"
 
@@ -529,15 +531,15 @@ extern "C" __attribute__((visibility("default"))) int ivl_debug_read_prep_wait(u
 // this BEFORE it launches the scan: with lazy module loading the first launch of a kernel can block on the
 // kernels already running, and a running scan is waiting for this very kernel.
 cudaError_t configure_gdn_prep() {
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (!configured[dev]) {
+  if (!configured[dev].load(std::memory_order_acquire)) {
     e = cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
     if (e != cudaSuccess) return e;
-    configured[dev] = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   return cudaSuccess;
 }

@@ -18,6 +18,8 @@
 // Warp roles: warp 0 copies (and follows the prep kernel's per-chunk ready flags), warps 1..BV/32 issue the
 // MMAs of one chain each, then four epilogue warps per chain (TMEM lane quadrant = warp % 4).
 // Packed variable-length batches (GdnVarlen tables) run one CTA group per sequence over that sequence's chunks.
+#include <atomic>
+
 #include "gdn_layout.cuh"
 #include "sm100.cuh"
 
@@ -439,14 +441,14 @@ template <int BV>
 cudaError_t launch_scan_variant(const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, const void* h0,
                                 int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, cudaStream_t stream) {
   using C = ScanCfg<BV>;
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64];
   int dev = 0;
   if (cudaError_t e = cudaGetDevice(&dev)) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (!configured[dev]) {
+  if (!configured[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(gdn_scan_kernel<BV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
-    configured[dev] = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   dim3 grid(GDN_V / BV, H, nseq);
   gdn_scan_kernel<BV><<<grid, C::THREADS, C::SMEM, stream>>>(ws, vl, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,

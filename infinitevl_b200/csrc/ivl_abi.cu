@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -94,20 +95,54 @@ inline bool tool_attached() {
   return cached == 1;
 }
 
+// sm_100 check, cached per device: every kernel in this library is compiled for sm_100a only, so on any other
+// device a launch would fail with "no kernel image" at best.  0 = unknown, 1 = ok, 2 = wrong architecture.
+inline int check_arch() {
+  static std::atomic<int> state[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return IVL_ERR_LAUNCH; }
+  if (dev < 0 || dev >= 64) return IVL_ERR_ARCH;
+  int s = state[dev].load(std::memory_order_relaxed);
+  if (s == 0) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return IVL_ERR_LAUNCH;
+    }
+    s = (major == 10) ? 1 : 2;
+    state[dev].store(s, std::memory_order_relaxed);
+  }
+  return s == 1 ? IVL_OK : IVL_ERR_ARCH;
+}
+#define IVL_ARCH() do { if (int e_ = check_arch()) return e_; } while (0)
+
 // Second stream + fork/join events of the overlapped chunk operator, one set per (device, caller stream), created
 // on first use (event record / wait across streams is also how a capturing stream forks, so the operator stays
 // graph-safe).  Callers on different streams -- or different host threads -- never share a set.
 struct ForkJoin {
   cudaStream_t aux = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  bool used = false;   // an overlapped call has recorded `join` outside of stream capture
 };
-inline ForkJoin* fork_join(cudaStream_t caller) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, ForkJoin> sets;
+std::mutex g_fj_mu;
+std::map<std::pair<int, cudaStream_t>, ForkJoin> g_fj_sets;
+
+// *other_busy: an overlapped call issued from ANOTHER stream of this device has not finished yet.  Its scan CTAs
+// each hold a whole SM and wait for flags; a second overlapped call next to it could leave no SM for either prep
+// (the caller then takes the back-to-back form, which cannot starve).
+inline ForkJoin* fork_join(cudaStream_t caller, bool* other_busy) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  ForkJoin& f = sets[std::make_pair(dev, caller)];
+  std::lock_guard<std::mutex> lock(g_fj_mu);
+  if (other_busy) {
+    *other_busy = false;
+    for (auto& kv : g_fj_sets)
+      if (kv.first.first == dev && kv.first.second != caller && kv.second.used &&
+          cudaEventQuery(kv.second.join) == cudaErrorNotReady)
+        *other_busy = true;
+    cudaGetLastError();
+  }
+  ForkJoin& f = g_fj_sets[std::make_pair(dev, caller)];
   if (!f.aux) {
     // lowest priority: when SMs come free, the block scheduler should place the scan's few whole-SM CTAs (caller's
     // stream) before prep's many small ones, so that the scan is resident early and the two really overlap
@@ -123,7 +158,33 @@ inline ForkJoin* fork_join(cudaStream_t caller) {
 
 extern "C" {
 
-int ivl_abi_version(void) { return 1; }
+int ivl_abi_version(void) { return 2; }
+
+int ivl_stream_init(void* stream) {
+  IVL_ARCH();
+  if (!fork_join(static_cast<cudaStream_t>(stream), nullptr)) {
+    cuda_failed(cudaGetLastError(), "fork_join stream/event creation");
+    return IVL_ERR_LAUNCH;
+  }
+  return IVL_OK;
+}
+
+int ivl_stream_release(void* stream) {
+  int dev = 0;
+  IVL_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_fj_mu);
+  auto it = g_fj_sets.find(std::make_pair(dev, static_cast<cudaStream_t>(stream)));
+  if (it == g_fj_sets.end()) return IVL_OK;
+  if (it->second.aux) {
+    cudaStreamSynchronize(it->second.aux);
+    cudaEventDestroy(it->second.fork);
+    cudaEventDestroy(it->second.join);
+    cudaStreamDestroy(it->second.aux);
+  }
+  g_fj_sets.erase(it);
+  cudaGetLastError();
+  return IVL_OK;
+}
 
 const char* ivl_last_cuda_error(void) { return g_last_cuda_error; }
 
@@ -151,6 +212,7 @@ int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float*
   if (!q || !k || !v || !g || !beta || !workspace) return IVL_ERR_NULL;
   if (workspace_bytes < ivl::gdn_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
     return IVL_ERR_WORKSPACE;
+  IVL_ARCH();
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, /*ring=*/0);  // one slot per chunk
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T, H), st));
@@ -166,6 +228,7 @@ int ivl_gdn_chunk_scan(const void* h0, int h0_dtype, void* o, void* ht, int ht_d
   if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
   if (workspace_bytes < ivl::gdn_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
     return IVL_ERR_WORKSPACE;
+  IVL_ARCH();
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, /*ring=*/0);
   IVL_CUDA(ivl::launch_gdn_scan(ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, h0, h0_dtype, o, ht, ht_dtype, T, H,
                                 scan_bv(32), static_cast<cudaStream_t>(stream)));
@@ -184,18 +247,23 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   const int T_ws = num_chunks * ivl::GDN_C;   // the workspace is sized by chunks
   if (workspace_bytes < ivl::gdn_workspace_bytes(B, T_ws, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
     return IVL_ERR_WORKSPACE;
+  IVL_ARCH();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float sc = default_scale(scale, ivl::GDN_K);
   // The first call on a device runs the two kernels back to back: a first launch may have to load the kernel
   // or grow the context's local-memory pool, both of which wait for running kernels -- and in the overlapped
   // form the running scan waits for prep.  (Not needed under stream capture: nothing runs at capture time.)
-  static bool warmed[64] = {};
+  static std::atomic<bool> warmed[64];
   int dev = 0;
   IVL_CUDA(cudaGetDevice(&dev));
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   IVL_CUDA(cudaStreamIsCapturing(st, &cap));
-  const bool first = dev >= 0 && dev < 64 && !warmed[dev] && cap == cudaStreamCaptureStatusNone;
-  if (first) warmed[dev] = true;
+  // exchange(): exactly one of several racing first callers sees `false`; the others may overlap while that one
+  // is still loading the kernels, which is why the warm-up call below also synchronises nothing but merely runs
+  // back to back -- a racing overlapped call then finds the module loaded or blocks in its own launch, not in a
+  // running scan
+  const bool first = dev >= 0 && dev < 64 && cap == cudaStreamCaptureStatusNone &&
+                     !warmed[dev].load(std::memory_order_acquire) && !warmed[dev].exchange(true);
   // Profilers and sanitizers (ncu, compute-sanitizer: their injection library is mapped into the process) and
   // CUDA_LAUNCH_BLOCKING=1 run one kernel at a time; a scan that waits for a prep that cannot start would only
   // hit its time-out trap, so those runs get the back-to-back form unless IVL_GDN_PIPE is set explicitly.
@@ -221,8 +289,16 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   // that are left and publishes chunk after chunk, so the operand images are consumed while they are still
   // in L2.  At 128K tokens both sides then take ~2.3 ms (scan alone on 64 SMs 2.32 ms, prep alone on 84 SMs
   // 1.34 x 148 / 84 = 2.37 ms), against 1.34 + 1.59 ms back to back.
-  ForkJoin* fj = fork_join(st);
+  bool other_busy = false;
+  ForkJoin* fj = fork_join(st, cap == cudaStreamCaptureStatusNone ? &other_busy : nullptr);
   if (!fj) { cuda_failed(cudaGetLastError(), "fork_join stream/event creation"); return IVL_ERR_LAUNCH; }
+  if (other_busy) {
+    ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
+    IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, st));
+    IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
+    return IVL_OK;
+  }
   // The image ring (gdn_layout.cuh: prep reuses a short ring of chunk slots and waits for the scan's progress)
   // stays disabled: it does keep the images in L2 (4.2 GB instead of 9.4 GB of DRAM traffic at 128K tokens with a
   // 16-chunk ring, ncu range replay) but prep needs ~16 chunks in flight, so the kernels then wait on each other
@@ -242,6 +318,10 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv, fj->aux));
   IVL_CUDA(cudaEventRecord(fj->join, fj->aux));
   IVL_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
+  if (cap == cudaStreamCaptureStatusNone) {
+    std::lock_guard<std::mutex> lock(g_fj_mu);
+    fj->used = true;
+  }
   return IVL_OK;
 }
 }  // namespace
@@ -273,6 +353,7 @@ int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, const flo
   if (int e = check_gdn_shape(B, T, H, K, V)) return e;
   if (!q || !k || !v || !g || !beta || !o) return IVL_ERR_NULL;
   if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
+  IVL_ARCH();
   cudaError_t e = ivl::launch_gdn_recurrent(q, k, v, g, beta, h0, h0 ? h0_dtype : 0, o, ht, ht ? ht_dtype : 0, B, T, H,
                                             default_scale(scale, K), l2norm_qk, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
@@ -288,6 +369,7 @@ int ivl_gdn_decode_step(const void* q_in, const void* k_in, const void* v_in, co
       !A_log || !dt_bias || !norm_weight || !conv_state_q || !conv_state_k || !conv_state_v || !state || !out)
     return IVL_ERR_NULL;
   if (bad_dtype(state_dtype)) return IVL_ERR_DTYPE;
+  IVL_ARCH();
   IVL_CUDA(ivl::launch_gdn_decode_step(q_in, k_in, v_in, a_in, b_in, gate_in, conv_weight_q, conv_weight_k,
                                        conv_weight_v, A_log, dt_bias, norm_weight, conv_state_q, conv_state_k,
                                        conv_state_v, state, state_dtype, out, B, H, default_scale(scale, K), norm_eps,
@@ -311,6 +393,7 @@ int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const in
        reinterpret_cast<uintptr_t>(o)) & 15)
     return IVL_ERR_BAD_SHAPE;
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  IVL_ARCH();
   cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, B, Tq, Tk, Hq, Hkv, window, sc,
                                       static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
@@ -334,6 +417,7 @@ int ivl_swa_decode_fwd(const void* q, const void* k, const int64_t* k_strides, c
     if ((ks[i] | vs[i]) & 7) return IVL_ERR_BAD_SHAPE;
   }
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  IVL_ARCH();
   cudaError_t e = ivl::launch_swa_decode(q, k, ks, v, vs, o, B, Tk, Hq, Hkv, window, sc, workspace,
                                          static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
@@ -345,6 +429,7 @@ int ivl_short_conv_fwd(const void* x, const void* w, const void* cache_in, void*
   if (!x || !w || !y) return IVL_ERR_NULL;
   if (cache_out && cache_out == cache_in) return IVL_ERR_BAD_SHAPE;
   if ((T + 31) / 32 > 65535) return IVL_ERR_BAD_SHAPE;
+  IVL_ARCH();
   cudaError_t e = ivl::launch_short_conv(x, w, cache_in, y, cache_out, B, T, D, activation_silu,
                                          static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
@@ -354,6 +439,7 @@ int ivl_gdn_gate_fwd(const void* a, const void* b, const float* A_log, const flo
                      int64_t n_tokens, int H, void* stream) {
   if (n_tokens <= 0 || H <= 0) return IVL_ERR_BAD_SHAPE;
   if (!a || !b || !A_log || !dt_bias || !g || !beta) return IVL_ERR_NULL;
+  IVL_ARCH();
   cudaError_t e = ivl::launch_gdn_gate(a, b, A_log, dt_bias, g, beta, (long long)n_tokens * H, H,
                                        static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
@@ -363,6 +449,7 @@ int ivl_rmsnorm_gated_fwd(const void* x, const void* gate, const void* w, void* 
                           void* stream) {
   if (rows <= 0 || dim != 256) return IVL_ERR_BAD_SHAPE;
   if (!x || !gate || !w || !y) return IVL_ERR_NULL;
+  IVL_ARCH();
   cudaError_t e = ivl::launch_rmsnorm_gated(x, gate, w, y, rows, eps, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
@@ -373,6 +460,7 @@ int ivl_mrope_apply(void* x, const int64_t* x_strides, const void* cos, const vo
   if (!x || !x_strides || !cos || !sin) return IVL_ERR_NULL;
   long long xs[3] = {x_strides[0], x_strides[1], x_strides[2]};
   if ((xs[0] | xs[1] | xs[2]) & 7) return IVL_ERR_BAD_SHAPE;
+  IVL_ARCH();
   cudaError_t e = ivl::launch_mrope(x, xs, cos, sin, B, T, Hn, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }

@@ -18,6 +18,7 @@
 // bound (ncu: tensor and XU pipes ~50 % each, profiles/r01c_summary.md), so its inner loops use the packed
 // FP32x2 instructions of sm_100 (scale and max subtraction in one FFMA2, row sum in FADD2).
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax / epilogue.
+#include <atomic>
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -356,13 +357,17 @@ cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, co
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, SwaArgs) =
       poly <= 0 ? swa_fwd_kernel<0> : poly <= 2 ? swa_fwd_kernel<2> : poly == 3 ? swa_fwd_kernel<3>
       : poly == 4 ? swa_fwd_kernel<4> : swa_fwd_kernel<5>;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<bool> configured_dev[64];   // function attributes are per device
+  int dev_ = 0;
+  if (cudaError_t e = cudaGetDevice(&dev_)) return e;
+  if (dev_ < 0 || dev_ >= 64) return cudaErrorInvalidDevice;
+  std::atomic<bool>& configured = configured_dev[dev_];
+  if (!configured.load(std::memory_order_acquire)) {
     for (auto f : {swa_fwd_kernel<0>, swa_fwd_kernel<2>, swa_fwd_kernel<3>, swa_fwd_kernel<4>, swa_fwd_kernel<5>}) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SWA_SMEM);
       if (e != cudaSuccess) return e;
     }
-    configured = true;
+    configured.store(true, std::memory_order_release);
   }
   CUtensorMap tq, tk, tv;
   if (!make_map(&tq, q, B, Tq, Hq, qs[0], qs[1], qs[2], BM) || !make_map(&tk, k, B, Tk, Hkv, ks[0], ks[1], ks[2], BN) ||

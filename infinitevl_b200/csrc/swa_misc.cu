@@ -8,6 +8,7 @@
 //                 bit-exact against the torch expression  q*cos + rotate_half(q)*sin.
 //   swa_decode  : attention of a few new tokens against the cached window (split over the
 //                 key axis, combined with a log-sum-exp reduction).
+#include <atomic>
 #include "sm100.cuh"
 
 namespace ivl {
@@ -238,12 +239,16 @@ size_t swa_decode_workspace_bytes(int B, int Tk, int Hq) {
 cudaError_t launch_swa_decode(const void* q, const void* k, const long long* ks, const void* v, const long long* vs,
                               void* o, int B, int Tk, int Hq, int Hkv, int window, float scale, void* workspace,
                               cudaStream_t stream) {
-  static bool configured = false;
+  static std::atomic<bool> configured_dev[64];   // function attributes are per device
+  int dev_ = 0;
+  if (cudaError_t e = cudaGetDevice(&dev_)) return e;
+  if (dev_ < 0 || dev_ >= 64) return cudaErrorInvalidDevice;
+  std::atomic<bool>& configured = configured_dev[dev_];
   const int smem = (int)sizeof(DecSmem);
-  if (!configured) {
+  if (!configured.load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(swa_decode_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.store(true, std::memory_order_release);
   }
   const int first_key = (window > 0 && Tk > window) ? Tk - window : 0;
   const int nsplit = (Tk - first_key + DEC_KEYS - 1) / DEC_KEYS;

@@ -200,6 +200,11 @@ class GatedDeltaNet(nn.Module):
             raise NotImplementedError("the B200 path implements the shipped configuration (short conv + output gate)")
         if (self.head_k_dim, self.head_v_dim, self.conv_size) != (128, 256, 4):
             raise NotImplementedError("the B200 kernels are specialised for head dims K=128, V=256 and conv_size=4")
+        if self.num_key_value_heads != self.num_heads:
+            # the reference views k / v with num_linear_key_value_heads and lets the Triton kernels index q with the
+            # same head count (std:1284-1286), which only works when the two are equal -- as in the shipped config
+            raise NotImplementedError("num_linear_key_value_heads != num_linear_heads is not supported "
+                                      f"({self.num_key_value_heads} vs {self.num_heads})")
         self.q_proj = nn.Linear(self.hidden_size, self.num_heads * self.head_dim, bias=False)
         self.k_proj = nn.Linear(self.hidden_size, self.key_dim, bias=False)
         self.v_proj = nn.Linear(self.hidden_size, self.value_dim, bias=False)
@@ -223,6 +228,11 @@ class GatedDeltaNet(nn.Module):
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 past_key_values=None, cache_position: Optional[torch.LongTensor] = None, **kwargs):
         # padding masks are ignored, exactly as the reference does (std:1223)
+        if kwargs.get("cu_seqlens") is not None:
+            # the reference forwards cu_seqlens to the convs and the kernels (std:1234,1267,1306); the B200 short
+            # conv does not cut its left context at sequence boundaries yet, so refuse instead of leaking state
+            raise NotImplementedError("packed sequences (cu_seqlens) are not supported by the B200 GatedDeltaNet "
+                                      "mixer; call ops.chunk_gated_delta_rule(cu_seqlens=...) directly")
         B, q_len, _ = hidden_states.shape
         mode = "fused_recurrent" if q_len <= 64 else self.mode
         prev_q = prev_k = prev_v = recurrent_state = None
@@ -261,25 +271,29 @@ class GatedDeltaNet(nn.Module):
         if os.environ.get("IVL_GDN_FUSED_DECODE", "1") == "0":
             return False
         ts = (prev_q, prev_k, prev_v, state)
+        ws = (self.q_proj.weight, self.q_conv1d.weight, self.k_conv1d.weight, self.v_conv1d.weight, self.o_norm.weight)
         return (all(t is not None and t.is_cuda and t.is_contiguous() for t in ts)
                 and all(t.dtype == torch.bfloat16 for t in ts[:3]) and state.dtype in (torch.bfloat16, torch.float32)
-                and self.num_key_value_heads == self.num_heads and self.q_proj.weight.dtype == torch.bfloat16)
+                and self.num_key_value_heads == self.num_heads
+                and all(w.dtype == torch.bfloat16 and w.is_contiguous() for w in ws))
 
     def _decode_step(self, hidden_states, past_key_values, cache_position, conv_q, conv_k, conv_v, state):
         B = hidden_states.shape[0]
         H = self.num_heads
         xq, xk, xv = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
         a, b, gate = self.a_proj(hidden_states), self.b_proj(hidden_states), self.g_proj(hidden_states)
-        f32 = getattr(self, "_gate_params_f32", None)
-        if f32 is None or f32[0].device != xq.device:
-            # fp32 copies of the two per-head gate parameters, made once (inference weights do not change)
-            f32 = (self.A_log.detach().float().contiguous(), self.dt_bias.detach().float().contiguous())
-            self._gate_params_f32 = f32
+        # fp32 copies of the two per-head gate parameters, refreshed whenever the parameters change (in-place
+        # update, load_state_dict, .to()): keyed on storage, version counter and device
+        key = (self.A_log.data_ptr(), self.A_log._version, self.dt_bias.data_ptr(), self.dt_bias._version, xq.device)
+        cached = getattr(self, "_gate_params_f32", None)
+        if cached is None or cached[0] != key:
+            cached = (key, self.A_log.detach().float().contiguous(), self.dt_bias.detach().float().contiguous())
+            self._gate_params_f32 = cached
+        f32 = cached[1:]
         out = torch.empty(B, 1, H * self.head_v_dim, dtype=torch.bfloat16, device=xq.device)
         wq, wk, wv = (m.weight for m in (self.q_conv1d, self.k_conv1d, self.v_conv1d))
         nw = self.o_norm.weight
-        tensors = [xq, xk, xv, a, b, gate, wq, wk, wv, nw]
-        assert all(t.dtype == torch.bfloat16 and t.is_contiguous() for t in tensors)
+        xq, xk, xv, a, b, gate = (t.contiguous() for t in (xq, xk, xv, a, b, gate))
         code = _lib.load().ivl_gdn_decode_step(
             xq.data_ptr(), xk.data_ptr(), xv.data_ptr(), a.data_ptr(), b.data_ptr(), gate.data_ptr(),
             wq.data_ptr(), wk.data_ptr(), wv.data_ptr(), f32[0].data_ptr(), f32[1].data_ptr(), nw.data_ptr(),
@@ -341,8 +355,15 @@ class InfiniteVLSelfAttention(nn.Module):
             key_states, value_states = past_key_values.update(
                 layer_idx=self.layer_idx, key_states=key_states, value_states=value_states, conv_state=None,
                 recurrent_state=None, cache_kwargs={"sin": sin, "cos": cos, "cache_position": cache_position})
-        out, _ = swa.sliding_window_attention_forward(self, q.transpose(1, 2), key_states, value_states, None,
-                                                      dropout=0.0, scaling=self.scaling,
+        # crop a 2-D padding mask to the visible keys exactly as the reference does before FA2 (std:1080-1090);
+        # the operator then refuses masks that really pad (it has no unpad path)
+        if attention_mask is not None and attention_mask.dim() != 2:
+            attention_mask = None   # 4-D additive masks are an eager/SDPA concept; the FA2 path builds none
+        if past_key_values is not None and self.sliding_window is not None and attention_mask is not None:
+            kv_len, kv_offset = past_key_values.layers[self.layer_idx].get_mask_sizes(cache_position)
+            attention_mask = None if kv_offset != 0 else attention_mask[:, kv_offset:kv_offset + kv_len]
+        out, _ = swa.sliding_window_attention_forward(self, q.transpose(1, 2), key_states, value_states,
+                                                      attention_mask, dropout=0.0, scaling=self.scaling,
                                                       sliding_window=self.sliding_window)
         out = self.o_proj(out.reshape(B, q_len, self.num_heads * self.head_dim))
         return out, None

@@ -42,11 +42,26 @@ def gdn_workspace(B: int, T: int, H: int, device) -> torch.Tensor:
     need = lib.ivl_gdn_chunk_workspace_bytes(B, T, H)
     key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
-    if ws is None or ws.numel() < need:
+    if ws is None or ws.numel() < need + 1024:
+        if torch.cuda.is_current_stream_capturing():
+            # a buffer allocated during capture lives in the graph's private pool; keeping it in this module-level
+            # cache would outlive the graph.  Pre-size with gdn_workspace(B, T, H, device) before capturing.
+            raise _lib.IvlError(f"GDN workspace of {need} bytes must be allocated before CUDA-graph capture: call "
+                                f"infinitevl_b200.ops.gdn_workspace({B}, {T}, {H}, device) on this stream first")
+        ws = None
+        _workspaces.pop(key, None)   # drop the old buffer before allocating the larger one
         ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     off = (-ws.data_ptr()) % 1024
     return ws[off:off + need]
+
+
+def release_workspaces() -> None:
+    """Free the cached scratch buffers of the chunk operator (22.5 KB per token per call shape: 2.95 GB after one
+    128K-token prefill, held per (device, stream) until this is called) and of the SWA decode kernel."""
+    _workspaces.clear()
+    from . import swa as _swa
+    _swa._decode_ws.clear()
 
 
 def _check_common(q, k, v, g, beta, initial_state, cu_seqlens, head_first):
@@ -54,7 +69,19 @@ def _check_common(q, k, v, g, beta, initial_state, cu_seqlens, head_first):
         raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
     assert q.dtype == k.dtype == v.dtype
     assert len(beta.shape) == 3, "beta must be of shape [B, T, H]."
+    # The kernels take B, T, H, K from q alone: every other operand must really have that geometry (a k / v with
+    # fewer heads would be read past its end, not broadcast).
+    if q.dim() != 4 or k.shape != q.shape:
+        raise ValueError(f"k must have q's shape [B, T, H, K]: q {tuple(q.shape)}, k {tuple(k.shape)}")
+    if v.dim() != 4 or v.shape[:3] != q.shape[:3]:
+        raise ValueError(f"v must be [B, T, H, V] with q's B, T, H: q {tuple(q.shape)}, v {tuple(v.shape)}")
+    lead = (q.shape[0], q.shape[2], q.shape[1]) if head_first else tuple(q.shape[:3])
+    if tuple(g.shape) != tuple(beta.shape) or tuple(beta.shape) not in (tuple(q.shape[:3]), lead):
+        raise ValueError(f"g and beta must be [B, T, H] like q: q {tuple(q.shape)}, g {tuple(g.shape)}, "
+                         f"beta {tuple(beta.shape)}")
     if cu_seqlens is not None:
+        if int(cu_seqlens[0]) != 0:
+            raise ValueError(f"cu_seqlens must start at 0, got {int(cu_seqlens[0])}")
         if q.shape[0] != 1:
             raise ValueError(
                 f"The batch size is expected to be 1 rather than {q.shape[0]} when using `cu_seqlens`."
