@@ -139,6 +139,14 @@ class HotPath:
         self.ws = ops.gdn_workspace(1, T_local, H, device)
         self.launches_per_step = 0
         self.has_swa = False
+        # sequence-sharded run: every layer owns its hand-off buffers, as every layer of the model owns its cache
+        # (no reuse hazards between the transfers of neighbouring layers)
+        from infinitevl_b200 import dist as ivl_dist
+        self.ivl_dist = ivl_dist
+        self.ho = ivl_dist.OperatorHandOff(rank, world) if world > 1 else None
+        if world > 1:
+            self.state_ins = [torch.empty_like(self.h0) for _ in range(N_GDN_LAYERS)]
+            self.hts = [torch.empty_like(self.h0) for _ in range(N_GDN_LAYERS)]
         try:
             from infinitevl_b200 import swa
             self.swa = swa
@@ -146,12 +154,18 @@ class HotPath:
             mk = lambda h: torch.randn(1, gen_T, h, D, generator=gen).bfloat16().repeat(1, rep, 1, 1)[:, :T_local] \
                 .contiguous().to(device)
             self.sq, self.sk, self.sv = mk(HQ), mk(HKV), mk(HKV)   # [B, T, H, D] (kernel-native layout)
-            halo = min(WINDOW - 1, T_local) if rank > 0 else 0
-            self.halo = halo
-            self.skv_full = None
             if world > 1:
-                self.k_halo = torch.zeros(1, WINDOW - 1, HKV, D, dtype=torch.bfloat16, device=device)
-                self.v_halo = torch.zeros(1, WINDOW - 1, HKV, D, dtype=torch.bfloat16, device=device)
+                # [halo of W-1 keys from the previous rank ; local keys] in ONE buffer per layer: the halo is received
+                # straight into the front rows, the kernel reads the whole buffer -- no concatenation
+                Hh = WINDOW - 1
+                self.kbufs = [torch.empty(1, Hh + T_local, HKV, D, dtype=torch.bfloat16, device=device)
+                              for _ in range(N_SWA_LAYERS)]
+                self.vbufs = [torch.empty_like(b) for b in self.kbufs]
+                for kb, vb in zip(self.kbufs, self.vbufs):
+                    kb[:, Hh:].copy_(self.sk)
+                    vb[:, Hh:].copy_(self.sv)
+                    kb[:, :Hh].zero_()
+                    vb[:, :Hh].zero_()
             self.so = torch.empty(1, T_local, HQ, D, dtype=torch.bfloat16, device=device)
             self.has_swa = True
         except ImportError:
@@ -179,48 +193,68 @@ class HotPath:
             h0.data_ptr(), 0, self.o.data_ptr(), self.ht.data_ptr(), 0, 1, self.T, H, K, V, 0.0, 1,
             self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_fwd")
 
+    def gdn_scan_into(self, h0, ht):
+        st = torch.cuda.current_stream().cuda_stream
+        self._lib_mod.check(self.lib.ivl_gdn_chunk_scan(
+            h0.data_ptr(), 0, self.o.data_ptr(), ht.data_ptr(), 0, 1, self.T, H,
+            self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_scan")
+
+    def _post_recv(self, layer):
+        """Post the receive of `layer`'s incoming hand-off (one layer ahead of its use)."""
+        if self.ho is None or self.ho.first or layer >= N_GDN_LAYERS + N_SWA_LAYERS:
+            return None
+        if layer % 4 == 0:
+            if not self.has_swa:
+                return None
+            i = layer // 4
+            Hh = WINDOW - 1
+            n_in = min(Hh, self.rank * self.T)     # tokens of the window that live on earlier ranks
+            return self.ho.post_recv([self.kbufs[i][:, Hh - n_in:Hh], self.vbufs[i][:, Hh - n_in:Hh]])
+        return self.ho.post_recv([self.state_ins[layer - layer // 4 - 1]])
+
     def step(self):
-        import torch.distributed as dist
+        """One pass of the hot path over this rank's token range.  Sharded (world > 1): the neighbour hand-off of
+        infinitevl_b200.dist (OperatorHandOff / gdn_layer_sharded): receives posted one layer ahead, the GDN
+        pre-pass runs before its state is awaited, sends never block the compute stream."""
         n = 0
-        for layer in range(N_GDN_LAYERS + N_SWA_LAYERS):
+        L = N_GDN_LAYERS + N_SWA_LAYERS
+        nxt = self._post_recv(0)
+        for layer in range(L):
+            cur, nxt = nxt, self._post_recv(layer + 1)
             if layer % 4 == 0:
                 if self.has_swa:
-                    n += self.swa_layer()
+                    n += self.swa_layer(layer // 4, cur)
                 continue
             if self.world == 1:
                 self.gdn_fwd(self.h0)
                 n += 2
                 continue
-            # sequence-sharded: prep does not depend on the incoming state, so it runs while the state of the
-            # previous rank's segment is still in flight, then the scan has the GPU to itself.  (Receiving first and
-            # running the overlapped operator was measured slower at N = 2: 89.5 vs 80.4 ms per step -- the
-            # send/recv rendezvous then sits on the critical path of both ranks at every layer.)
-            self.gdn_prep()
-            h0 = self.h0
-            if self.rank > 0:
-                dist.recv(self.state_in, src=self.rank - 1)
-                h0 = self.state_in
-            self.gdn_scan(h0)
-            if self.rank < self.world - 1:
-                dist.send(self.ht, dst=self.rank + 1)
+            g = layer - layer // 4 - 1
+            self.ivl_dist.gdn_layer_sharded(self.ho, self.gdn_prep, lambda h0, g=g: self.gdn_scan_into(h0, self.hts[g]),
+                                            self.h0, self.state_ins[g], self.hts[g], cur)
             n += 2
+        if self.ho is not None:
+            self.ho.drain()
         self.launches_per_step = n
         return n
 
-    def swa_layer(self):
-        import torch.distributed as dist
+    def swa_layer(self, i=0, pending=None):
         if self.world > 1:
-            # halo hand-off: the last W-1 keys/values of this rank's range go to the next rank
-            if self.rank < self.world - 1:
-                dist.send(self.sk[:, -(WINDOW - 1):].contiguous(), dst=self.rank + 1)
-                dist.send(self.sv[:, -(WINDOW - 1):].contiguous(), dst=self.rank + 1)
-            if self.rank > 0:
-                dist.recv(self.k_halo, src=self.rank - 1)
-                dist.recv(self.v_halo, src=self.rank - 1)
-                kf = torch.cat([self.k_halo, self.sk], dim=1)
-                vf = torch.cat([self.v_halo, self.sv], dim=1)
-                self.swa.swa_attention_bthd(self.sq, kf, vf, window=WINDOW, out=self.so)
-                return 1
+            Hh = WINDOW - 1
+            kb, vb = self.kbufs[i], self.vbufs[i]
+            n_in = min(Hh, self.rank * self.T)
+            n_out = min(Hh, (self.rank + 1) * self.T)
+            # halo hand-off: the last W-1 keys/values up to the end of this rank's range go to the next rank (the tail
+            # of the layer's K/V buffer: contiguous, no staging copy).  Only when the local range is shorter than the
+            # window does the outgoing halo contain received rows, and the send has to follow the receive.
+            if n_out <= self.T:
+                self.ho.post_send([kb[:, Hh + self.T - n_out:], vb[:, Hh + self.T - n_out:]])
+            if pending is not None:
+                pending.wait()
+            if n_out > self.T:
+                self.ho.post_send([kb[:, Hh + self.T - n_out:], vb[:, Hh + self.T - n_out:]])
+            self.swa.swa_attention_bthd(self.sq, kb[:, Hh - n_in:], vb[:, Hh - n_in:], window=WINDOW, out=self.so)
+            return 1
         self.swa.swa_attention_bthd(self.sq, self.sk, self.sv, window=WINDOW, out=self.so)
         return 1
 
@@ -277,6 +311,38 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total.item() / args.steps
 
+    # ---- sharded runs: latency of ONE prompt (the loop above pipelines prompts: rank 0 starts step i + 1 while the
+    #      last rank still finishes step i, so the wavefront fill of P - 1 layers is paid once per loop) and parity
+    #      of the package's sharded prefill against the one-GPU run
+    dist_info = None
+    if world > 1:
+        lat = []
+        for _ in range(max(3, min(args.steps, 5))):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            hp.step()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lat.append(t.item())
+        lat.sort()
+        dist_info = {"single_prompt_ms": round(lat[len(lat) // 2], 3),
+                     "single_prompt_tokens_per_s": round(T / (lat[len(lat) // 2] * 1e-3), 1),
+                     "pipelined_ms_per_step": round(ms_step, 3),
+                     "ideal_wavefront_efficiency": round((N_GDN_LAYERS + N_SWA_LAYERS) / (N_GDN_LAYERS + N_SWA_LAYERS + world - 1), 4)}
+        if not args.no_parity:
+            par = hp.ivl_dist.sharded_parity_check(T=min(T, 32768) if T % (64 * world) == 0 else 64 * world * 8, num_layers=8)
+            par_t = torch.zeros(4, device=dev)
+            if par:
+                par_t = torch.tensor([par["out"], par["state"], par["kv"], 1.0 if par["ints_equal"] else 0.0], device=dev)
+            dist.all_reduce(par_t, op=dist.ReduceOp.MAX)
+            pl = par_t.tolist()
+            dist_info["parity_err"] = {"out": pl[0], "state": pl[1], "kv": pl[2], "ints_equal": bool(pl[3]),
+                                       "what": "dist.sharded_prefill (HybridDecoder, 8 layers, 3B mixer dims, T=%d) over NCCL vs the "
+                                               "same decoder on one GPU; RMS error ratio, gate 1e-3" % min(T, 32768)}
+
     # ---- per-kernel timing for the roofline (device events on the launching stream) --------------
     roof = None
     kernels = {}
@@ -309,8 +375,13 @@ def run_ours(args):
     # ---- end-to-end through the public operator API with HOST buffers ---------------------------
     decode = None
     e2e = run_e2e(hp, args, world, dev)
+    gpu_ref = config2 = None
     if world == 1 and hp.has_swa:
         decode = run_decode(dev, peaks)
+        if not args.no_gpu_reference:
+            gpu_ref = gpu_reference(hp, T, ms_step)
+        if T != 32768 and not args.no_config2:
+            config2 = run_config2(dev, peaks)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -328,9 +399,134 @@ def run_ours(args):
                        "parallelism": f"sequence-chunk x{world}" if world > 1 else "single GPU",
                        "l2": "inputs (>3 GB per layer) exceed the 126 MB L2; no flush needed"},
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "decode": decode,
+            "gpu_reference": gpu_ref, "config2_32k": config2, "dist": dist_info,
             "gpu_launches": hp.launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gpu_reference(hp, T, ours_ms_step, warmup=3, iters=3):
+    """The reference's own GPU path on the same box, same process, same inputs: pip flash-linear-attention's Triton
+    chunk_gated_delta_rule (requirements.txt:19-20; called at modeling_infinitevl.py:1298-1308) and flash-attn's
+    flash_attn_func with the sliding window (requirements.txt:18; modeling_infinitevl.py:1092-1108), as one step of
+    27 + 9 calls.  Library code, timed as a denominator only -- nothing of it is on our path."""
+    res = {"what": "fla Triton chunk_gated_delta_rule x27 + flash_attn_func(window) x9 on the same inputs, same process"}
+    try:
+        import fla
+        import flash_attn
+        from fla.ops.gated_delta_rule import chunk_gated_delta_rule as fla_chunk
+        from flash_attn import flash_attn_func
+        res["versions"] = {"fla": getattr(fla, "__version__", "?"), "flash_attn": getattr(flash_attn, "__version__", "?")}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"import failed: {e!r}"}
+
+    def gdn():
+        return fla_chunk(hp.q, hp.k, hp.v, hp.g, hp.beta, initial_state=hp.h0, output_final_state=True,
+                         use_qk_l2norm_in_kernel=True)
+
+    def swa():
+        return flash_attn_func(hp.sq, hp.sk, hp.sv, causal=True, window_size=(WINDOW - 1, WINDOW - 1))
+
+    def step():
+        for layer in range(N_GDN_LAYERS + N_SWA_LAYERS):
+            if layer % 4 == 0:
+                swa()
+            else:
+                gdn()
+
+    try:
+        for _ in range(warmup):
+            gdn()
+            swa()
+        torch.cuda.synchronize()
+        t_gdn = sorted(time_events(gdn, 5))[2]
+        t_swa = sorted(time_events(swa, 5))[2]
+        step()
+        torch.cuda.synchronize()
+        ts = sorted(time_events(step, iters))
+        ms = ts[len(ts) // 2]
+    except Exception as e:  # noqa: BLE001   (OOM at very long T is a result, not a failure of the bench)
+        torch.cuda.empty_cache()
+        return {**res, "unavailable": f"reference GPU path failed at T={T}: {type(e).__name__}: {str(e)[:200]}"}
+    res.update({"ms_per_step": round(ms, 3), "tokens_per_s": round(T / (ms * 1e-3), 1), "gdn_layer_ms": round(t_gdn, 4),
+                "swa_layer_ms": round(t_swa, 4), "ours_ms_per_step": round(ours_ms_step, 3),
+                "hot_path_ratio": round(ms / ours_ms_step, 3)})
+    return res
+
+
+def run_config2(dev, peaks, T=32768):
+    """BASELINE.json config 2: the same hot path at 32K tokens on one GPU (throughput + roofline of the GDN operator)."""
+    hp = HotPath(T, 0, 1, dev, seed=7)
+    for _ in range(3):
+        hp.step()
+    torch.cuda.synchronize()
+    ts = sorted(time_events(hp.step, 5))
+    ms = ts[len(ts) // 2]
+    fwd = sorted(time_events(lambda: hp.gdn_fwd(hp.h0), 10))
+    t_layer = fwd[len(fwd) // 2]
+    alg = GDN_BYTES_PER_TOKEN * T + GDN_STATE_BYTES
+    out = {"seq_len": T, "ms_per_step": round(ms, 3), "tokens_per_s": round(T / (ms * 1e-3), 1),
+           "gdn_layer_ms": round(t_layer, 4), "gdn_achieved_gbs": round(alg / (t_layer * 1e-3) / 1e9, 1),
+           "gdn_hbm_frac": round(alg / (t_layer * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+    if hp.has_swa:
+        sw = sorted(time_events(hp.swa_layer, 5))
+        t_swa = sw[len(sw) // 2]
+        out.update({"swa_fwd_ms": round(t_swa, 4), "swa_tflops": round(swa_flops(T) / (t_swa * 1e-3) / 1e12, 1)})
+    del hp
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sweep(args):
+    """BASELINE.json config 5: prefill throughput of the hot path for T = 4K ... 1M at this world size, next to the
+    reference's GPU path (one GPU only: the reference does not shard a sequence).  Writes one JSON file."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rows = []
+    for T in [int(x) for x in args.sweep.split(",")]:
+        if T % (64 * world):
+            continue
+        row = {"seq_len": T, "n_gpus": world}
+        try:
+            hp = HotPath(T // world, rank, world, dev)
+            for _ in range(2):
+                hp.step()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                hp.step()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / 3], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            row.update({"ms_per_step": round(t.item(), 3), "tokens_per_s": round(T / (t.item() * 1e-3), 1)})
+            if world == 1 and not args.no_gpu_reference:
+                row["gpu_reference"] = gpu_reference(hp, T, t.item(), warmup=2, iters=2)
+            del hp
+        except Exception as e:  # noqa: BLE001
+            row["error"] = f"{type(e).__name__}: {str(e)[:200]}"
+        from infinitevl_b200 import ops
+        ops.release_workspaces()
+        torch.cuda.empty_cache()
+        rows.append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"sweep_n{world}.json"), "w") as f:
+            json.dump({"workload": "prefill hot path (27 GDN + 9 SWA mixer calls), synthetic", "rows": rows}, f, indent=1)
     if world > 1:
         dist.destroy_process_group()
 
@@ -458,11 +654,12 @@ def run_e2e(hp, args, world=1, dev=None):
     T = hp.T * world
     names = ["q", "k", "v", "g", "beta"] + (["sq", "sk", "sv"] if hp.has_swa else [])
     host = {n: getattr(hp, n).cpu().pin_memory() for n in names}
-    out_host = torch.empty(hp.o.shape, dtype=hp.o.dtype).pin_memory()
+    outs = ["o"] + (["so"] if hp.has_swa else [])      # every result of the step leaves the device
+    out_host = {n: torch.empty(getattr(hp, n).shape, dtype=getattr(hp, n).dtype).pin_memory() for n in outs}
     h2d = sum(x.numel() * x.element_size() for x in host.values())
-    d2h = out_host.numel() * out_host.element_size()
-    sets = [{n: getattr(hp, n) for n in names + ["o"]},
-            {n: torch.empty_like(getattr(hp, n)) for n in names + ["o"]}]
+    d2h = sum(x.numel() * x.element_size() for x in out_host.values())
+    sets = [{n: getattr(hp, n) for n in names + outs},
+            {n: torch.empty_like(getattr(hp, n)) for n in names + outs}]
     compute = torch.cuda.current_stream()
     copy = torch.cuda.Stream()
     fed = [torch.cuda.Event() for _ in range(2)]      # inputs of the set are on the device
@@ -483,13 +680,19 @@ def run_e2e(hp, args, world=1, dev=None):
         compute.wait_event(fed[i % 2])
         if i >= 2:
             compute.wait_event(read[i % 2])           # the previous output in this set has left the device
-        for n in names + ["o"]:
+        for n in names + outs:
             setattr(hp, n, st[n])
+        if world > 1 and hp.has_swa:     # sharded: the layers read K/V from their hand-off buffers
+            Hh = WINDOW - 1
+            for kb, vb in zip(hp.kbufs, hp.vbufs):
+                kb[:, Hh:].copy_(st["sk"])
+                vb[:, Hh:].copy_(st["sv"])
         hp.step()
         free[i % 2].record(compute)
         with torch.cuda.stream(copy):
             copy.wait_event(free[i % 2])
-            out_host.copy_(st["o"], non_blocking=True)
+            for n in outs:
+                out_host[n].copy_(st[n], non_blocking=True)
             read[i % 2].record(copy)
 
     def barrier():
@@ -513,7 +716,7 @@ def run_e2e(hp, args, world=1, dev=None):
     copy.synchronize()
     b.record()
     barrier()
-    for n in names + ["o"]:
+    for n in names + outs:
         setattr(hp, n, sets[0][n])
     ms_t = torch.tensor([a.elapsed_time(b) / steps], device=hp.dev)
     if world > 1:
@@ -596,10 +799,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-config2", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--sweep", default=None, nargs="?", const="4096,8192,16384,32768,65536,131072,262144,524288,1048576",
+                    help="comma-separated sequence lengths: run the config-5 sweep instead of the bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.sweep:
+        run_sweep(args)
     else:
         run_ours(args)
 

@@ -130,7 +130,7 @@ class StaticLinearLayerPrealloc:
     is_sliding = False
 
     def __init__(self, *, config, batch_size: int, device="cpu", dtype=torch.float32, zero_init: bool = False,
-                 recurrent_state_shape: Optional[Tuple[int, ...]] = None):
+                 recurrent_state_shape: Optional[Tuple[int, ...]] = None, state_dtype: Optional[torch.dtype] = None):
         cfg = _get_decoder_cfg(config)
         self.num_linear_heads = int(getattr(cfg, "num_linear_heads", getattr(cfg, "num_attention_heads")))
         self.num_linear_kv_heads = int(getattr(cfg, "num_linear_key_value_heads", self.num_linear_heads))
@@ -156,7 +156,10 @@ class StaticLinearLayerPrealloc:
             recurrent_state_shape = (B, Hq, C, Cv)
         else:
             assert recurrent_state_shape[0] == B, "recurrent_state_shape batch dim must match pre-allocated batch_size"
-        self.recurrent_state = alloc(tuple(recurrent_state_shape), dtype=dtype, device=device)
+        # state_dtype (extension): keep S in fp32 instead of re-rounding it to the cache dtype at
+        # every call boundary (Appendix B point 11) -- what the sequence-sharded prefill hands over so that the
+        # sharded run reproduces the one-GPU run.  None = the reference's behaviour (cache dtype).
+        self.recurrent_state = alloc(tuple(recurrent_state_shape), dtype=state_dtype or dtype, device=device)
 
     def update(self, key_states=None, value_states=None, conv_state: Optional[tuple] = None,
                recurrent_state: Optional[torch.Tensor] = None, cache_kwargs: Optional[dict] = None) -> tuple:
@@ -226,7 +229,7 @@ class StaticCachePrealloc:
 
     def __init__(self, *, config, batch_size: int = 1, device="cpu", dtype=torch.float32, zero_init: bool = False,
                  recurrent_state_shape: Optional[Tuple[int, ...]] = None, offloading: bool = False,
-                 offload_only_non_sliding: bool = False):
+                 offload_only_non_sliding: bool = False, state_dtype: Optional[torch.dtype] = None):
         cfg = _get_decoder_cfg(config)
         layer_types = getattr(cfg, "layer_types", None)
         if layer_types is None:
@@ -241,7 +244,8 @@ class StaticCachePrealloc:
             elif lt in ("linear_attention", "delta_net", "retnet", "state_space"):
                 self.layers.append(StaticLinearLayerPrealloc(config=cfg, batch_size=batch_size, device=device,
                                                              dtype=dtype, zero_init=zero_init,
-                                                             recurrent_state_shape=recurrent_state_shape))
+                                                             recurrent_state_shape=recurrent_state_shape,
+                                                             state_dtype=state_dtype))
             # full-attention layers are skipped, as in the reference (std:417-421); the shipped config has none
 
     def update(self, layer_idx: int, key_states=None, value_states=None, conv_state=None, recurrent_state=None,

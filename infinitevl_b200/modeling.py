@@ -472,10 +472,10 @@ class HybridDecoder(nn.Module):
         self.rotary_emb = InfiniteVLRotaryEmbedding(config=config)
         self.mixers_only = mixers_only
 
-    def allocate_inference_cache(self, batch_size: int, device=None, dtype=None):
+    def allocate_inference_cache(self, batch_size: int, device=None, dtype=None, state_dtype=None):
         p = next(self.parameters())
         return StaticCachePrealloc(config=self.config, batch_size=batch_size, device=device or p.device,
-                                   dtype=dtype or p.dtype)
+                                   dtype=dtype or p.dtype, state_dtype=state_dtype)
 
     @torch.no_grad()
     def forward(self, inputs_embeds, position_ids=None, past_key_values=None, cache_position=None, use_cache=None):
