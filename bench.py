@@ -181,7 +181,7 @@ class HotPath:
     def gdn_scan(self, h0):
         st = torch.cuda.current_stream().cuda_stream
         self._lib_mod.check(self.lib.ivl_gdn_chunk_scan(
-            h0.data_ptr(), 0, self.o.data_ptr(), self.ht.data_ptr(), 0, 1, self.T, H,
+            self.v.data_ptr(), h0.data_ptr(), 0, self.o.data_ptr(), self.ht.data_ptr(), 0, 1, self.T, H,
             self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_scan")
 
     def gdn_fwd(self, h0):
@@ -196,7 +196,7 @@ class HotPath:
     def gdn_scan_into(self, h0, ht):
         st = torch.cuda.current_stream().cuda_stream
         self._lib_mod.check(self.lib.ivl_gdn_chunk_scan(
-            h0.data_ptr(), 0, self.o.data_ptr(), ht.data_ptr(), 0, 1, self.T, H,
+            self.v.data_ptr(), h0.data_ptr(), 0, self.o.data_ptr(), ht.data_ptr(), 0, 1, self.T, H,
             self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_scan")
 
     def _post_recv(self, layer):

@@ -104,12 +104,13 @@ IVL_API int ivl_gdn_chunk_fwd_varlen(const void* q, const void* k, const void* v
 
 /* The two halves of the above, exposed so that the bench can time them separately and so that a
  * sequence-sharded caller can start prep before the previous rank's state has arrived.  prep must
- * have been enqueued on `stream` (or be otherwise ordered) before scan. */
+ * have been enqueued on `stream` (or be otherwise ordered) before scan.  `v` is the same value tensor prep was given:
+ * the scan reads its tiles itself (prep only writes the operands derived from q, k, g, beta). */
 IVL_API int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                        int B, int T, int H, float scale, int l2norm_qk, void* workspace,
                        size_t workspace_bytes, void* stream);
-IVL_API int ivl_gdn_chunk_scan(const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T,
-                       int H, void* workspace, size_t workspace_bytes, void* stream);
+IVL_API int ivl_gdn_chunk_scan(const void* v, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B,
+                       int T, int H, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Gated DeltaNet, ONE decode step of the whole mixer core in one launch: everything between the input

@@ -19,6 +19,8 @@
 //   ublob[b][h][slot][s] (4 KiB each, s = V slice of 32 columns): U = A (beta V), laid out
 //                        [piece p of 8 columns][token][8] so that a thread owning a token
 //                        row reads four conflict-free 16-byte pieces.
+//   Transposed scan (gdn_scan_t.cu): the first 8 KiB of the chunk's ublob region hold the Au image instead
+//                        (K-major no-swizzle [64][64], Au = T diag(beta)); U = Au V is formed by the scan itself.
 //   ready[b][h][c]      uint32 flag, zeroed by the host entry point before the launch and set to 1
 //                       (release, gpu scope) by the prep CTA once every image of the chunk is written.
 //                       The scan's copy warp polls it (acquire), so the two kernels can run
@@ -57,6 +59,7 @@ constexpr uint32_t TAIL_BYTES = 128;             // gamma (fp32) + padding: what
 constexpr uint32_t TAIL_STRIDE = 1024;           // what the blob reserves, so that blobs stay 1 KiB aligned
 constexpr uint32_t BLOB_BYTES = P_BYTES + A1_BYTES + KT_BYTES + TAIL_STRIDE;  // 57 KiB
 constexpr uint32_t UBLOB_BYTES = 64 * GDN_BV * 2;               // 4 KiB
+constexpr uint32_t AU_BYTES = 64 * 64 * 2;                      // 8 KiB: Au = T diag(beta) image (transposed scan)
 
 constexpr uint32_t BLOB_OFF_A1 = 0;
 constexpr uint32_t BLOB_OFF_P = A1_BYTES;

@@ -130,6 +130,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define PTR(slot) do { } while (0)
 #endif
 
+// TR = true: operands for the transposed scan (gdn_scan_t.cu).  That kernel forms U = Au V itself from the raw
+// value rows (one more small MMA per chunk on a tensor pipe it does not saturate), so this kernel neither reads V
+// nor writes the eight U slices: it emits the 8 KiB Au image instead (a third less tensor work, half the loads
+// and 36 % fewer image bytes per chunk).
+template <bool TR>
 __global__ void __launch_bounds__(PREP_THREADS, 3)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
@@ -179,7 +184,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
         const size_t poff = ((ptok + row) * H + ph) * GDN_K + qt * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q + poff));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(k + poff));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(v + ((ptok + row) * H + ph) * GDN_V + qt * 64));
+        if (!TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(v + ((ptok + row) * H + ph) * GDN_V + qt * 64));
         if (qt == 0) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (ptok + row) * H + ph));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(beta + (ptok + row) * H + ph));
@@ -187,15 +192,17 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       }
     }
   }
-  for (int i = tid; i < 64 * 16; i += PREP_THREADS) {
-    const int row = i >> 4, piece = i & 15;
-    __nv_bfloat16* dst = &s.vb[row * V_LD + piece * 8];
-    if (row < valid)
-      cp_async16(dst, v + ((tok0 + row) * H + h) * GDN_V + piece * 8);
-    else
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  if (!TR) {
+    for (int i = tid; i < 64 * 16; i += PREP_THREADS) {
+      const int row = i >> 4, piece = i & 15;
+      __nv_bfloat16* dst = &s.vb[row * V_LD + piece * 8];
+      if (row < valid)
+        cp_async16(dst, v + ((tok0 + row) * H + h) * GDN_V + piece * 8);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < 64 * L_LD; i += PREP_THREADS) sL[i] = 0.f;
   if (warp == 0) {
     float g0 = (lane < valid) ? g[(tok0 + lane) * H + h] : 0.f;
@@ -423,15 +430,25 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   PTR(6);
   // T is dead: fetch value columns 128..255 into its place while Wg and the first half of U are computed
   __nv_bfloat16* const vb2 = s.qh;
-  for (int i = tid; i < 64 * 16; i += PREP_THREADS) {
-    const int row = i >> 4, piece = i & 15;
-    __nv_bfloat16* dst = &vb2[row * V_LD + piece * 8];
-    if (row < valid)
-      cp_async16(dst, v + ((tok0 + row) * H + h) * GDN_V + 128 + piece * 8);
-    else
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  if (!TR) {
+    for (int i = tid; i < 64 * 16; i += PREP_THREADS) {
+      const int row = i >> 4, piece = i & 15;
+      __nv_bfloat16* dst = &vb2[row * V_LD + piece * 8];
+      if (row < valid)
+        cp_async16(dst, v + ((tok0 + row) * H + h) * GDN_V + 128 + piece * 8);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+    // Au image for the transposed scan: K-major no-swizzle [64 rows i][64 k = j] (core (i/8, j/8) at
+    // (i/8) * 1024 + (j/8) * 128), 16-byte pieces, eight consecutive threads fill one 128-byte core matrix
+    for (int e = tid; e < 512; e += PREP_THREADS) {
+      const int r = e & 7, kg = (e >> 3) & 7, rg = e >> 6, i = rg * 8 + r;
+      *reinterpret_cast<uint4*>(ublob + rg * 1024 + kg * 128 + r * 16) =
+          *reinterpret_cast<const uint4*>(&sAu[i * A_LD + kg * 8]);
+    }
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   // ---- stage 4: Wg = Aw Kn (negated, into rows 0..63 of the A1 image), U = Au V ------------
   // warp (strip, half): key dims 64*half..+63 of Wg; value columns 128*hv + 64*half..+63 of U in pass hv
   {
@@ -464,7 +481,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
       *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(-acc[lt][2], -acc[lt][3]);
     }
 #pragma unroll
-    for (int hv = 0; hv < 2; ++hv) {  // two passes of 64 value columns, one per staged half of V
+    for (int hv = 0; hv < (TR ? 0 : 2); ++hv) {  // two passes of 64 value columns, one per staged half of V
       const int vbase = hv * 128 + half * 64;
       const __nv_bfloat16* vsrc = hv == 0 ? s.vb : vb2;
       if (hv == 1) {
@@ -537,7 +554,9 @@ cudaError_t configure_gdn_prep() {
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (!configured[dev].load(std::memory_order_acquire)) {
-    e = cudaFuncSetAttribute(gdn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
+    e = cudaFuncSetAttribute(gdn_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gdn_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
     if (e != cudaSuccess) return e;
     configured[dev].store(true, std::memory_order_release);
   }
@@ -549,7 +568,7 @@ cudaError_t configure_gdn_prep() {
 // vl.chunk_tok0 != nullptr: packed variable-length batch (B must be 1) of num_chunks chunks
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                             const GdnWorkspace& ws, const GdnVarlen& vl, int num_chunks, int B, int T, int H,
-                            float scale, int l2norm, int scan_ctas_per_head, cudaStream_t stream) {
+                            float scale, int l2norm, int scan_ctas_per_head, int transposed, cudaStream_t stream) {
   const int smem = (int)sizeof(PrepSmem);
   if (cudaError_t e = configure_gdn_prep()) return e;
   static int resident = 0;
@@ -560,7 +579,8 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
     resident = 3 * sms;
   }
   dim3 grid((unsigned)num_chunks * (unsigned)H, 1, B);
-  gdn_prep_kernel<<<grid, PREP_THREADS, smem, stream>>>(
+  auto kern = transposed ? gdn_prep_kernel<true> : gdn_prep_kernel<false>;
+  kern<<<grid, PREP_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
       static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, vl, T, H, scale, l2norm,
       resident, scan_ctas_per_head);

@@ -16,8 +16,11 @@
 namespace ivl {
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                             const GdnWorkspace& ws, const GdnVarlen& vl, int num_chunks, int B, int T, int H,
-                            float scale, int l2norm, int scan_ctas_per_head, cudaStream_t stream);
+                            float scale, int l2norm, int scan_ctas_per_head, int transposed, cudaStream_t stream);
 cudaError_t configure_gdn_prep();
+cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, int B,
+                              const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H,
+                              cudaStream_t stream);
 cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, const void* h0,
                             int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int bv, cudaStream_t stream);
 cudaError_t launch_gdn_decode_step(const void* q_in, const void* k_in, const void* v_in, const void* a_in,
@@ -71,6 +74,9 @@ inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
+//   IVL_GDN_TSCAN 1 = transposed scan (gdn_scan_t.cu: two CTAs per head, state and v_new as TMEM A operands;
+//                 default), 0 = row-major scan (gdn_scan.cu: 32/64/128-column slices)
+inline bool tscan() { return env_int("IVL_GDN_TSCAN", 1) != 0; }
 inline int scan_bv(int dflt) {
   const int bv = env_int("IVL_GDN_BV", dflt);
   return (bv == 32 || bv == 64 || bv == 128) ? bv : dflt;
@@ -217,21 +223,25 @@ int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T, H), st));
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, T, H,
-                                default_scale(scale, ivl::GDN_K), l2norm_qk, 0, st));
+                                default_scale(scale, ivl::GDN_K), l2norm_qk, 0, tscan() ? 1 : 0, st));
   return IVL_OK;
 }
 
-int ivl_gdn_chunk_scan(const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H,
+int ivl_gdn_chunk_scan(const void* v, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H,
                        void* workspace, size_t workspace_bytes, void* stream) {
   if (int e = check_gdn_shape(B, T, H, ivl::GDN_K, ivl::GDN_V)) return e;
-  if (!o || !workspace) return IVL_ERR_NULL;
+  if (!v || !o || !workspace) return IVL_ERR_NULL;
   if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
   if (workspace_bytes < ivl::gdn_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
     return IVL_ERR_WORKSPACE;
   IVL_ARCH();
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, /*ring=*/0);
-  IVL_CUDA(ivl::launch_gdn_scan(ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, h0, h0_dtype, o, ht, ht_dtype, T, H,
-                                scan_bv(32), static_cast<cudaStream_t>(stream)));
+  if (tscan())
+    IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, B, h0, h0_dtype, o, ht, ht_dtype,
+                                    T, H, static_cast<cudaStream_t>(stream)));
+  else
+    IVL_CUDA(ivl::launch_gdn_scan(ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, h0, h0_dtype, o, ht, ht_dtype, T, H,
+                                  scan_bv(32), static_cast<cudaStream_t>(stream)));
   return IVL_OK;
 }
 
@@ -274,14 +284,18 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   // or, failing that, the back-to-back form.
   int sms = 0;
   IVL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int bv_overlap = scan_bv(64);
+  const bool tr = tscan();
+  int bv_overlap = tr ? 128 : scan_bv(64);   // the transposed scan always owns 128 value columns per CTA
   if ((long long)nseq * H * (ivl::GDN_V / bv_overlap) > sms / 2) bv_overlap = 128;
   const bool fits = (long long)nseq * H * (ivl::GDN_V / bv_overlap) <= sms / 2;
   if (first || !fits || env_int("IVL_GDN_PIPE", overlap_default) == 0) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, st));
-    IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, tr ? 1 : 0, st));
+    if (tr)
+      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, st));
+    else
+      IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
     return IVL_OK;
   }
   // Overlapped form.  The scan goes first, on the caller's stream, with 64-column slices: its few CTAs (64 at
@@ -295,8 +309,11 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   if (other_busy) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, st));
-    IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, tr ? 1 : 0, st));
+    if (tr)
+      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, st));
+    else
+      IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
     return IVL_OK;
   }
   // The image ring (gdn_layout.cuh: prep reuses a short ring of chunk slots and waits for the scan's progress)
@@ -313,9 +330,13 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
   IVL_CUDA(cudaEventRecord(fj->fork, st));
   IVL_CUDA(cudaStreamWaitEvent(fj->aux, fj->fork, 0));
-  IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, bv, st));
+  if (tr)
+    IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, st));
+  else
+    IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, bv, st));
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
-  IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv, fj->aux));
+  IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv,
+                                tr ? 1 : 0, fj->aux));
   IVL_CUDA(cudaEventRecord(fj->join, fj->aux));
   IVL_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   if (cap == cudaStreamCaptureStatusNone) {

@@ -40,7 +40,9 @@ def gdn_workspace(B: int, T: int, H: int, device) -> torch.Tensor:
     layers so that steady-state calls allocate nothing -- a CUDA-graph requirement)."""
     lib = _lib.load()
     need = lib.ivl_gdn_chunk_workspace_bytes(B, T, H)
-    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need + 1024:
         if torch.cuda.is_current_stream_capturing():

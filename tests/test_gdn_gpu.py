@@ -116,13 +116,17 @@ def test_split_scan_is_bit_identical_at_full_size(ops):
     assert err_ratio(ro, o[:, T - tail:].float().cpu()) < TOL_O and err_ratio(rs, s.cpu()) < TOL_S
 
 
+@pytest.mark.parametrize("tscan", ["1", "0"])
 @pytest.mark.parametrize("T,H", [(2048, 16), (4160, 4), (100, 2)])
-def test_overlapped_and_sliced_variants_are_bit_identical(ops, monkeypatch, T, H):
+def test_overlapped_and_sliced_variants_are_bit_identical(ops, monkeypatch, T, H, tscan):
     """ivl_gdn_chunk_fwd either runs prep then scan on the caller's stream or overlaps them on two streams
-    (the scan following prep's per-chunk ready flags), and the scan owns 32, 64 or 128 value columns per CTA.  The arithmetic per value column is
-    the same in every form, so all of them must agree bit for bit, under CUDA-graph replay too.  Every form
+    (the scan following prep's per-chunk ready flags); the scan is the transposed kernel (IVL_GDN_TSCAN=1: two CTAs
+    per head) or the row-major one owning 32, 64 or 128 value columns per CTA.  Within one scan kernel the
+    arithmetic per value column is the same in every form, so the forms must agree bit for bit, under CUDA-graph
+    replay too; the two scan kernels round at different points and agree within the oracle tolerance.  Every form
     gets fresh inputs in the same (cached) workspace, so an image or gamma read before it was published shows up
     as a mismatch."""
+    monkeypatch.setenv("IVL_GDN_TSCAN", tscan)
     seed = 3
     for pipe, bv, ring in ((1, 64, 32), (1, 128, 8), (1, 32, 9), (0, 64, 0), (0, 128, 0), (1, 64, 8)):
         seed += 1
@@ -163,6 +167,20 @@ def test_overlapped_and_sliced_variants_are_bit_identical(ops, monkeypatch, T, H
         gr.replay()
         torch.cuda.synchronize()
         assert torch.equal(og, o0) and torch.equal(sg, s0)
+
+
+def test_transposed_and_row_major_scans_agree(ops, monkeypatch):
+    """The two scan kernels (gdn_scan_t.cu / gdn_scan.cu) implement the same recurrence with the same bf16 operand
+    roundings except for the order of the fp32 sums (U is formed inside the transposed scan's accumulator and never
+    rounded to bf16): they agree with each other far inside the oracle tolerance."""
+    q, k, v, g, beta, h0 = _cuda(gdn_inputs(T=1536, H=4, seed=17))
+    outs = {}
+    for tscan in ("1", "0"):
+        monkeypatch.setenv("IVL_GDN_TSCAN", tscan)
+        outs[tscan] = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                                 use_qk_l2norm_in_kernel=True)
+    assert err_ratio(outs["0"][0].float(), outs["1"][0].float()) < 4e-3
+    assert err_ratio(outs["0"][1], outs["1"][1]) < 4e-3
 
 
 def test_chunk_then_recurrent_streaming(ops):

@@ -43,7 +43,7 @@ def main():
                                               1, T, 16, 0.0, 1, ws.data_ptr(), ws.numel(), st), "prep")
 
         def scan():
-            _lib.check(lib.ivl_gdn_chunk_scan(h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, 16,
+            _lib.check(lib.ivl_gdn_chunk_scan(v.data_ptr(), h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, 16,
                                               ws.data_ptr(), ws.numel(), st), "scan")
 
         for name, fn in (("prep", prep), ("scan", scan)):

@@ -19,7 +19,7 @@ for H in (1, 2, 4, 8, 12, 16):
         _lib.check(lib.ivl_gdn_chunk_prep(q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(),
                                           1, T, H, 0.0, 1, ws.data_ptr(), ws.numel(), st), "prep")
     def scan():
-        _lib.check(lib.ivl_gdn_chunk_scan(h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, H,
+        _lib.check(lib.ivl_gdn_chunk_scan(v.data_ptr(), h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, H,
                                           ws.data_ptr(), ws.numel(), st), "scan")
     res = {}
     for name, fn in (("prep", prep), ("scan", scan)):

@@ -52,7 +52,7 @@ def prep():
 
 
 def scan():
-    _lib.check(lib.ivl_gdn_chunk_scan(h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, H,
+    _lib.check(lib.ivl_gdn_chunk_scan(v.data_ptr(), h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, H,
                                       ws.data_ptr(), ws.numel(), st), "scan")
 
 

@@ -23,11 +23,11 @@ ws = torch.empty(need + 1024, dtype=torch.uint8, device="cuda"); off = (-ws.data
 o = torch.empty(1, T, 16, 256, dtype=torch.bfloat16, device="cuda"); ht = torch.empty(1, 16, 128, 256, device="cuda")
 P = ctypes.c_void_p
 lib.ivl_gdn_chunk_prep.argtypes = [P] * 5 + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, P, ctypes.c_size_t, P]
-lib.ivl_gdn_chunk_scan.argtypes = [P, ctypes.c_int, P, P, ctypes.c_int] + [ctypes.c_int] * 3 + [P, ctypes.c_size_t, P]
+lib.ivl_gdn_chunk_scan.argtypes = [P, P, ctypes.c_int, P, P, ctypes.c_int] + [ctypes.c_int] * 3 + [P, ctypes.c_size_t, P]
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(3):
     assert lib.ivl_gdn_chunk_prep(q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(), 1, T, 16, 0.0, 1, ws.data_ptr(), need, st) == 0
-    assert lib.ivl_gdn_chunk_scan(h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, 16, ws.data_ptr(), need, st) == 0
+    assert lib.ivl_gdn_chunk_scan(v.data_ptr(), h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, 16, ws.data_ptr(), need, st) == 0
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * (64 * 16))()
 lib.ivl_debug_read_trace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
