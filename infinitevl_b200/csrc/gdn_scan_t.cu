@@ -26,7 +26,8 @@
 // The U part of chunk c+1 does not depend on the state and is issued right behind chunk c's products, so the
 // serial chain per chunk is  W part -> epi V -> B part -> epi S.
 // Warp roles: warp 0 copies (TMA engine; follows the pre-pass's ready flags), warp 1 issues the MMAs, warps 2..5
-// are the v_new / output epilogue, warps 6..9 own the state (TMEM lane quadrant = warp % 4 in both groups).
+// are the v_new / output epilogue, warps 6..13 own the state (TMEM lane quadrant = warp % 4 in both groups; two
+// state warps per quadrant split the 128 key dims).
 #include <atomic>
 #include <cuda.h>
 
@@ -38,7 +39,7 @@ namespace ivl {
 namespace {
 
 struct TCfg {
-  static constexpr int THREADS = 320;
+  static constexpr int THREADS = 448;   // 14 warps: copy, MMA, 4 v_new/output, 8 state
   static constexpr int NA = 2, NK = 2;
   // A slot: operands that are dead once the W and O parts have retired (early in the step)
   static constexpr uint32_t A_BW = 0;                         // [-Wg ; Qg]  32 KiB, K-major, no swizzle
@@ -80,9 +81,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_t(const uint32_t* p) {
   return v;
 }
 
-// 200 registers: a state thread keeps 128 fp32 state entries for the whole sequence (320 threads x 200 fits the
-// register file; __launch_bounds__(320) alone makes ptxas budget for 384 threads = 168 registers, which spills)
-__global__ void __maxnreg__(200)
+// 448 threads: registers are granted per four warps, so the budget is 65536 / 512 = 128 per thread -- a state thread
+// keeps 64 fp32 state entries (half a row of S^T) for the whole sequence plus one 32-column staging buffer
+__global__ void __launch_bounds__(TCfg::THREADS, 1)
 gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnVarlen vl, const void* __restrict__ h0,
                   int h0_dtype, __nv_bfloat16* __restrict__ o, void* __restrict__ ht, int ht_dtype, int T, int H,
                   int NTROW) {
@@ -123,10 +124,10 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars.fullA[s], 1); mbar_init(&bars.emptyA[s], 1);
       mbar_init(&bars.fullK[s], 1);
-      mbar_init(&bars.emptyK[s], 1 + 4);   // the C part has retired + the four state warps have read gamma
+      mbar_init(&bars.emptyK[s], 1 + 8);   // the C part has retired + the eight state warps have read gamma
       mbar_init(&bars.dv[s], 1); mbar_init(&bars.dofull[s], 1); mbar_init(&bars.dofree[s], 4);
     }
-    mbar_init(&bars.sb, 4); mbar_init(&bars.vb, 4); mbar_init(&bars.ds, 1);
+    mbar_init(&bars.sb, 8); mbar_init(&bars.vb, 4); mbar_init(&bars.ds, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmV);
   }
@@ -281,31 +282,29 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
     output(NT - 1);
   } else {
     // ------------------------------- state warps ---------------------------------------
-    const int quad = warp & 3;
+    // two warps per TMEM lane quadrant: warp (quad, half) owns key dims 64 * half .. + 63 of its 32 value columns
+    const int quad = warp & 3, half = (warp - 6) >> 2;
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const int col = col0 + quad * 32 + lane;
-    float S[128];                                // S^T row of this value column: all 128 key dims, fp32
-    const size_t sbase_off = ((size_t)seq * H + h) * GDN_K * GDN_V + col;
+    float S[64];                                 // half a row of S^T (this value column, 64 key dims), fp32
+    const size_t sbase_off = (((size_t)seq * H + h) * GDN_K + half * 64) * GDN_V + col;
     if (h0 == nullptr) {
 #pragma unroll
-      for (int i = 0; i < 128; ++i) S[i] = 0.f;
+      for (int i = 0; i < 64; ++i) S[i] = 0.f;
     } else if (h0_dtype == 0) {
       const float* p = static_cast<const float*>(h0) + sbase_off;
 #pragma unroll
-      for (int i = 0; i < 128; ++i) S[i] = __ldg(p + (size_t)i * GDN_V);
+      for (int i = 0; i < 64; ++i) S[i] = __ldg(p + (size_t)i * GDN_V);
     } else {
       const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(h0) + sbase_off;
 #pragma unroll
-      for (int i = 0; i < 128; ++i) S[i] = __bfloat162float(p[(size_t)i * GDN_V]);
+      for (int i = 0; i < 64; ++i) S[i] = __bfloat162float(p[(size_t)i * GDN_V]);
     }
-    uint32_t r[32], w[32];
+    uint32_t r[32];
     auto publish = [&]() {   // bf16 S^T -> TMEM A operand (word i = key dims 2i, 2i+1)
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) w[i] = pack_bf16(S[hlf * 64 + 2 * i], S[hlf * 64 + 2 * i + 1]);
-        tmem_st32(tlane + C::TM_SB + hlf * 32, w);
-      }
+      for (int i = 0; i < 32; ++i) r[i] = pack_bf16(S[2 * i], S[2 * i + 1]);
+      tmem_st32(tlane + C::TM_SB + half * 32, r);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -321,8 +320,8 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
       mbar_wait(&bars.ds, c & 1);
       tc_fence_after();
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        tmem_ld32(tlane + C::TM_DS + p * 32, r);
+      for (int p = 0; p < 2; ++p) {
+        tmem_ld32(tlane + C::TM_DS + half * 64 + p * 32, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) S[p * 32 + i] = fmaf(gamma, S[p * 32 + i], __uint_as_float(r[i]));
@@ -337,11 +336,11 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
       if (ht_dtype == 0) {
         float* p = static_cast<float*>(ht) + sbase_off;
 #pragma unroll
-        for (int i = 0; i < 128; ++i) p[(size_t)i * GDN_V] = S[i];
+        for (int i = 0; i < 64; ++i) p[(size_t)i * GDN_V] = S[i];
       } else {
         __nv_bfloat16* p = static_cast<__nv_bfloat16*>(ht) + sbase_off;
 #pragma unroll
-        for (int i = 0; i < 128; ++i) p[(size_t)i * GDN_V] = __float2bfloat16(S[i]);
+        for (int i = 0; i < 64; ++i) p[(size_t)i * GDN_V] = __float2bfloat16(S[i]);
       }
     }
   }
