@@ -69,6 +69,18 @@ struct TCfg {
   static_assert(SMEM <= 232448, "exceeds 227 KiB");
 };
 
+// Developer-only timeline probe (compiled in with -DIVL_TRACE by tools/trace_tscan.py; never in the product build)
+#ifdef IVL_TRACE
+__device__ long long ivl_ttrace_buf[64 * 16];
+#define TTR(slot)                                                                                        \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && c >= 1000 && c < 1064)                        \
+      ivl_ttrace_buf[(c - 1000) * 16 + (slot)] = clock64();                                              \
+  } while (0)
+#else
+#define TTR(slot) do { } while (0)
+#endif
+
 struct TBars {
   uint64_t fullA[2], emptyA[2], fullK[2], emptyK[2];
   uint64_t sb, vb, ds, dv[2], dofull[2], dofree[2];
@@ -206,15 +218,18 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
       mbar_wait(&bars.sb, c & 1);                                    // bf16 S_c^T is in tensor memory
       if (c >= 2) mbar_wait(&bars.dofree[buf], ((c >> 1) - 1) & 1);  // O accumulator of chunk c - 2 has been read
       tc_fence_after();
+      TTR(0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(dvb, tm + C::TM_SB + j * 8, dW + j * 16, idesc64, 1);
       umma_commit_ws(&bars.dv[buf]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(dob, tm + C::TM_SB + j * 8, dQ + j * 16, idesc64, j > 0);
       umma_commit_ws(&bars.emptyA[sa]);
+      TTR(1);
       mbar_wait(&bars.fullK[sk], (c / C::NK) & 1);
       mbar_wait(&bars.vb, c & 1);                                    // bf16 v_new^T is in tensor memory
       tc_fence_after();
+      TTR(2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DS, tm + C::TM_VB + j * 8, dKt + j * 16, idescB, j > 0);
       umma_commit_ws(&bars.ds);
@@ -222,11 +237,13 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
       for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(dob, tm + C::TM_VB + j * 8, dP + j * 16, idesc64, 1);
       umma_commit_ws(&bars.dofull[buf]);
       umma_commit_ws(&bars.emptyK[sk]);
+      TTR(3);
       if (c + 1 < NT) {
         mbar_wait(&bars.fullA[(c + 1) % C::NA], ((c + 1) / C::NA) & 1);
         tc_fence_after();
         issue_u(c + 1);
       }
+      TTR(4);
     }
   } else if (warp < 6) {
     // ------------------------------- v_new / output epilogue --------------------------
@@ -264,9 +281,11 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
       const int buf = c & 1;
       mbar_wait(&bars.dv[buf], (c >> 1) & 1);
       tc_fence_after();
+      if (quad == 0) TTR(5);
       tmem_ld32(tlane + C::TM_DV + buf * 64, r);
       tmem_ld32(tlane + C::TM_DV + buf * 64 + 32, r2);
       tmem_ld_wait();
+      if (quad == 0) TTR(6);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         w[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
@@ -277,7 +296,9 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.vb);
+      if (quad == 0) TTR(7);
       if (c > 0) output(c - 1);
+      if (quad == 0) TTR(8);
     }
     output(NT - 1);
   } else {
@@ -319,6 +340,7 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
       if (lane == 0) mbar_arrive(&bars.emptyK[sk]);
       mbar_wait(&bars.ds, c & 1);
       tc_fence_after();
+      if (warp == 8) TTR(9);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         tmem_ld32(tlane + C::TM_DS + half * 64 + p * 32, r);
@@ -326,11 +348,13 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
 #pragma unroll
         for (int i = 0; i < 32; ++i) S[p * 32 + i] = fmaf(gamma, S[p * 32 + i], __uint_as_float(r[i]));
       }
+      if (warp == 8) TTR(10);
       if (c + 1 < NT) {
         publish();
       } else {
         tc_fence_before();
       }
+      if (warp == 8) TTR(11);
     }
     if (ht != nullptr) {
       if (ht_dtype == 0) {
@@ -401,5 +425,11 @@ cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVa
                                                            ht_dtype, T, H, ntrow);
   return cudaGetLastError();
 }
+
+#ifdef IVL_TRACE
+extern "C" __attribute__((visibility("default"))) int ivl_debug_read_ttrace(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, ivl_ttrace_buf, sizeof(long long) * n);
+}
+#endif
 
 }  // namespace ivl
