@@ -21,6 +21,8 @@
 //                        row reads four conflict-free 16-byte pieces.
 //   Transposed scan (gdn_scan_t.cu): the first 8 KiB of the chunk's ublob region hold the Au image instead
 //                        (K-major no-swizzle [64][64], Au = T diag(beta)); U = Au V is formed by the scan itself.
+//                        Lag form: the next 8 KiB hold -R_c = -Wg_c Kt_{c-1}^T (same layout; k = token of chunk c-1)
+//                        and rows 0..63 of the A1 image hold -gamma_{c-1} Wg_c.
 //   ready[b][h][c]      uint32 flag, zeroed by the host entry point before the launch and set to 1
 //                       (release, gpu scope) by the prep CTA once every image of the chunk is written.
 //                       The scan's copy warp polls it (acquire), so the two kernels can run
@@ -73,6 +75,7 @@ struct GdnVarlen {
   const int* chunk_tok0;       // [num_chunks]  first token of the chunk on the flattened axis
   const int* chunk_valid;      // [num_chunks]  tokens in the chunk (1..64)
   const int* seq_chunk_begin;  // [N + 1]       chunks of sequence n are seq_chunk_begin[n] .. seq_chunk_begin[n+1]-1
+  int num_seqs;                // N
 };
 
 struct GdnWorkspace {

@@ -42,6 +42,7 @@ struct __align__(16) PrepSmem {
   float LA[2 * 64 * A_LD / 2];   // 18432 B >= 64 * L_LD floats
   float G[64];
   float beta[64];
+  float Gp[64];                  // lag form: cumsum of the previous chunk's g
 };
 static_assert(sizeof(float) * 64 * L_LD <= sizeof(PrepSmem::LA), "L must fit");
 static_assert(sizeof(__nv_bfloat16) * 64 * V_LD <= sizeof(PrepSmem::qh), "V half must fit in the q tile");
@@ -134,12 +135,21 @@ __device__ __forceinline__ unsigned long long gtime() {
 // value rows (one more small MMA per chunk on a tensor pipe it does not saturate), so this kernel neither reads V
 // nor writes the eight U slices: it emits the 8 KiB Au image instead (a third less tensor work, half the loads
 // and 36 % fewer image bytes per chunk).
-template <bool TR>
+//
+// MODE 0: row-major scan (U slices).  MODE 1: transposed scan (Au image).  MODE 2: transposed scan with the
+// shortened serial chain (gdn_scan_t.cu, lag form): v_new of chunk c is formed from the state BEFORE chunk c-1,
+//   v_new_c = U_c - gamma_{c-1} Wg_c S_{c-1} - (Wg_c Kt_{c-1}^T) v_new_{c-1},
+// so this kernel additionally scales the Wg rows by the previous chunk's decay gamma_{c-1} and emits the 64 x 64
+// coupling matrix R_c = Wg_c Kt_{c-1}^T (negated, 8 KiB image behind Au); the first chunk of a sequence has
+// gamma_{-1} = 1 and R = 0.  It recomputes Kt_{c-1} from the previous chunk's k rows and g (bit-identical to the
+// image the previous chunk's CTA writes, which the state update uses).
+template <int MODE>
 __global__ void __launch_bounds__(PREP_THREADS, 3)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
                 const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, GdnVarlen vl, int T, int H, float scale,
                 int l2norm, int prefetch_ahead, int scan_ctas_per_head) {
+  constexpr bool TR = MODE != 0, LAG = MODE == 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
   float* const sL = s.LA;                                                  // strictly lower triangular, fp32
@@ -157,6 +167,22 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   const size_t slot = ((size_t)b * H + h) * ws.ring + (c % ws.ring);  // where its images live
   uint8_t* blob = ws.blob + slot * BLOB_BYTES;
   uint8_t* ublob = ws.ublob + slot * (GDN_NS * UBLOB_BYTES);
+  // lag form: does this chunk have a predecessor in its own sequence?  (packed batches: c is the first chunk of a
+  // sequence iff it appears in seq_chunk_begin -- binary search, the table is sorted)
+  bool has_prev = false;
+  if (LAG) {
+    if (!varlen) {
+      has_prev = c > 0;
+    } else {
+      int lo = 0, hi = vl.num_seqs;   // find the last n with seq_chunk_begin[n] <= c
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(vl.seq_chunk_begin + mid) <= c) lo = mid; else hi = mid - 1;
+      }
+      has_prev = __ldg(vl.seq_chunk_begin + lo) != c;
+    }
+  }
+  const size_t ptok0 = (size_t)b * T + (has_prev ? (varlen ? __ldg(vl.chunk_tok0 + c - 1) : t0 - GDN_C) : 0);
 
 #ifdef IVL_TRACE
   if (tid == 0 && h < 16 && c < 2048) ivl_prep_tl[(h * 2048 + c) * 4 + 0] = gtime();
@@ -218,6 +244,19 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     s.beta[lane] = (lane < valid) ? __bfloat162float(beta[(tok0 + lane) * H + h]) : 0.f;
     s.beta[lane + 32] = (lane + 32 < valid) ? __bfloat162float(beta[(tok0 + lane + 32) * H + h]) : 0.f;
   }
+  if (LAG && warp == 2) {
+    // in-chunk cumsum of the previous chunk's g (a full chunk: only the last chunk of a sequence can be short)
+    float g0 = has_prev ? g[(ptok0 + lane) * H + h] : 0.f;
+    float g1 = has_prev ? g[(ptok0 + lane + 32) * H + h] : 0.f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      float a0 = __shfl_up_sync(0xffffffffu, g0, d), a1 = __shfl_up_sync(0xffffffffu, g1, d);
+      if (lane >= d) { g0 += a0; g1 += a1; }
+    }
+    g1 += __shfl_sync(0xffffffffu, g0, 31);
+    s.Gp[lane] = g0;
+    s.Gp[lane + 32] = g1;
+  }
   if (warp == 1 && c >= ws.ring) {
     // Ring hand-off (overlapped form only): the slot still holds chunk c - ring until every scan CTA of this
     // head has consumed it.  CTAs are dispatched in chunk order, so everything the scan is waiting for is
@@ -269,6 +308,39 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
                        return (uint32_t)((qt * 4 + p) * 1024 + (row >> 3) * 128 + (row & 7) * 16);
                      });
     if (tid == 0) *reinterpret_cast<float*>(blob + BLOB_OFF_TAIL) = __expf(Gc);
+  }
+  if (LAG && has_prev) {
+    // Kt_{c-1} rows (the previous chunk's normalised keys with their decay to the end of that chunk), bf16, into
+    // the value staging tile (unused in the transposed modes): the B operand of R = Wg Kt_{c-1}^T below
+    const int row = tid >> 2, qt = tid & 3;
+    uint4 rawp[4];
+    load_row_quarter(k + ((ptok0 + row) * H + h) * GDN_K + qt * 32, true, rawp);
+    float ss = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&rawp[p]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo = bf16_lo(w[e]), hi = bf16_hi(w[e]);
+        ss += lo * lo + hi * hi;
+      }
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    const float rstd = l2norm ? 1.0f / sqrtf(ss + 1e-6f) : 1.0f;
+    const float weight = __expf(s.Gp[63] - s.Gp[row]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&rawp[p]);
+      uint4 wgt;
+      uint32_t* gg = reinterpret_cast<uint32_t*>(&wgt);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t n = pack_bf16(bf16_lo(w[e]) * rstd, bf16_hi(w[e]) * rstd);
+        gg[e] = pack_bf16(bf16_lo(n) * weight, bf16_hi(n) * weight);
+      }
+      *reinterpret_cast<uint4*>(&s.vb[row * V_LD + qt * 32 + p * 8]) = wgt;
+    }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -473,12 +545,49 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
         }
       }
     }
+    const float wsc = (LAG && has_prev) ? -__expf(s.Gp[63]) : -1.f;   // lag form: - gamma_{c-1} Wg
 #pragma unroll
     for (int lt = 0; lt < 8; ++lt) {
       const int nt = half * 8 + lt;
       uint8_t* img = blob + BLOB_OFF_A1 + nt * 128 + tq * 4;
-      *reinterpret_cast<uint32_t*>(img + (i0 >> 3) * 2048 + (i0 & 7) * 16) = pack_bf16(-acc[lt][0], -acc[lt][1]);
-      *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(-acc[lt][2], -acc[lt][3]);
+      *reinterpret_cast<uint32_t*>(img + (i0 >> 3) * 2048 + (i0 & 7) * 16) = pack_bf16(wsc * acc[lt][0], wsc * acc[lt][1]);
+      *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(wsc * acc[lt][2], wsc * acc[lt][3]);
+      if (LAG) {   // bf16 Wg rows (unscaled) into the dead T tile: the A operand of R
+        *reinterpret_cast<uint32_t*>(&s.qh[i0 * KH_LD + nt * 8 + 2 * tq]) = pack_bf16(acc[lt][0], acc[lt][1]);
+        *reinterpret_cast<uint32_t*>(&s.qh[i1 * KH_LD + nt * 8 + 2 * tq]) = pack_bf16(acc[lt][2], acc[lt][3]);
+      }
+    }
+    if (LAG) {
+      // R = Wg Kt_{c-1}^T (64 x 64, contraction over the 128 key dims), negated, K-major no-swizzle image
+      // [row i = token of this chunk][k = j = token of the previous chunk] behind the Au image
+      __syncthreads();
+      float cr[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cr[i][e] = 0.f;
+      if (has_prev) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint32_t aw[4];
+          ldsm_x4(smem_u32(&s.qh[(r0 + (lane & 15)) * KH_LD + ks * 16 + (lane >> 4) * 8]), aw[0], aw[1], aw[2], aw[3]);
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            uint32_t b0, b1, b2, b3;
+            const int n = (half * 2 + pp) * 16 + (lane & 7) + (lane >> 4) * 8, kk = ks * 16 + ((lane >> 3) & 1) * 8;
+            ldsm_x4(smem_u32(&s.vb[n * V_LD + kk]), b0, b1, b2, b3);
+            mma16816(cr[2 * pp], aw, b0, b1);
+            mma16816(cr[2 * pp + 1], aw, b2, b3);
+          }
+        }
+      }
+#pragma unroll
+      for (int lt = 0; lt < 4; ++lt) {
+        const int nt = half * 4 + lt;
+        uint8_t* rimg = ublob + AU_BYTES + nt * 128 + tq * 4;
+        *reinterpret_cast<uint32_t*>(rimg + (i0 >> 3) * 1024 + (i0 & 7) * 16) = pack_bf16(-cr[lt][0], -cr[lt][1]);
+        *reinterpret_cast<uint32_t*>(rimg + (i1 >> 3) * 1024 + (i1 & 7) * 16) = pack_bf16(-cr[lt][2], -cr[lt][3]);
+      }
     }
 #pragma unroll
     for (int hv = 0; hv < (TR ? 0 : 2); ++hv) {  // two passes of 64 value columns, one per staged half of V
@@ -554,9 +663,11 @@ cudaError_t configure_gdn_prep() {
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (!configured[dev].load(std::memory_order_acquire)) {
-    e = cudaFuncSetAttribute(gdn_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
+    e = cudaFuncSetAttribute(gdn_prep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gdn_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
+    e = cudaFuncSetAttribute(gdn_prep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gdn_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
     if (e != cudaSuccess) return e;
     configured[dev].store(true, std::memory_order_release);
   }
@@ -579,7 +690,7 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
     resident = 3 * sms;
   }
   dim3 grid((unsigned)num_chunks * (unsigned)H, 1, B);
-  auto kern = transposed ? gdn_prep_kernel<true> : gdn_prep_kernel<false>;
+  auto kern = transposed == 2 ? gdn_prep_kernel<2> : (transposed == 1 ? gdn_prep_kernel<1> : gdn_prep_kernel<0>);
   kern<<<grid, PREP_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
       static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, vl, T, H, scale, l2norm,

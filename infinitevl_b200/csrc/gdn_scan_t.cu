@@ -373,6 +373,376 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
   if (warp == 1) tmem_dealloc<C::TM_COLS>(tmem);
 }
 
+
+// =====================================================================================================
+// Lag form of the transposed scan (operands from gdn_prep_kernel<2>): the serial chain is shortened from
+//   W part -> epi V -> B part -> epi S          (state -> v_new -> state, two tensor / epilogue round trips per chunk)
+// to
+//   R part -> epi V                             (v_new_c -> v_new_{c+1}: one 64 x 64 product per chunk)
+// by expanding the state inside v_new_{c+1} = U_{c+1} - Wg_{c+1} S_{c+1} with S_{c+1} = gamma_c S_c + Kt_c^T v_new_c:
+//   v_new_{c+1}^T = U_{c+1}^T - bf16(S_c^T) (gamma_c Wg_{c+1})^T - bf16(v_new_c^T) (Wg_{c+1} Kt_c^T)^T .
+// The state update (B part, epi S) and the outputs leave the chain; they only have to keep up on average, and the
+// state-dependent term of chunk c+2 is issued as soon as S_{c+1} is published.  Two MMA-issuing warps, one per
+// trigger, so that neither kind of product queues behind a wait for the other event:
+//   warp 1 (follows v_new):  R part(c+1) | B part(c) | C part(c)          after v_new_c is in tensor memory
+//   warp 2 (follows S):      X part(c+2) | O part(c+1) | U part(c+3)      after S_{c+1} is in tensor memory
+//     U part   DV[k]  = V_k^T Au_k^T                      SS  N64 K64
+//     X part   DV[k] += bf16(S_{k-1}^T) (-gamma Wg_k)^T   TS  N64 K128     (chunk 0: S_0 and the unscaled Wg_0)
+//     R part   DV[k] += bf16(v_new_{k-1}^T) (-R_k)^T      TS  N64 K64
+//     O part   DO[k]  = bf16(S_k^T) Qg_k^T                TS  N64 K128
+//     B part   DS     = bf16(v_new_k^T) Kt_k              TS  N128 K64
+//     C part   DO[k] += bf16(v_new_k^T) P_k^T             TS  N64 K64
+// tcgen05.commit only tracks the issuing thread's MMAs, so barriers that guard products of both warps take one
+// commit from each; an accumulator that one warp initialises and the other accumulates into is handed over
+// through a commit barrier (uinit, oinit).
+// Shared memory: E slots (early operands of a chunk: -gamma Wg rows, value tile, Au, -R: 48 KiB, dead once its
+// v_new accumulator is complete) and L slots (Qg rows, P, Kt, gamma: 41 KiB, dead after the C part).
+// =====================================================================================================
+struct T2Cfg {
+  static constexpr int THREADS = 480;   // 15 warps: copy, 2 x MMA, 4 v_new/output, 8 state
+  static constexpr int NE = 2, NL = 2;
+  static constexpr uint32_t E_W = 0;                          // rows 0..63 of the A1 image: -gamma Wg, 16 KiB
+  static constexpr uint32_t E_V = 16384;                      // value tile, 2 swizzled panels, 16 KiB
+  static constexpr uint32_t V_PANEL = 8192;
+  static constexpr uint32_t E_AU = 32768;                     // Au | -R, 8 KiB each (adjacent in the workspace)
+  static constexpr uint32_t E_R = E_AU + AU_BYTES;
+  static constexpr uint32_t ESLOT = E_R + AU_BYTES;           // 48 KiB
+  static constexpr uint32_t E_TX = ESLOT;
+  static constexpr uint32_t L_Q = 0;                          // rows 64..127 of the A1 image: Qg, 16 KiB
+  static constexpr uint32_t L_P = 16384;                      // P | Kt | gamma with one copy
+  static constexpr uint32_t L_KT = L_P + P_BYTES;
+  static constexpr uint32_t L_TAIL = L_KT + KT_BYTES;
+  static constexpr uint32_t L_TX = 16384 + P_BYTES + KT_BYTES + TAIL_BYTES;
+  static constexpr uint32_t LSLOT = 16384 + P_BYTES + KT_BYTES + 1024;   // 41 KiB
+  static constexpr uint32_t OFF_E = 0;
+  static constexpr uint32_t OFF_L = NE * ESLOT;
+  static constexpr uint32_t OFF_BARS = OFF_L + NL * LSLOT;
+  static constexpr uint32_t SMEM = OFF_BARS + 512 + 1024;
+  static constexpr uint32_t TM_DS = 0;       // 128
+  static constexpr uint32_t TM_SB = 128;     //  64
+  static constexpr uint32_t TM_DV = 192;     // 2 x 64
+  static constexpr uint32_t TM_VB = 320;     // 2 x 32: the R part of chunk c+1 reads v_new_c while chunk c+1's is written
+  static constexpr uint32_t TM_DO = 384;     // 2 x 64
+  static constexpr uint32_t TM_COLS = 512;
+  static_assert(ESLOT % 1024 == 0 && LSLOT % 1024 == 0 && E_V % 1024 == 0, "swizzled tiles need 1 KiB alignment");
+  static_assert(SMEM <= 232448, "exceeds 227 KiB");
+};
+
+struct T2Bars {
+  uint64_t fullE[2], emptyE[2], fullL[2], emptyL[2];
+  uint64_t sb, vb, ds, dsfree, dv[2], dvfree[2], uinit[2], oinit[2], dofull[2], dofree[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(T2Cfg::THREADS, 1)
+gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnVarlen vl, const void* __restrict__ h0,
+                   int h0_dtype, __nv_bfloat16* __restrict__ o, void* __restrict__ ht, int ht_dtype, int T, int H,
+                   int NTROW) {
+  using C = T2Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  T2Bars& bars = *reinterpret_cast<T2Bars*>(smem + C::OFF_BARS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int vh = blockIdx.x, h = blockIdx.y;
+  const bool varlen = vl.chunk_tok0 != nullptr;
+  const int b = varlen ? 0 : blockIdx.z;
+  const int seq = blockIdx.z;
+  const int cb = varlen ? __ldg(vl.seq_chunk_begin + seq) : 0;
+  const int NT = varlen ? __ldg(vl.seq_chunk_begin + seq + 1) - cb : NTROW;
+  const size_t ch0 = ((size_t)b * H + h) * NTROW + cb;
+  const size_t slot0 = ((size_t)b * H + h) * ws.ring;
+  const int ring = ws.ring;
+  const int col0 = vh * 128;
+  if (NT <= 0) {
+    if (ht != nullptr) {
+      const size_t base = ((size_t)seq * H + h) * GDN_K * GDN_V;
+      for (int i = tid; i < GDN_K * 128; i += C::THREADS) {
+        const size_t off = base + (size_t)(i >> 7) * GDN_V + col0 + (i & 127);
+        const float x = h0 == nullptr ? 0.f
+                        : (h0_dtype == 0 ? static_cast<const float*>(h0)[off]
+                                         : __bfloat162float(static_cast<const __nv_bfloat16*>(h0)[off]));
+        if (ht_dtype == 0) static_cast<float*>(ht)[off] = x;
+        else static_cast<__nv_bfloat16*>(ht)[off] = __float2bfloat16(x);
+      }
+    }
+    return;
+  }
+  const uint8_t* blob = ws.blob + slot0 * BLOB_BYTES;
+  const uint8_t* aublob = ws.ublob + slot0 * (GDN_NS * UBLOB_BYTES);
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.fullE[s], 1); mbar_init(&bars.emptyE[s], 2);     // X part (warp 2) + R part (warp 1) retired
+      mbar_init(&bars.fullL[s], 1); mbar_init(&bars.emptyL[s], 2 + 8); // O part + C part retired, 8 state warps read gamma
+      mbar_init(&bars.dv[s], 2);                                       // U + X (warp 2) and R (warp 1) retired
+      mbar_init(&bars.uinit[s], 1); mbar_init(&bars.oinit[s], 1);
+      mbar_init(&bars.dofull[s], 1); mbar_init(&bars.dofree[s], 4); mbar_init(&bars.dvfree[s], 4);
+    }
+    mbar_init(&bars.sb, 8); mbar_init(&bars.vb, 4); mbar_init(&bars.ds, 1); mbar_init(&bars.dsfree, 8);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) tmem_alloc<C::TM_COLS>(&bars.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+  constexpr uint32_t idescU = umma_idesc_bf16(128, 64, /*a_mn=*/1, /*b_mn=*/0);
+  constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0);
+  constexpr uint32_t idescB = umma_idesc_bf16(128, 128, 0, /*b_mn=*/1);
+
+  if (warp == 0) {
+    // ------------------------------- copy warp (TMA engine) ---------------------------
+    const uint32_t* ready = ws.ready + ch0;
+    uint32_t* progress = ws.progress + ((size_t)b * H + h) * GDN_NS + vh;
+    int known = 0;
+    for (int c = 0; c < NT; ++c) {
+      if (c >= known) {
+        long long spins = 0;
+        do {
+          const int idx = known + lane;
+          const uint32_t f = (idx < NT) ? ld_acquire_gpu_t(ready + idx) : 0u;
+          const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
+          known += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+          if (c >= known) {
+            __nanosleep(200);
+            if (++spins > (1ll << 24)) asm volatile("trap;");  // the pre-pass never ran: fail loudly, do not hang
+          }
+        } while (c >= known);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      const int se = c % C::NE, sl = c % C::NL;
+      const size_t cs = (size_t)((cb + c) % ring);
+      const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
+      if (c >= C::NE) mbar_wait(&bars.emptyE[se], (c / C::NE - 1) & 1);
+      uint8_t* es = smem + C::OFF_E + se * C::ESLOT;
+      mbar_arrive_expect_tx_ws(&bars.fullE[se], C::E_TX);
+      bulk_g2s_ws(es + C::E_W, blob + cs * BLOB_BYTES + BLOB_OFF_A1, 16384, &bars.fullE[se]);
+      bulk_g2s_ws(es + C::E_AU, aublob + cs * (GDN_NS * UBLOB_BYTES), 2 * AU_BYTES, &bars.fullE[se]);
+      tma_load_4d_ws(es + C::E_V, &tmV, col0, h, tok0, b, &bars.fullE[se]);
+      tma_load_4d_ws(es + C::E_V + C::V_PANEL, &tmV, col0 + 64, h, tok0, b, &bars.fullE[se]);
+      if (c >= C::NL) {
+        mbar_wait(&bars.emptyL[sl], (c / C::NL - 1) & 1);
+        if (lane == 0 && ring < NTROW)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(c - C::NL + 1)) : "memory");
+      }
+      uint8_t* ls = smem + C::OFF_L + sl * C::LSLOT;
+      mbar_arrive_expect_tx_ws(&bars.fullL[sl], C::L_TX);
+      bulk_g2s_ws(ls + C::L_Q, blob + cs * BLOB_BYTES + BLOB_OFF_A1 + 16384, 16384, &bars.fullL[sl]);
+      bulk_g2s_ws(ls + C::L_P, blob + cs * BLOB_BYTES + BLOB_OFF_P, P_BYTES + KT_BYTES + TAIL_BYTES, &bars.fullL[sl]);
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer that follows v_new ---------------------
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    // chunk 0 has no R part: this warp's share of its barriers is an empty commit
+    umma_commit_ws(&bars.dv[0]);
+    umma_commit_ws(&bars.emptyE[0]);
+    for (int c = 0; c < NT; ++c) {
+      const int sl = c % C::NL, buf = c & 1;
+      const uint32_t ls = sbase + C::OFF_L + sl * C::LSLOT;
+      const uint32_t vbc = tm + C::TM_VB + buf * 32;
+      mbar_wait(&bars.vb, c & 1);                                    // bf16 v_new_c^T is in tensor memory
+      if (c + 1 < NT) {
+        const int k = c + 1, se = k % C::NE;
+        mbar_wait(&bars.uinit[k & 1], (k >> 1) & 1);                 // DV[k] holds U_k (+ possibly X_k): accumulate
+        tc_fence_after();
+        const uint64_t dR = umma_desc(sbase + C::OFF_E + se * C::ESLOT + C::E_R, 128, 1024, SWZ_NONE);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DV + (k & 1) * 64, vbc + j * 8, dR + j * 16, idesc64, 1);
+        umma_commit_ws(&bars.dv[k & 1]);
+        umma_commit_ws(&bars.emptyE[se]);
+      }
+      mbar_wait(&bars.fullL[sl], (c / C::NL) & 1);
+      if (c >= 1) mbar_wait(&bars.dsfree, (c - 1) & 1);              // the state warps have read DS of chunk c - 1
+      tc_fence_after();
+      const uint64_t dKt = umma_desc(ls + C::L_KT, 128, 1024, SWZ_NONE);
+      const uint64_t dP = umma_desc(ls + C::L_P, 128, 1024, SWZ_NONE);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DS, vbc + j * 8, dKt + j * 16, idescB, j > 0);
+      umma_commit_ws(&bars.ds);
+      mbar_wait(&bars.oinit[buf], (c >> 1) & 1);                     // DO[c] holds S_c^T Qg_c^T: accumulate
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DO + buf * 64, vbc + j * 8, dP + j * 16, idesc64, 1);
+      umma_commit_ws(&bars.dofull[buf]);
+      umma_commit_ws(&bars.emptyL[sl]);
+    }
+  } else if (warp == 2) {
+    // ------------------------------- MMA issuer that follows the state -----------------
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    auto issue_u = [&](int k) {   // DV[k] = V_k^T Au_k^T
+      const uint32_t es = sbase + C::OFF_E + (k % C::NE) * C::ESLOT;
+      mbar_wait(&bars.fullE[k % C::NE], (k / C::NE) & 1);
+      if (k >= 2) mbar_wait(&bars.dvfree[k & 1], ((k >> 1) - 1) & 1);   // v_new accumulator of chunk k - 2 has been read
+      tc_fence_after();
+      const uint64_t dV = umma_desc(es + C::E_V, C::V_PANEL, 1024, SWZ_128B);
+      const uint64_t dAu = umma_desc(es + C::E_AU, 128, 1024, SWZ_NONE);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma_bf16_ws(tm + C::TM_DV + (k & 1) * 64, dV + j * 128, dAu + j * 16, idescU, j > 0);
+      umma_commit_ws(&bars.uinit[k & 1]);
+    };
+    auto issue_x = [&](int k) {   // DV[k] += bf16(S^T) (-gamma Wg_k)^T  (S = the state before chunk k - 1; chunk 0: S_0)
+      const uint32_t es = sbase + C::OFF_E + (k % C::NE) * C::ESLOT;
+      const uint64_t dW = umma_desc(es + C::E_W, 128, 2048, SWZ_NONE);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_DV + (k & 1) * 64, tm + C::TM_SB + j * 8, dW + j * 16, idesc64, 1);
+      umma_commit_ws(&bars.dv[k & 1]);
+      umma_commit_ws(&bars.emptyE[k % C::NE]);
+    };
+    auto issue_o = [&](int k) {   // DO[k] = bf16(S_k^T) Qg_k^T
+      const uint32_t ls = sbase + C::OFF_L + (k % C::NL) * C::LSLOT;
+      mbar_wait(&bars.fullL[k % C::NL], (k / C::NL) & 1);
+      if (k >= 2) mbar_wait(&bars.dofree[k & 1], ((k >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint64_t dQ = umma_desc(ls + C::L_Q, 128, 2048, SWZ_NONE);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_DO + (k & 1) * 64, tm + C::TM_SB + j * 8, dQ + j * 16, idesc64, j > 0);
+      umma_commit_ws(&bars.oinit[k & 1]);     // also covers the X part issued just before (the state warps wait for it)
+      umma_commit_ws(&bars.emptyL[k % C::NL]);
+    };
+    // prologue: everything that depends on S_0 only
+    issue_u(0);
+    if (NT > 1) issue_u(1);
+    mbar_wait(&bars.sb, 0);
+    tc_fence_after();
+    issue_x(0);
+    if (NT > 1) issue_x(1);
+    issue_o(0);
+    if (NT > 2) issue_u(2);
+    for (int c = 0; c + 1 < NT; ++c) {
+      mbar_wait(&bars.sb, (c + 1) & 1);        // bf16 S_{c+1}^T is in tensor memory
+      tc_fence_after();
+      if (c + 2 < NT) issue_x(c + 2);
+      issue_o(c + 1);
+      if (c + 3 < NT) issue_u(c + 3);
+    }
+  } else if (warp < 7) {
+    // ------------------------------- v_new / output epilogue (warps 3..6) ----------------
+    const int quad = warp & 3;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const int col = col0 + quad * 32 + lane;
+    uint32_t r[32], r2[32], w[32];
+    auto output = [&](int c) {
+      const int buf = c & 1;
+      mbar_wait(&bars.dofull[buf], (c >> 1) & 1);
+      tc_fence_after();
+      tmem_ld32(tlane + C::TM_DO + buf * 64, r);
+      tmem_ld32(tlane + C::TM_DO + buf * 64 + 32, r2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.dofree[buf]);
+      const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
+      const int valid = varlen ? __ldg(vl.chunk_valid + cb + c) : min(GDN_C, T - tok0);
+      const size_t tstride = (size_t)H * GDN_V;
+      __nv_bfloat16* p0 = o + (((size_t)b * T + tok0) * H + h) * GDN_V + col;
+      __nv_bfloat16* p1 = p0 + 32 * tstride;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < valid) *p0 = __float2bfloat16(__uint_as_float(r[i]));
+        if (i + 32 < valid) *p1 = __float2bfloat16(__uint_as_float(r2[i]));
+        asm volatile("" : "+l"(p0), "+l"(p1));
+        p0 += tstride;
+        p1 += tstride;
+      }
+    };
+    for (int c = 0; c < NT; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&bars.dv[buf], (c >> 1) & 1);
+      tc_fence_after();
+      tmem_ld32(tlane + C::TM_DV + buf * 64, r);
+      tmem_ld32(tlane + C::TM_DV + buf * 64 + 32, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        w[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        w[16 + i] = pack_bf16(__uint_as_float(r2[2 * i]), __uint_as_float(r2[2 * i + 1]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.dvfree[buf]);
+      tmem_st32(tlane + C::TM_VB + buf * 32, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.vb);
+      if (c > 0) output(c - 1);
+    }
+    output(NT - 1);
+  } else {
+    // ------------------------------- state warps (7..14) --------------------------------
+    const int quad = warp & 3, half = (warp - 7) >> 2;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const int col = col0 + quad * 32 + lane;
+    float S[64];
+    const size_t sbase_off = (((size_t)seq * H + h) * GDN_K + half * 64) * GDN_V + col;
+    if (h0 == nullptr) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) S[i] = 0.f;
+    } else if (h0_dtype == 0) {
+      const float* p = static_cast<const float*>(h0) + sbase_off;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) S[i] = __ldg(p + (size_t)i * GDN_V);
+    } else {
+      const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(h0) + sbase_off;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) S[i] = __bfloat162float(p[(size_t)i * GDN_V]);
+    }
+    uint32_t r[32];
+    auto publish = [&]() {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = pack_bf16(S[2 * i], S[2 * i + 1]);
+      tmem_st32(tlane + C::TM_SB + half * 32, r);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.sb);
+    };
+    publish();
+    for (int c = 0; c < NT; ++c) {
+      const int sl = c % C::NL;
+      mbar_wait(&bars.fullL[sl], (c / C::NL) & 1);
+      const float gamma = *reinterpret_cast<const float*>(smem + C::OFF_L + sl * C::LSLOT + C::L_TAIL);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.emptyL[sl]);
+      mbar_wait(&bars.ds, c & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        tmem_ld32(tlane + C::TM_DS + half * 64 + p * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) S[p * 32 + i] = fmaf(gamma, S[p * 32 + i], __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.dsfree);   // DS may be overwritten by the next B part
+      if (c + 1 < NT) {
+        // every product that reads bf16 S_c^T (X part of chunk c+1, O part of chunk c: warp 2 issues them in that
+        // order and commits after the O part) has retired before the operand is overwritten
+        mbar_wait(&bars.oinit[c & 1], (c >> 1) & 1);
+        publish();
+      }
+    }
+    if (ht != nullptr) {
+      if (ht_dtype == 0) {
+        float* p = static_cast<float*>(ht) + sbase_off;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) p[(size_t)i * GDN_V] = S[i];
+      } else {
+        __nv_bfloat16* p = static_cast<__nv_bfloat16*>(ht) + sbase_off;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) p[(size_t)i * GDN_V] = __float2bfloat16(S[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TM_COLS>(tmem);
+}
+
 typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -397,7 +767,7 @@ EncodeTiledFnT encode_fn_t() {
 // v: the caller's value tensor [B, T, H, 256] bf16 (dense).  The scan reads its tiles directly (box = 64 value
 // columns x 64 tokens, 128-byte swizzle); rows past T are zero-filled by the TMA engine.
 cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, int B,
-                              const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H,
+                              const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int lag,
                               cudaStream_t stream) {
   using C = TCfg;
   static std::atomic<bool> configured[64];
@@ -406,6 +776,8 @@ cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVa
   if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   if (!configured[dev].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(gdn_scan_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gdn_scan_t2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg::SMEM);
     if (e != cudaSuccess) return e;
     configured[dev].store(true, std::memory_order_release);
   }
@@ -421,8 +793,13 @@ cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVa
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return cudaErrorInvalidValue;
   dim3 grid(2, H, nseq);
-  gdn_scan_t_kernel<<<grid, C::THREADS, C::SMEM, stream>>>(tm, ws, vl, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,
-                                                           ht_dtype, T, H, ntrow);
+  if (lag)
+    gdn_scan_t2_kernel<<<grid, T2Cfg::THREADS, T2Cfg::SMEM, stream>>>(tm, ws, vl, h0, h0_dtype,
+                                                                      static_cast<__nv_bfloat16*>(o), ht, ht_dtype, T, H,
+                                                                      ntrow);
+  else
+    gdn_scan_t_kernel<<<grid, C::THREADS, C::SMEM, stream>>>(tm, ws, vl, h0, h0_dtype, static_cast<__nv_bfloat16*>(o), ht,
+                                                             ht_dtype, T, H, ntrow);
   return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
                             float scale, int l2norm, int scan_ctas_per_head, int transposed, cudaStream_t stream);
 cudaError_t configure_gdn_prep();
 cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, int B,
-                              const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H,
+                              const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int lag,
                               cudaStream_t stream);
 cudaError_t launch_gdn_scan(const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, const void* h0,
                             int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int bv, cudaStream_t stream);
@@ -76,7 +76,9 @@ inline int env_int(const char* name, int dflt) {
 }
 //   IVL_GDN_TSCAN 1 = transposed scan (gdn_scan_t.cu: two CTAs per head, state and v_new as TMEM A operands;
 //                 default), 0 = row-major scan (gdn_scan.cu: 32/64/128-column slices)
-inline bool tscan() { return env_int("IVL_GDN_TSCAN", 1) != 0; }
+//                 2 = transposed scan, lag form (shortened serial chain; prep also emits R = Wg Kt_prev^T)
+inline int tscan_mode() { const int m = env_int("IVL_GDN_TSCAN", 2); return (m >= 0 && m <= 2) ? m : 2; }
+inline bool tscan() { return tscan_mode() != 0; }
 inline int scan_bv(int dflt) {
   const int bv = env_int("IVL_GDN_BV", dflt);
   return (bv == 32 || bv == 64 || bv == 128) ? bv : dflt;
@@ -223,7 +225,7 @@ int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T, H), st));
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, T, H,
-                                default_scale(scale, ivl::GDN_K), l2norm_qk, 0, tscan() ? 1 : 0, st));
+                                default_scale(scale, ivl::GDN_K), l2norm_qk, 0, tscan_mode(), st));
   return IVL_OK;
 }
 
@@ -238,7 +240,7 @@ int ivl_gdn_chunk_scan(const void* v, const void* h0, int h0_dtype, void* o, voi
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, /*ring=*/0);
   if (tscan())
     IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, B, h0, h0_dtype, o, ht, ht_dtype,
-                                    T, H, static_cast<cudaStream_t>(stream)));
+                                    T, H, tscan_mode() == 2, static_cast<cudaStream_t>(stream)));
   else
     IVL_CUDA(ivl::launch_gdn_scan(ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, h0, h0_dtype, o, ht, ht_dtype, T, H,
                                   scan_bv(32), static_cast<cudaStream_t>(stream)));
@@ -284,16 +286,17 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   // or, failing that, the back-to-back form.
   int sms = 0;
   IVL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const bool tr = tscan();
+  const int trm = tscan_mode();
+  const bool tr = trm != 0;
   int bv_overlap = tr ? 128 : scan_bv(64);   // the transposed scan always owns 128 value columns per CTA
   if ((long long)nseq * H * (ivl::GDN_V / bv_overlap) > sms / 2) bv_overlap = 128;
   const bool fits = (long long)nseq * H * (ivl::GDN_V / bv_overlap) <= sms / 2;
   if (first || !fits || env_int("IVL_GDN_PIPE", overlap_default) == 0) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, tr ? 1 : 0, st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, trm, st));
     if (tr)
-      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, st));
+      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm == 2, st));
     else
       IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
     return IVL_OK;
@@ -309,9 +312,9 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   if (other_busy) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, tr ? 1 : 0, st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, trm, st));
     if (tr)
-      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, st));
+      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm == 2, st));
     else
       IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
     return IVL_OK;
@@ -331,12 +334,12 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   IVL_CUDA(cudaEventRecord(fj->fork, st));
   IVL_CUDA(cudaStreamWaitEvent(fj->aux, fj->fork, 0));
   if (tr)
-    IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, st));
+    IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm == 2, st));
   else
     IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, bv, st));
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv,
-                                tr ? 1 : 0, fj->aux));
+                                trm, fj->aux));
   IVL_CUDA(cudaEventRecord(fj->join, fj->aux));
   IVL_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   if (cap == cudaStreamCaptureStatusNone) {
@@ -363,7 +366,7 @@ int ivl_gdn_chunk_fwd_varlen(const void* q, const void* k, const void* v, const 
   if (int e = check_gdn_shape(1, T, H, K, V)) return e;
   if (num_chunks <= 0 || num_seqs <= 0 || num_seqs > 65535) return IVL_ERR_BAD_SHAPE;
   if (!chunk_tok0 || !chunk_valid || !seq_chunk_begin) return IVL_ERR_NULL;
-  ivl::GdnVarlen vl{chunk_tok0, chunk_valid, seq_chunk_begin};
+  ivl::GdnVarlen vl{chunk_tok0, chunk_valid, seq_chunk_begin, num_seqs};
   return gdn_chunk_fwd_impl(q, k, v, g, beta, h0, h0_dtype, o, ht, ht_dtype, 1, T, H, scale, l2norm_qk, vl, num_chunks,
                             num_seqs, workspace, workspace_bytes, stream);
 }
