@@ -399,8 +399,8 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
 // v_new accumulator is complete) and L slots (Qg rows, P, Kt, gamma: 41 KiB, dead after the C part).
 // =====================================================================================================
 struct T2Cfg {
-  static constexpr int THREADS = 480;   // 15 warps: copy, 2 x MMA, 4 v_new/output, 8 state
-  static constexpr int NE = 2, NL = 2;
+  static constexpr int THREADS = 512;   // 16 warps: E copy, 2 x MMA, 4 v_new/output, 8 state, L copy
+  static constexpr int NE = 3, NL = 2;
   static constexpr uint32_t E_W = 0;                          // rows 0..63 of the A1 image: -gamma Wg, 16 KiB
   static constexpr uint32_t E_V = 16384;                      // value tile, 2 swizzled panels, 16 KiB
   static constexpr uint32_t V_PANEL = 8192;
@@ -413,7 +413,7 @@ struct T2Cfg {
   static constexpr uint32_t L_KT = L_P + P_BYTES;
   static constexpr uint32_t L_TAIL = L_KT + KT_BYTES;
   static constexpr uint32_t L_TX = 16384 + P_BYTES + KT_BYTES + TAIL_BYTES;
-  static constexpr uint32_t LSLOT = 16384 + P_BYTES + KT_BYTES + 1024;   // 41 KiB
+  static constexpr uint32_t LSLOT = 16384 + P_BYTES + KT_BYTES + TAIL_BYTES;   // 40 KiB + 128 B (no swizzled tile inside)
   static constexpr uint32_t OFF_E = 0;
   static constexpr uint32_t OFF_L = NE * ESLOT;
   static constexpr uint32_t OFF_BARS = OFF_L + NL * LSLOT;
@@ -424,13 +424,13 @@ struct T2Cfg {
   static constexpr uint32_t TM_VB = 320;     // 2 x 32: the R part of chunk c+1 reads v_new_c while chunk c+1's is written
   static constexpr uint32_t TM_DO = 384;     // 2 x 64
   static constexpr uint32_t TM_COLS = 512;
-  static_assert(ESLOT % 1024 == 0 && LSLOT % 1024 == 0 && E_V % 1024 == 0, "swizzled tiles need 1 KiB alignment");
+  static_assert(ESLOT % 1024 == 0 && E_V % 1024 == 0 && LSLOT % 128 == 0, "swizzled tiles need 1 KiB alignment");
   static_assert(SMEM <= 232448, "exceeds 227 KiB");
 };
 
 struct T2Bars {
-  uint64_t fullE[2], emptyE[2], fullL[2], emptyL[2];
-  uint64_t sb, vb, ds, dsfree, dv[2], dvfree[2], uinit[2], oinit[2], dofull[2], dofree[2];
+  uint64_t fullE[3], emptyE[3], fullL[2], emptyL[2];
+  uint64_t sb, vb, ds, dsfree, dv[2], dvfree[2], uinit[2], rdone[2], oinit[2], dofull[2], dofree[2];
   uint32_t tmem_base;
 };
 
@@ -471,11 +471,13 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   const uint8_t* aublob = ws.ublob + slot0 * (GDN_NS * UBLOB_BYTES);
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&bars.fullE[s], 1); mbar_init(&bars.emptyE[s], 2);     // X part (warp 2) + R part (warp 1) retired
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bars.fullL[s], 1); mbar_init(&bars.emptyL[s], 2 + 8); // O part + C part retired, 8 state warps read gamma
       mbar_init(&bars.dv[s], 2);                                       // U + X (warp 2) and R (warp 1) retired
-      mbar_init(&bars.uinit[s], 1); mbar_init(&bars.oinit[s], 1);
+      mbar_init(&bars.uinit[s], 1); mbar_init(&bars.oinit[s], 1); mbar_init(&bars.rdone[s], 1);
       mbar_init(&bars.dofull[s], 1); mbar_init(&bars.dofree[s], 4); mbar_init(&bars.dvfree[s], 4);
     }
     mbar_init(&bars.sb, 8); mbar_init(&bars.vb, 4); mbar_init(&bars.ds, 1); mbar_init(&bars.dsfree, 8);
@@ -491,8 +493,11 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0);
   constexpr uint32_t idescB = umma_idesc_bf16(128, 128, 0, /*b_mn=*/1);
 
-  if (warp == 0) {
-    // ------------------------------- copy warp (TMA engine) ---------------------------
+  if (warp == 0 || warp == 15) {
+    // ------------------------------- copy warps (TMA engine) ---------------------------
+    // warp 0 streams the E slots, warp 15 the L slots: the two rings are recycled at different points of a step,
+    // and one warp waiting for a late slot must not hold up the other ring's prefetch distance
+    const bool early = warp == 0;
     const uint32_t* ready = ws.ready + ch0;
     uint32_t* progress = ws.progress + ((size_t)b * H + h) * GDN_NS + vh;
     int known = 0;
@@ -511,25 +516,31 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
         } while (c >= known);
         asm volatile("fence.proxy.async;" ::: "memory");
       }
-      const int se = c % C::NE, sl = c % C::NL;
       const size_t cs = (size_t)((cb + c) % ring);
-      const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
-      if (c >= C::NE) mbar_wait(&bars.emptyE[se], (c / C::NE - 1) & 1);
-      uint8_t* es = smem + C::OFF_E + se * C::ESLOT;
-      mbar_arrive_expect_tx_ws(&bars.fullE[se], C::E_TX);
-      bulk_g2s_ws(es + C::E_W, blob + cs * BLOB_BYTES + BLOB_OFF_A1, 16384, &bars.fullE[se]);
-      bulk_g2s_ws(es + C::E_AU, aublob + cs * (GDN_NS * UBLOB_BYTES), 2 * AU_BYTES, &bars.fullE[se]);
-      tma_load_4d_ws(es + C::E_V, &tmV, col0, h, tok0, b, &bars.fullE[se]);
-      tma_load_4d_ws(es + C::E_V + C::V_PANEL, &tmV, col0 + 64, h, tok0, b, &bars.fullE[se]);
-      if (c >= C::NL) {
-        mbar_wait(&bars.emptyL[sl], (c / C::NL - 1) & 1);
-        if (lane == 0 && ring < NTROW)
-          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(c - C::NL + 1)) : "memory");
+      if (early) {
+        const int se = c % C::NE;
+        const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
+        if (c >= C::NE) mbar_wait(&bars.emptyE[se], (c / C::NE - 1) & 1);
+        uint8_t* es = smem + C::OFF_E + se * C::ESLOT;
+        mbar_arrive_expect_tx_ws(&bars.fullE[se], C::E_TX);
+        bulk_g2s_ws(es + C::E_W, blob + cs * BLOB_BYTES + BLOB_OFF_A1, 16384, &bars.fullE[se]);
+        bulk_g2s_ws(es + C::E_AU, aublob + cs * (GDN_NS * UBLOB_BYTES), 2 * AU_BYTES, &bars.fullE[se]);
+        tma_load_4d_ws(es + C::E_V, &tmV, col0, h, tok0, b, &bars.fullE[se]);
+        tma_load_4d_ws(es + C::E_V + C::V_PANEL, &tmV, col0 + 64, h, tok0, b, &bars.fullE[se]);
+      } else {
+        const int sl = c % C::NL;
+        if (c >= C::NL) {
+          mbar_wait(&bars.emptyL[sl], (c / C::NL - 1) & 1);
+          // every product that read chunk c - NL has retired (its E slot was released earlier in the step): the
+          // image slot of that chunk may be overwritten (ring hand-off with the pre-pass)
+          if (lane == 0 && ring < NTROW)
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(c - C::NL + 1)) : "memory");
+        }
+        uint8_t* ls = smem + C::OFF_L + sl * C::LSLOT;
+        mbar_arrive_expect_tx_ws(&bars.fullL[sl], C::L_TX);
+        bulk_g2s_ws(ls + C::L_Q, blob + cs * BLOB_BYTES + BLOB_OFF_A1 + 16384, 16384, &bars.fullL[sl]);
+        bulk_g2s_ws(ls + C::L_P, blob + cs * BLOB_BYTES + BLOB_OFF_P, P_BYTES + KT_BYTES + TAIL_BYTES, &bars.fullL[sl]);
       }
-      uint8_t* ls = smem + C::OFF_L + sl * C::LSLOT;
-      mbar_arrive_expect_tx_ws(&bars.fullL[sl], C::L_TX);
-      bulk_g2s_ws(ls + C::L_Q, blob + cs * BLOB_BYTES + BLOB_OFF_A1 + 16384, 16384, &bars.fullL[sl]);
-      bulk_g2s_ws(ls + C::L_P, blob + cs * BLOB_BYTES + BLOB_OFF_P, P_BYTES + KT_BYTES + TAIL_BYTES, &bars.fullL[sl]);
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer that follows v_new ---------------------
@@ -543,6 +554,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       const uint32_t ls = sbase + C::OFF_L + sl * C::LSLOT;
       const uint32_t vbc = tm + C::TM_VB + buf * 32;
       mbar_wait(&bars.vb, c & 1);                                    // bf16 v_new_c^T is in tensor memory
+      TTR(0);
       if (c + 1 < NT) {
         const int k = c + 1, se = k % C::NE;
         mbar_wait(&bars.uinit[k & 1], (k >> 1) & 1);                 // DV[k] holds U_k (+ possibly X_k): accumulate
@@ -552,7 +564,9 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
         for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DV + (k & 1) * 64, vbc + j * 8, dR + j * 16, idesc64, 1);
         umma_commit_ws(&bars.dv[k & 1]);
         umma_commit_ws(&bars.emptyE[se]);
+        umma_commit_ws(&bars.rdone[k & 1]);
       }
+      TTR(1);
       mbar_wait(&bars.fullL[sl], (c / C::NL) & 1);
       if (c >= 1) mbar_wait(&bars.dsfree, (c - 1) & 1);              // the state warps have read DS of chunk c - 1
       tc_fence_after();
@@ -567,6 +581,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DO + buf * 64, vbc + j * 8, dP + j * 16, idesc64, 1);
       umma_commit_ws(&bars.dofull[buf]);
       umma_commit_ws(&bars.emptyL[sl]);
+      TTR(2);
     }
   } else if (warp == 2) {
     // ------------------------------- MMA issuer that follows the state -----------------
@@ -585,6 +600,12 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     };
     auto issue_x = [&](int k) {   // DV[k] += bf16(S^T) (-gamma Wg_k)^T  (S = the state before chunk k - 1; chunk 0: S_0)
       const uint32_t es = sbase + C::OFF_E + (k % C::NE) * C::ESLOT;
+      // fixed summation order inside the v_new accumulator (U, then R, then X): the R part is issued by the other
+      // warp as soon as v_new_{k-1} exists, which in steady state is before S_{k-1} is published anyway
+      if (k >= 1) {
+        mbar_wait(&bars.rdone[k & 1], ((k - 1) >> 1) & 1);
+        tc_fence_after();
+      }
       const uint64_t dW = umma_desc(es + C::E_W, 128, 2048, SWZ_NONE);
 #pragma unroll
       for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_DV + (k & 1) * 64, tm + C::TM_SB + j * 8, dW + j * 16, idesc64, 1);
@@ -614,9 +635,12 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     for (int c = 0; c + 1 < NT; ++c) {
       mbar_wait(&bars.sb, (c + 1) & 1);        // bf16 S_{c+1}^T is in tensor memory
       tc_fence_after();
+      TTR(3);
       if (c + 2 < NT) issue_x(c + 2);
       issue_o(c + 1);
+      TTR(4);
       if (c + 3 < NT) issue_u(c + 3);
+      TTR(5);
     }
   } else if (warp < 7) {
     // ------------------------------- v_new / output epilogue (warps 3..6) ----------------
@@ -652,6 +676,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       const int buf = c & 1;
       mbar_wait(&bars.dv[buf], (c >> 1) & 1);
       tc_fence_after();
+      if (quad == 0) TTR(6);
       tmem_ld32(tlane + C::TM_DV + buf * 64, r);
       tmem_ld32(tlane + C::TM_DV + buf * 64 + 32, r2);
       tmem_ld_wait();
@@ -668,6 +693,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.vb);
+      if (quad == 0) TTR(7);
       if (c > 0) output(c - 1);
     }
     output(NT - 1);
@@ -709,6 +735,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       if (lane == 0) mbar_arrive(&bars.emptyL[sl]);
       mbar_wait(&bars.ds, c & 1);
       tc_fence_after();
+      if (warp == 8) TTR(8);
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         tmem_ld32(tlane + C::TM_DS + half * 64 + p * 32, r);
@@ -719,11 +746,14 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.dsfree);   // DS may be overwritten by the next B part
+      if (warp == 8) TTR(9);
       if (c + 1 < NT) {
         // every product that reads bf16 S_c^T (X part of chunk c+1, O part of chunk c: warp 2 issues them in that
         // order and commits after the O part) has retired before the operand is overwritten
         mbar_wait(&bars.oinit[c & 1], (c >> 1) & 1);
+        if (warp == 8) TTR(10);
         publish();
+        if (warp == 8) TTR(11);
       }
     }
     if (ht != nullptr) {

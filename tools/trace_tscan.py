@@ -26,7 +26,8 @@ P = ctypes.c_void_p
 lib.ivl_gdn_chunk_prep.argtypes = [P] * 5 + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, P, ctypes.c_size_t, P]
 lib.ivl_gdn_chunk_scan.argtypes = [P, P, ctypes.c_int, P, P, ctypes.c_int] + [ctypes.c_int] * 3 + [P, ctypes.c_size_t, P]
 st = torch.cuda.current_stream().cuda_stream
-os.environ["IVL_GDN_TSCAN"] = "1"
+MODE = sys.argv[1] if len(sys.argv) > 1 else "2"
+os.environ["IVL_GDN_TSCAN"] = MODE
 for _ in range(3):
     assert lib.ivl_gdn_chunk_prep(q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(), 1, T, 16, 0.0, 1, ws.data_ptr(), need, st) == 0
     assert lib.ivl_gdn_chunk_scan(v.data_ptr(), h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, 16, ws.data_ptr(), need, st) == 0
@@ -35,8 +36,12 @@ buf = (ctypes.c_longlong * (64 * 16))()
 lib.ivl_debug_read_ttrace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 assert lib.ivl_debug_read_ttrace(buf, 64 * 16) == 0
 t = np.array(buf[:]).reshape(64, 16).astype(np.int64)
+names2 = ["M1:vb seen", "M1:R issued", "M1:B+C issued", "M2:sb(c+1) seen", "M2:X(c+2)+O(c+1) issued", "M2:U(c+3) issued", "V:dv seen",
+          "V:vb arrived", "S:ds seen", "S:ld+fma done", "S:oinit seen", "S:sb arrived"]
 names = ["M:sb seen", "M:W+O issued", "M:vb seen", "M:B+C issued", "M:U(c+1) issued", "V:dv seen", "V:ld done", "V:vb arrived",
          "V:output done", "S:ds seen", "S:ld+fma done", "S:sb arrived"]
+if MODE == "2":
+    names = names2
 period = np.diff(t[:, 0])
 print("chunk period (cycles): median", np.median(period), "min", period.min(), "max", period.max())
 rel = t[:, :12] - t[:, 0:1]
