@@ -430,7 +430,7 @@ struct T2Cfg {
 
 struct T2Bars {
   uint64_t fullE[3], emptyE[3], fullL[2], emptyL[2];
-  uint64_t sb, vb, ds, dsfree, dv[2], dvfree[2], uinit[2], rdone[2], oinit[2], dofull[2], dofree[2];
+  uint64_t sb, vb, ds, dsfree, dv[2], dvfree[2], uinit[2], xdone[2], oinit[2], dofull[2], dofree[2];
   uint32_t tmem_base;
 };
 
@@ -477,7 +477,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars.fullL[s], 1); mbar_init(&bars.emptyL[s], 2 + 8); // O part + C part retired, 8 state warps read gamma
       mbar_init(&bars.dv[s], 2);                                       // U + X (warp 2) and R (warp 1) retired
-      mbar_init(&bars.uinit[s], 1); mbar_init(&bars.oinit[s], 1); mbar_init(&bars.rdone[s], 1);
+      mbar_init(&bars.uinit[s], 1); mbar_init(&bars.oinit[s], 1); mbar_init(&bars.xdone[s], 1);
       mbar_init(&bars.dofull[s], 1); mbar_init(&bars.dofree[s], 4); mbar_init(&bars.dvfree[s], 4);
     }
     mbar_init(&bars.sb, 8); mbar_init(&bars.vb, 4); mbar_init(&bars.ds, 1); mbar_init(&bars.dsfree, 8);
@@ -491,7 +491,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   const uint32_t tmem = bars.tmem_base;
   constexpr uint32_t idescU = umma_idesc_bf16(128, 64, /*a_mn=*/1, /*b_mn=*/0);
   constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0);
-  constexpr uint32_t idescB = umma_idesc_bf16(128, 128, 0, /*b_mn=*/1);
+  constexpr uint32_t idescB64 = umma_idesc_bf16(128, 64, 0, /*b_mn=*/1);
 
   if (warp == 0 || warp == 15) {
     // ------------------------------- copy warps (TMA engine) ---------------------------
@@ -557,14 +557,16 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       TTR(0);
       if (c + 1 < NT) {
         const int k = c + 1, se = k % C::NE;
-        mbar_wait(&bars.uinit[k & 1], (k >> 1) & 1);                 // DV[k] holds U_k (+ possibly X_k): accumulate
+        // fixed summation order inside the v_new accumulator: U, X (both issued by warp 2, which commits xdone after
+        // the X part), then R.  X is the longer product and its operand S_{k-1} is published at about the same time
+        // as v_new_{k-1}, so it goes first.
+        mbar_wait(&bars.xdone[k & 1], (k >> 1) & 1);
         tc_fence_after();
         const uint64_t dR = umma_desc(sbase + C::OFF_E + se * C::ESLOT + C::E_R, 128, 1024, SWZ_NONE);
 #pragma unroll
         for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DV + (k & 1) * 64, vbc + j * 8, dR + j * 16, idesc64, 1);
         umma_commit_ws(&bars.dv[k & 1]);
         umma_commit_ws(&bars.emptyE[se]);
-        umma_commit_ws(&bars.rdone[k & 1]);
       }
       TTR(1);
       mbar_wait(&bars.fullL[sl], (c / C::NL) & 1);
@@ -572,8 +574,14 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       tc_fence_after();
       const uint64_t dKt = umma_desc(ls + C::L_KT, 128, 1024, SWZ_NONE);
       const uint64_t dP = umma_desc(ls + C::L_P, 128, 1024, SWZ_NONE);
+      // B part as two independent N = 64 halves (key dims 0..63 / 64..127), interleaved MMA by MMA: consecutive MMAs
+      // into the SAME accumulator are issued ~56 cycles apart by the tensor pipe (measured), independent ones back
+      // to back
 #pragma unroll
-      for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DS, vbc + j * 8, dKt + j * 16, idescB, j > 0);
+      for (int j = 0; j < 4; ++j) {
+        umma_bf16_ts_ws(tm + C::TM_DS, vbc + j * 8, dKt + j * 16, idescB64, j > 0);
+        umma_bf16_ts_ws(tm + C::TM_DS + 64, vbc + j * 8, dKt + 512 + j * 16, idescB64, j > 0);
+      }
       umma_commit_ws(&bars.ds);
       mbar_wait(&bars.oinit[buf], (c >> 1) & 1);                     // DO[c] holds S_c^T Qg_c^T: accumulate
       tc_fence_after();
@@ -598,46 +606,51 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       for (int j = 0; j < 4; ++j) umma_bf16_ws(tm + C::TM_DV + (k & 1) * 64, dV + j * 128, dAu + j * 16, idescU, j > 0);
       umma_commit_ws(&bars.uinit[k & 1]);
     };
-    auto issue_x = [&](int k) {   // DV[k] += bf16(S^T) (-gamma Wg_k)^T  (S = the state before chunk k - 1; chunk 0: S_0)
-      const uint32_t es = sbase + C::OFF_E + (k % C::NE) * C::ESLOT;
-      // fixed summation order inside the v_new accumulator (U, then R, then X): the R part is issued by the other
-      // warp as soon as v_new_{k-1} exists, which in steady state is before S_{k-1} is published anyway
-      if (k >= 1) {
-        mbar_wait(&bars.rdone[k & 1], ((k - 1) >> 1) & 1);
-        tc_fence_after();
+    // X part of chunk kx (DV[kx] += bf16(S^T) (-gamma Wg_kx)^T; S = the state before chunk kx - 1, chunk 0: S_0) and
+    // O part of chunk ko (DO[ko] = bf16(S_ko^T) Qg_ko^T), interleaved MMA by MMA (two independent accumulators: the
+    // tensor pipe issues dependent MMAs ~56 cycles apart, independent ones back to back).  kx or ko < 0: skip.
+    auto issue_xo = [&](int kx, int ko) {
+      uint64_t dW = 0, dQ = 0;
+      uint32_t dvx = 0, dox = 0;
+      if (kx >= 0) {
+        dW = umma_desc(sbase + C::OFF_E + (kx % C::NE) * C::ESLOT + C::E_W, 128, 2048, SWZ_NONE);
+        dvx = tm + C::TM_DV + (kx & 1) * 64;
       }
-      const uint64_t dW = umma_desc(es + C::E_W, 128, 2048, SWZ_NONE);
+      if (ko >= 0) {
+        mbar_wait(&bars.fullL[ko % C::NL], (ko / C::NL) & 1);
+        if (ko >= 2) mbar_wait(&bars.dofree[ko & 1], ((ko >> 1) - 1) & 1);
+        tc_fence_after();
+        dQ = umma_desc(sbase + C::OFF_L + (ko % C::NL) * C::LSLOT + C::L_Q, 128, 2048, SWZ_NONE);
+        dox = tm + C::TM_DO + (ko & 1) * 64;
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_DV + (k & 1) * 64, tm + C::TM_SB + j * 8, dW + j * 16, idesc64, 1);
-      umma_commit_ws(&bars.dv[k & 1]);
-      umma_commit_ws(&bars.emptyE[k % C::NE]);
-    };
-    auto issue_o = [&](int k) {   // DO[k] = bf16(S_k^T) Qg_k^T
-      const uint32_t ls = sbase + C::OFF_L + (k % C::NL) * C::LSLOT;
-      mbar_wait(&bars.fullL[k % C::NL], (k / C::NL) & 1);
-      if (k >= 2) mbar_wait(&bars.dofree[k & 1], ((k >> 1) - 1) & 1);
-      tc_fence_after();
-      const uint64_t dQ = umma_desc(ls + C::L_Q, 128, 2048, SWZ_NONE);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_DO + (k & 1) * 64, tm + C::TM_SB + j * 8, dQ + j * 16, idesc64, j > 0);
-      umma_commit_ws(&bars.oinit[k & 1]);     // also covers the X part issued just before (the state warps wait for it)
-      umma_commit_ws(&bars.emptyL[k % C::NL]);
+      for (int j = 0; j < 8; ++j) {
+        if (kx >= 0) umma_bf16_ts_ws(dvx, tm + C::TM_SB + j * 8, dW + j * 16, idesc64, 1);
+        if (ko >= 0) umma_bf16_ts_ws(dox, tm + C::TM_SB + j * 8, dQ + j * 16, idesc64, j > 0);
+      }
+      if (kx >= 0) {
+        umma_commit_ws(&bars.xdone[kx & 1]);
+        umma_commit_ws(&bars.dv[kx & 1]);
+        umma_commit_ws(&bars.emptyE[kx % C::NE]);
+      }
+      if (ko >= 0) {
+        umma_commit_ws(&bars.oinit[ko & 1]);   // also covers the X part (the state warps wait for both before S moves on)
+        umma_commit_ws(&bars.emptyL[ko % C::NL]);
+      }
     };
     // prologue: everything that depends on S_0 only
     issue_u(0);
     if (NT > 1) issue_u(1);
     mbar_wait(&bars.sb, 0);
     tc_fence_after();
-    issue_x(0);
-    if (NT > 1) issue_x(1);
-    issue_o(0);
+    issue_xo(0, -1);
+    issue_xo(NT > 1 ? 1 : -1, 0);
     if (NT > 2) issue_u(2);
     for (int c = 0; c + 1 < NT; ++c) {
       mbar_wait(&bars.sb, (c + 1) & 1);        // bf16 S_{c+1}^T is in tensor memory
       tc_fence_after();
       TTR(3);
-      if (c + 2 < NT) issue_x(c + 2);
-      issue_o(c + 1);
+      issue_xo(c + 2 < NT ? c + 2 : -1, c + 1);
       TTR(4);
       if (c + 3 < NT) issue_u(c + 3);
       TTR(5);
