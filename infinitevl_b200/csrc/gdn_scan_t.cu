@@ -374,63 +374,62 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
 }
 
 
+
 // =====================================================================================================
 // Lag form of the transposed scan (operands from gdn_prep_kernel<2>): the serial chain is shortened from
 //   W part -> epi V -> B part -> epi S          (state -> v_new -> state, two tensor / epilogue round trips per chunk)
 // to
-//   R part -> epi V                             (v_new_c -> v_new_{c+1}: one 64 x 64 product per chunk)
+//   RC part -> epi V                            (v_new_c -> v_new_{c+1}: one product with K = 64 per chunk)
 // by expanding the state inside v_new_{c+1} = U_{c+1} - Wg_{c+1} S_{c+1} with S_{c+1} = gamma_c S_c + Kt_c^T v_new_c:
 //   v_new_{c+1}^T = U_{c+1}^T - bf16(S_c^T) (gamma_c Wg_{c+1})^T - bf16(v_new_c^T) (Wg_{c+1} Kt_c^T)^T .
-// The state update (B part, epi S) and the outputs leave the chain; they only have to keep up on average, and the
-// state-dependent term of chunk c+2 is issued as soon as S_{c+1} is published.  Two MMA-issuing warps, one per
-// trigger, so that neither kind of product queues behind a wait for the other event:
-//   warp 1 (follows v_new):  R part(c+1) | B part(c) | C part(c)          after v_new_c is in tensor memory
-//   warp 2 (follows S):      X part(c+2) | O part(c+1) | U part(c+3)      after S_{c+1} is in tensor memory
-//     U part   DV[k]  = V_k^T Au_k^T                      SS  N64 K64
-//     X part   DV[k] += bf16(S_{k-1}^T) (-gamma Wg_k)^T   TS  N64 K128     (chunk 0: S_0 and the unscaled Wg_0)
-//     R part   DV[k] += bf16(v_new_{k-1}^T) (-R_k)^T      TS  N64 K64
-//     O part   DO[k]  = bf16(S_k^T) Qg_k^T                TS  N64 K128
-//     B part   DS     = bf16(v_new_k^T) Kt_k              TS  N128 K64
-//     C part   DO[k] += bf16(v_new_k^T) P_k^T             TS  N64 K64
-// tcgen05.commit only tracks the issuing thread's MMAs, so barriers that guard products of both warps take one
-// commit from each; an accumulator that one warp initialises and the other accumulates into is handed over
-// through a commit barrier (uinit, oinit).
-// Shared memory: E slots (early operands of a chunk: -gamma Wg rows, value tile, Au, -R: 48 KiB, dead once its
-// v_new accumulator is complete) and L slots (Qg rows, P, Kt, gamma: 41 KiB, dead after the C part).
+// The state update (B part, epi S) and the outputs leave the chain; they only have to keep up on average.
+//
+// A tcgen05.mma with a TMEM A operand costs ~64 cycles whatever its N <= 128 (measured on the first version of this
+// kernel: N = 64 products ran at 56-64 cycles per MMA, i.e. at half the tensor rate), so products that share an A
+// operand are merged into ONE N = 128 MMA chain over operands stacked in shared memory and accumulators adjacent
+// in tensor memory.  STEP k (k = 0 .. NT-1) owns the accumulator pair PAIR[k & 1] = [ DV: v_new_{k+1}^T | DO: O_k^T ]:
+//   U part    PAIR.DV  = V_{k+1}^T Au_{k+1}^T                              SS  N64  K64   (issued two steps ahead)
+//   XO part   PAIR    += bf16(S_k^T) [ -gamma_k Wg_{k+1} ; Qg_k ]^T        TS  N128 K128  after S_k is published
+//   B part    DS       = bf16(v_new_k^T) Kt_k                              TS  N128 K64   after v_new_k is published
+//   RC part   PAIR    += bf16(v_new_k^T) [ -R_{k+1} ; P_k ]^T              TS  N128 K64   after v_new_k and the XO part
+//   epi V     PAIR.DV -> bf16 -> TMEM (v_new_{k+1});  PAIR.DO -> bf16 -> global (O_k), then PAIR.DO is zeroed
+//   epi S     S^T = gamma_k S^T + DS (fp32, registers) -> bf16 -> TMEM (S_{k+1})
+// (chunk 0's v_new = U_0 - Wg_0 S_0 is an extra N = 64 product in the prologue; the last step has no chunk k+1 and
+// uses N = 64 products over the Qg / P halves.)  Two MMA-issuing warps, one per trigger: warp 2 follows the state
+// (XO, U), warp 1 follows v_new (B, RC).  tcgen05.commit only tracks the issuing thread's MMAs; the summation order
+// inside an accumulator is fixed (U, XO, RC) by making warp 1 wait for the XO part's commit, so results do not
+// depend on timing.
+// Shared memory: U slots (value tile + Au of a chunk, 24 KiB, three deep) and step slots ([-gamma Wg_{k+1}; Qg_k] |
+// [-R_{k+1}; P_k] | Kt_k | gamma_k, 64 KiB + 128 B, two deep), each ring with its own copy warp.
 // =====================================================================================================
 struct T2Cfg {
-  static constexpr int THREADS = 512;   // 16 warps: E copy, 2 x MMA, 4 v_new/output, 8 state, L copy
-  static constexpr int NE = 3, NL = 2;
-  static constexpr uint32_t E_W = 0;                          // rows 0..63 of the A1 image: -gamma Wg, 16 KiB
-  static constexpr uint32_t E_V = 16384;                      // value tile, 2 swizzled panels, 16 KiB
+  static constexpr int THREADS = 512;   // 16 warps: U copy, 2 x MMA, 4 v_new/output, 8 state, step copy
+  static constexpr int NU = 3, NS = 2;
+  static constexpr uint32_t U_V = 0;                          // value tile, 2 swizzled panels, 16 KiB
   static constexpr uint32_t V_PANEL = 8192;
-  static constexpr uint32_t E_AU = 32768;                     // Au | -R, 8 KiB each (adjacent in the workspace)
-  static constexpr uint32_t E_R = E_AU + AU_BYTES;
-  static constexpr uint32_t ESLOT = E_R + AU_BYTES;           // 48 KiB
-  static constexpr uint32_t E_TX = ESLOT;
-  static constexpr uint32_t L_Q = 0;                          // rows 64..127 of the A1 image: Qg, 16 KiB
-  static constexpr uint32_t L_P = 16384;                      // P | Kt | gamma with one copy
-  static constexpr uint32_t L_KT = L_P + P_BYTES;
-  static constexpr uint32_t L_TAIL = L_KT + KT_BYTES;
-  static constexpr uint32_t L_TX = 16384 + P_BYTES + KT_BYTES + TAIL_BYTES;
-  static constexpr uint32_t LSLOT = 16384 + P_BYTES + KT_BYTES + TAIL_BYTES;   // 40 KiB + 128 B (no swizzled tile inside)
-  static constexpr uint32_t OFF_E = 0;
-  static constexpr uint32_t OFF_L = NE * ESLOT;
-  static constexpr uint32_t OFF_BARS = OFF_L + NL * LSLOT;
+  static constexpr uint32_t U_AU = 16384;                     // Au, 8 KiB
+  static constexpr uint32_t USLOT = 24576;
+  static constexpr uint32_t S_XO = 0;                         // rows 0..63: -gamma Wg_{k+1}; rows 64..127: Qg_k (32 KiB)
+  static constexpr uint32_t S_RC = 32768;                     // rows 0..63: -R_{k+1}; rows 64..127: P_k (16 KiB)
+  static constexpr uint32_t S_KT = 49152;                     // Kt_k (16 KiB) | gamma_k (128 B)
+  static constexpr uint32_t S_TAIL = S_KT + KT_BYTES;
+  static constexpr uint32_t SSLOT = S_TAIL + TAIL_BYTES;      // 64 KiB + 128 B (no swizzled tile inside)
+  static constexpr uint32_t OFF_U = 0;
+  static constexpr uint32_t OFF_S = NU * USLOT;
+  static constexpr uint32_t OFF_BARS = OFF_S + NS * SSLOT;
   static constexpr uint32_t SMEM = OFF_BARS + 512 + 1024;
   static constexpr uint32_t TM_DS = 0;       // 128
   static constexpr uint32_t TM_SB = 128;     //  64
-  static constexpr uint32_t TM_DV = 192;     // 2 x 64
-  static constexpr uint32_t TM_VB = 320;     // 2 x 32: the R part of chunk c+1 reads v_new_c while chunk c+1's is written
-  static constexpr uint32_t TM_DO = 384;     // 2 x 64
+  static constexpr uint32_t TM_PAIR = 192;   // 2 x (64 DV + 64 DO)
+  static constexpr uint32_t TM_VB = 448;     // 2 x 32
   static constexpr uint32_t TM_COLS = 512;
-  static_assert(ESLOT % 1024 == 0 && E_V % 1024 == 0 && LSLOT % 128 == 0, "swizzled tiles need 1 KiB alignment");
+  static_assert(USLOT % 1024 == 0 && OFF_S % 1024 == 0 && SSLOT % 128 == 0, "alignment");
   static_assert(SMEM <= 232448, "exceeds 227 KiB");
 };
 
 struct T2Bars {
-  uint64_t fullE[3], emptyE[3], fullL[2], emptyL[2];
-  uint64_t sb, vb, ds, dsfree, dv[2], dvfree[2], uinit[2], xdone[2], oinit[2], dofull[2], dofree[2];
+  uint64_t fullU[3], emptyU[3], fullS[2], emptyS[2];
+  uint64_t sb, vb, ds, dsfree, w0full, w0done, dv0, xo[2], rc[2], dvfree[2], dofree[2];
   uint32_t tmem_base;
 };
 
@@ -471,16 +470,15 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   const uint8_t* aublob = ws.ublob + slot0 * (GDN_NS * UBLOB_BYTES);
 
   if (tid == 0) {
-    for (int s = 0; s < 3; ++s) {
-      mbar_init(&bars.fullE[s], 1); mbar_init(&bars.emptyE[s], 2);     // X part (warp 2) + R part (warp 1) retired
-    }
+    for (int s = 0; s < 3; ++s) { mbar_init(&bars.fullU[s], 1); mbar_init(&bars.emptyU[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars.fullL[s], 1); mbar_init(&bars.emptyL[s], 2 + 8); // O part + C part retired, 8 state warps read gamma
-      mbar_init(&bars.dv[s], 2);                                       // U + X (warp 2) and R (warp 1) retired
-      mbar_init(&bars.uinit[s], 1); mbar_init(&bars.oinit[s], 1); mbar_init(&bars.xdone[s], 1);
-      mbar_init(&bars.dofull[s], 1); mbar_init(&bars.dofree[s], 4); mbar_init(&bars.dvfree[s], 4);
+      mbar_init(&bars.fullS[s], 1);
+      mbar_init(&bars.emptyS[s], 2 + 8);   // XO part (warp 2), B + RC parts (warp 1) retired, 8 state warps read gamma
+      mbar_init(&bars.xo[s], 1); mbar_init(&bars.rc[s], 1);
+      mbar_init(&bars.dvfree[s], 4); mbar_init(&bars.dofree[s], 4);
     }
     mbar_init(&bars.sb, 8); mbar_init(&bars.vb, 4); mbar_init(&bars.ds, 1); mbar_init(&bars.dsfree, 8);
+    mbar_init(&bars.w0full, 1); mbar_init(&bars.w0done, 1); mbar_init(&bars.dv0, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmV);
   }
@@ -489,170 +487,190 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
+  if (warp >= 3 && warp < 7) {
+    // the O halves of both accumulator pairs start at zero (every product accumulates)
+    uint32_t z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0u;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      tmem_st32(tl + C::TM_PAIR + p * 128 + 64, z);
+      tmem_st32(tl + C::TM_PAIR + p * 128 + 96, z);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   constexpr uint32_t idescU = umma_idesc_bf16(128, 64, /*a_mn=*/1, /*b_mn=*/0);
   constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0);
-  constexpr uint32_t idescB64 = umma_idesc_bf16(128, 64, 0, /*b_mn=*/1);
+  constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idescB = umma_idesc_bf16(128, 128, 0, /*b_mn=*/1);
 
   if (warp == 0 || warp == 15) {
     // ------------------------------- copy warps (TMA engine) ---------------------------
-    // warp 0 streams the E slots, warp 15 the L slots: the two rings are recycled at different points of a step,
-    // and one warp waiting for a late slot must not hold up the other ring's prefetch distance
-    const bool early = warp == 0;
+    // warp 0 streams the U slots (chunk c needs chunk c published), warp 15 the step slots (step k needs chunk
+    // k + 1 published): two rings recycled at different points of a step, each with its own prefetch distance
+    const bool uwarp = warp == 0;
     const uint32_t* ready = ws.ready + ch0;
     uint32_t* progress = ws.progress + ((size_t)b * H + h) * GDN_NS + vh;
     int known = 0;
-    for (int c = 0; c < NT; ++c) {
-      if (c >= known) {
-        long long spins = 0;
-        do {
-          const int idx = known + lane;
-          const uint32_t f = (idx < NT) ? ld_acquire_gpu_t(ready + idx) : 0u;
-          const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
-          known += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
-          if (c >= known) {
-            __nanosleep(200);
-            if (++spins > (1ll << 24)) asm volatile("trap;");  // the pre-pass never ran: fail loudly, do not hang
-          }
-        } while (c >= known);
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
-      const size_t cs = (size_t)((cb + c) % ring);
-      if (early) {
-        const int se = c % C::NE;
-        const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
-        if (c >= C::NE) mbar_wait(&bars.emptyE[se], (c / C::NE - 1) & 1);
-        uint8_t* es = smem + C::OFF_E + se * C::ESLOT;
-        mbar_arrive_expect_tx_ws(&bars.fullE[se], C::E_TX);
-        bulk_g2s_ws(es + C::E_W, blob + cs * BLOB_BYTES + BLOB_OFF_A1, 16384, &bars.fullE[se]);
-        bulk_g2s_ws(es + C::E_AU, aublob + cs * (GDN_NS * UBLOB_BYTES), 2 * AU_BYTES, &bars.fullE[se]);
-        tma_load_4d_ws(es + C::E_V, &tmV, col0, h, tok0, b, &bars.fullE[se]);
-        tma_load_4d_ws(es + C::E_V + C::V_PANEL, &tmV, col0 + 64, h, tok0, b, &bars.fullE[se]);
-      } else {
-        const int sl = c % C::NL;
-        if (c >= C::NL) {
-          mbar_wait(&bars.emptyL[sl], (c / C::NL - 1) & 1);
-          // every product that read chunk c - NL has retired (its E slot was released earlier in the step): the
-          // image slot of that chunk may be overwritten (ring hand-off with the pre-pass)
-          if (lane == 0 && ring < NTROW)
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(c - C::NL + 1)) : "memory");
+    auto need = [&](int c) {   // block until chunks [0, c] are published by the pre-pass
+      if (c < known) return;
+      long long spins = 0;
+      do {
+        const int idx = known + lane;
+        const uint32_t f = (idx < NT) ? ld_acquire_gpu_t(ready + idx) : 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
+        known += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+        if (c >= known) {
+          __nanosleep(200);
+          if (++spins > (1ll << 24)) asm volatile("trap;");  // the pre-pass never ran: fail loudly, do not hang
         }
-        uint8_t* ls = smem + C::OFF_L + sl * C::LSLOT;
-        mbar_arrive_expect_tx_ws(&bars.fullL[sl], C::L_TX);
-        bulk_g2s_ws(ls + C::L_Q, blob + cs * BLOB_BYTES + BLOB_OFF_A1 + 16384, 16384, &bars.fullL[sl]);
-        bulk_g2s_ws(ls + C::L_P, blob + cs * BLOB_BYTES + BLOB_OFF_P, P_BYTES + KT_BYTES + TAIL_BYTES, &bars.fullL[sl]);
+      } while (c >= known);
+      asm volatile("fence.proxy.async;" ::: "memory");
+    };
+    if (uwarp) {
+      for (int c = 0; c < NT; ++c) {
+        need(c);
+        const int su = c % C::NU;
+        const size_t cs = (size_t)((cb + c) % ring);
+        const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
+        if (c >= C::NU) mbar_wait(&bars.emptyU[su], (c / C::NU - 1) & 1);
+        uint8_t* us = smem + C::OFF_U + su * C::USLOT;
+        mbar_arrive_expect_tx_ws(&bars.fullU[su], C::USLOT);
+        bulk_g2s_ws(us + C::U_AU, aublob + cs * (GDN_NS * UBLOB_BYTES), AU_BYTES, &bars.fullU[su]);
+        tma_load_4d_ws(us + C::U_V, &tmV, col0, h, tok0, b, &bars.fullU[su]);
+        tma_load_4d_ws(us + C::U_V + C::V_PANEL, &tmV, col0 + 64, h, tok0, b, &bars.fullU[su]);
+      }
+    } else {
+      // chunk 0's own Wg rows (for v_new_0 = U_0 - Wg_0 S_0) borrow the XO area of step slot 1 until that product
+      // has retired
+      need(0);
+      mbar_arrive_expect_tx_ws(&bars.w0full, 16384);
+      bulk_g2s_ws(smem + C::OFF_S + C::SSLOT + C::S_XO, blob + (size_t)(cb % ring) * BLOB_BYTES + BLOB_OFF_A1, 16384,
+                  &bars.w0full);
+      for (int k = 0; k < NT; ++k) {
+        const bool last = k + 1 == NT;
+        need(last ? k : k + 1);
+        const int ss = k % C::NS;
+        const size_t cs = (size_t)((cb + k) % ring), cn = (size_t)((cb + k + 1) % ring);
+        if (k == 1) mbar_wait(&bars.w0done, 0);
+        if (k >= C::NS) {
+          mbar_wait(&bars.emptyS[ss], (k / C::NS - 1) & 1);
+          // every product that read step k - NS has retired, so every copy out of chunk k - NS's images completed
+          // long ago: that image slot may be overwritten (ring hand-off with the pre-pass)
+          if (lane == 0 && ring < NTROW)
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(k - C::NS + 1)) : "memory");
+        }
+        uint8_t* sl = smem + C::OFF_S + ss * C::SSLOT;
+        mbar_arrive_expect_tx_ws(&bars.fullS[ss], (last ? 0u : 16384u + AU_BYTES) + 16384u + P_BYTES + KT_BYTES + TAIL_BYTES);
+        if (!last) {
+          bulk_g2s_ws(sl + C::S_XO, blob + cn * BLOB_BYTES + BLOB_OFF_A1, 16384, &bars.fullS[ss]);
+          bulk_g2s_ws(sl + C::S_RC, aublob + cn * (GDN_NS * UBLOB_BYTES) + AU_BYTES, AU_BYTES, &bars.fullS[ss]);
+        }
+        bulk_g2s_ws(sl + C::S_XO + 16384, blob + cs * BLOB_BYTES + BLOB_OFF_A1 + 16384, 16384, &bars.fullS[ss]);
+        bulk_g2s_ws(sl + C::S_RC + AU_BYTES, blob + cs * BLOB_BYTES + BLOB_OFF_P, P_BYTES, &bars.fullS[ss]);
+        bulk_g2s_ws(sl + C::S_KT, blob + cs * BLOB_BYTES + BLOB_OFF_KT, KT_BYTES + TAIL_BYTES, &bars.fullS[ss]);
       }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer that follows v_new ---------------------
     const uint32_t sbase = smem_u32(smem);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    // chunk 0 has no R part: this warp's share of its barriers is an empty commit
-    umma_commit_ws(&bars.dv[0]);
-    umma_commit_ws(&bars.emptyE[0]);
-    for (int c = 0; c < NT; ++c) {
-      const int sl = c % C::NL, buf = c & 1;
-      const uint32_t ls = sbase + C::OFF_L + sl * C::LSLOT;
-      const uint32_t vbc = tm + C::TM_VB + buf * 32;
-      mbar_wait(&bars.vb, c & 1);                                    // bf16 v_new_c^T is in tensor memory
+    for (int k = 0; k < NT; ++k) {
+      const int ss = k % C::NS, p = k & 1;
+      const bool last = k + 1 == NT;
+      const uint32_t sl = sbase + C::OFF_S + ss * C::SSLOT;
+      const uint32_t vbk = tm + C::TM_VB + p * 32;
+      const uint32_t pair = tm + C::TM_PAIR + p * 128;
+      mbar_wait(&bars.vb, k & 1);                                    // bf16 v_new_k^T is in tensor memory
+      mbar_wait(&bars.fullS[ss], (k / C::NS) & 1);
       TTR(0);
-      if (c + 1 < NT) {
-        const int k = c + 1, se = k % C::NE;
-        // fixed summation order inside the v_new accumulator: U, X (both issued by warp 2, which commits xdone after
-        // the X part), then R.  X is the longer product and its operand S_{k-1} is published at about the same time
-        // as v_new_{k-1}, so it goes first.
-        mbar_wait(&bars.xdone[k & 1], (k >> 1) & 1);
+      const uint64_t dKt = umma_desc(sl + C::S_KT, 128, 1024, SWZ_NONE);
+      const uint64_t dRC = umma_desc(sl + C::S_RC, 128, 1024, SWZ_NONE);
+      auto issue_b = [&]() {
+        if (k >= 1) mbar_wait(&bars.dsfree, (k - 1) & 1);            // the state warps have read DS of step k - 1
         tc_fence_after();
-        const uint64_t dR = umma_desc(sbase + C::OFF_E + se * C::ESLOT + C::E_R, 128, 1024, SWZ_NONE);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DV + (k & 1) * 64, vbc + j * 8, dR + j * 16, idesc64, 1);
-        umma_commit_ws(&bars.dv[k & 1]);
-        umma_commit_ws(&bars.emptyE[se]);
+        for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DS, vbk + j * 8, dKt + j * 16, idescB, j > 0);
+        umma_commit_ws(&bars.ds);
+      };
+      auto issue_rc = [&]() {
+        tc_fence_after();
+        if (!last) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(pair, vbk + j * 8, dRC + j * 16, idesc128, 1);
+        } else {   // no chunk k + 1: only the P half, into the O half of the pair
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(pair + 64, vbk + j * 8, dRC + (AU_BYTES >> 4) + j * 16, idesc64, 1);
+        }
+        umma_commit_ws(&bars.rc[p]);
+      };
+      // the RC part is the serial chain, the B part feeds the state: whichever is not blocked goes first (the two
+      // write different accumulators, so the order does not change a bit of the result)
+      if (__any_sync(0xffffffffu, mbar_try_wait(&bars.xo[p], (k >> 1) & 1))) {
+        issue_rc();
+        issue_b();
+      } else {
+        issue_b();
+        mbar_wait(&bars.xo[p], (k >> 1) & 1);
+        issue_rc();
       }
+      umma_commit_ws(&bars.emptyS[ss]);
       TTR(1);
-      mbar_wait(&bars.fullL[sl], (c / C::NL) & 1);
-      if (c >= 1) mbar_wait(&bars.dsfree, (c - 1) & 1);              // the state warps have read DS of chunk c - 1
-      tc_fence_after();
-      const uint64_t dKt = umma_desc(ls + C::L_KT, 128, 1024, SWZ_NONE);
-      const uint64_t dP = umma_desc(ls + C::L_P, 128, 1024, SWZ_NONE);
-      // B part as two independent N = 64 halves (key dims 0..63 / 64..127), interleaved MMA by MMA: consecutive MMAs
-      // into the SAME accumulator are issued ~56 cycles apart by the tensor pipe (measured), independent ones back
-      // to back
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        umma_bf16_ts_ws(tm + C::TM_DS, vbc + j * 8, dKt + j * 16, idescB64, j > 0);
-        umma_bf16_ts_ws(tm + C::TM_DS + 64, vbc + j * 8, dKt + 512 + j * 16, idescB64, j > 0);
-      }
-      umma_commit_ws(&bars.ds);
-      mbar_wait(&bars.oinit[buf], (c >> 1) & 1);                     // DO[c] holds S_c^T Qg_c^T: accumulate
-      tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DO + buf * 64, vbc + j * 8, dP + j * 16, idesc64, 1);
-      umma_commit_ws(&bars.dofull[buf]);
-      umma_commit_ws(&bars.emptyL[sl]);
-      TTR(2);
     }
   } else if (warp == 2) {
     // ------------------------------- MMA issuer that follows the state -----------------
     const uint32_t sbase = smem_u32(smem);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-    auto issue_u = [&](int k) {   // DV[k] = V_k^T Au_k^T
-      const uint32_t es = sbase + C::OFF_E + (k % C::NE) * C::ESLOT;
-      mbar_wait(&bars.fullE[k % C::NE], (k / C::NE) & 1);
-      if (k >= 2) mbar_wait(&bars.dvfree[k & 1], ((k >> 1) - 1) & 1);   // v_new accumulator of chunk k - 2 has been read
+    auto issue_u = [&](int c) {   // DV half of PAIR[(c + 1) & 1] = V_c^T Au_c^T
+      const int su = c % C::NU;
+      const uint32_t us = sbase + C::OFF_U + su * C::USLOT;
+      mbar_wait(&bars.fullU[su], (c / C::NU) & 1);
+      if (c >= 2) mbar_wait(&bars.dvfree[(c + 1) & 1], ((c - 2) >> 1) & 1);   // v_new accumulator of chunk c - 2 has been read
       tc_fence_after();
-      const uint64_t dV = umma_desc(es + C::E_V, C::V_PANEL, 1024, SWZ_128B);
-      const uint64_t dAu = umma_desc(es + C::E_AU, 128, 1024, SWZ_NONE);
+      const uint64_t dV = umma_desc(us + C::U_V, C::V_PANEL, 1024, SWZ_128B);
+      const uint64_t dAu = umma_desc(us + C::U_AU, 128, 1024, SWZ_NONE);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) umma_bf16_ws(tm + C::TM_DV + (k & 1) * 64, dV + j * 128, dAu + j * 16, idescU, j > 0);
-      umma_commit_ws(&bars.uinit[k & 1]);
+      for (int j = 0; j < 4; ++j)
+        umma_bf16_ws(tm + C::TM_PAIR + ((c + 1) & 1) * 128, dV + j * 128, dAu + j * 16, idescU, j > 0);
+      umma_commit_ws(&bars.emptyU[su]);
     };
-    // X part of chunk kx (DV[kx] += bf16(S^T) (-gamma Wg_kx)^T; S = the state before chunk kx - 1, chunk 0: S_0) and
-    // O part of chunk ko (DO[ko] = bf16(S_ko^T) Qg_ko^T), interleaved MMA by MMA (two independent accumulators: the
-    // tensor pipe issues dependent MMAs ~56 cycles apart, independent ones back to back).  kx or ko < 0: skip.
-    auto issue_xo = [&](int kx, int ko) {
-      uint64_t dW = 0, dQ = 0;
-      uint32_t dvx = 0, dox = 0;
-      if (kx >= 0) {
-        dW = umma_desc(sbase + C::OFF_E + (kx % C::NE) * C::ESLOT + C::E_W, 128, 2048, SWZ_NONE);
-        dvx = tm + C::TM_DV + (kx & 1) * 64;
-      }
-      if (ko >= 0) {
-        mbar_wait(&bars.fullL[ko % C::NL], (ko / C::NL) & 1);
-        if (ko >= 2) mbar_wait(&bars.dofree[ko & 1], ((ko >> 1) - 1) & 1);
-        tc_fence_after();
-        dQ = umma_desc(sbase + C::OFF_L + (ko % C::NL) * C::LSLOT + C::L_Q, 128, 2048, SWZ_NONE);
-        dox = tm + C::TM_DO + (ko & 1) * 64;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (kx >= 0) umma_bf16_ts_ws(dvx, tm + C::TM_SB + j * 8, dW + j * 16, idesc64, 1);
-        if (ko >= 0) umma_bf16_ts_ws(dox, tm + C::TM_SB + j * 8, dQ + j * 16, idesc64, j > 0);
-      }
-      if (kx >= 0) {
-        umma_commit_ws(&bars.xdone[kx & 1]);
-        umma_commit_ws(&bars.dv[kx & 1]);
-        umma_commit_ws(&bars.emptyE[kx % C::NE]);
-      }
-      if (ko >= 0) {
-        umma_commit_ws(&bars.oinit[ko & 1]);   // also covers the X part (the state warps wait for both before S moves on)
-        umma_commit_ws(&bars.emptyL[ko % C::NL]);
-      }
-    };
-    // prologue: everything that depends on S_0 only
     issue_u(0);
     if (NT > 1) issue_u(1);
     mbar_wait(&bars.sb, 0);
+    mbar_wait(&bars.w0full, 0);
     tc_fence_after();
-    issue_xo(0, -1);
-    issue_xo(NT > 1 ? 1 : -1, 0);
-    if (NT > 2) issue_u(2);
-    for (int c = 0; c + 1 < NT; ++c) {
-      mbar_wait(&bars.sb, (c + 1) & 1);        // bf16 S_{c+1}^T is in tensor memory
+    {   // v_new_0^T = U_0^T - bf16(S_0^T) Wg_0^T
+      const uint64_t dW0 = umma_desc(sbase + C::OFF_S + C::SSLOT + C::S_XO, 128, 2048, SWZ_NONE);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_PAIR + 128, tm + C::TM_SB + j * 8, dW0 + j * 16, idesc64, 1);
+      umma_commit_ws(&bars.dv0);
+      umma_commit_ws(&bars.w0done);
+    }
+    for (int k = 0; k < NT; ++k) {
+      const int ss = k % C::NS, p = k & 1;
+      const bool last = k + 1 == NT;
+      if (k >= 1) mbar_wait(&bars.sb, k & 1);      // bf16 S_k^T is in tensor memory
+      mbar_wait(&bars.fullS[ss], (k / C::NS) & 1);
+      if (k >= 2) mbar_wait(&bars.dofree[p], ((k >> 1) - 1) & 1);   // O half of the pair has been read and zeroed
       tc_fence_after();
       TTR(3);
-      issue_xo(c + 2 < NT ? c + 2 : -1, c + 1);
+      const uint64_t dXO = umma_desc(sbase + C::OFF_S + ss * C::SSLOT + C::S_XO, 128, 2048, SWZ_NONE);
+      if (!last) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_PAIR + p * 128, tm + C::TM_SB + j * 8, dXO + j * 16, idesc128, 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_ts_ws(tm + C::TM_PAIR + p * 128 + 64, tm + C::TM_SB + j * 8, dXO + (16384 >> 4) + j * 16, idesc64, 1);
+      }
+      umma_commit_ws(&bars.xo[p]);
+      umma_commit_ws(&bars.emptyS[ss]);
       TTR(4);
-      if (c + 3 < NT) issue_u(c + 3);
+      if (k + 2 < NT) issue_u(k + 2);
       TTR(5);
     }
   } else if (warp < 7) {
@@ -661,16 +679,19 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
     const int col = col0 + quad * 32 + lane;
     uint32_t r[32], r2[32], w[32];
-    auto output = [&](int c) {
-      const int buf = c & 1;
-      mbar_wait(&bars.dofull[buf], (c >> 1) & 1);
-      tc_fence_after();
-      tmem_ld32(tlane + C::TM_DO + buf * 64, r);
-      tmem_ld32(tlane + C::TM_DO + buf * 64 + 32, r2);
+    auto output = [&](int c) {   // O_c^T from the O half of PAIR[c & 1] (complete with the RC part of step c)
+      const uint32_t dox = tlane + C::TM_PAIR + (c & 1) * 128 + 64;
+      tmem_ld32(dox, r);
+      tmem_ld32(dox + 32, r2);
       tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = 0u;
+      tmem_st32(dox, w);
+      tmem_st32(dox + 32, w);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.dofree[buf]);
+      if (lane == 0) mbar_arrive(&bars.dofree[c & 1]);
       const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
       const int valid = varlen ? __ldg(vl.chunk_valid + cb + c) : min(GDN_C, T - tok0);
       const size_t tstride = (size_t)H * GDN_V;
@@ -686,12 +707,14 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       }
     };
     for (int c = 0; c < NT; ++c) {
-      const int buf = c & 1;
-      mbar_wait(&bars.dv[buf], (c >> 1) & 1);
+      // v_new_c^T sits in the DV half of PAIR[(c + 1) & 1]: complete with the RC part of step c - 1 (chunk 0: prologue)
+      if (c == 0) mbar_wait(&bars.dv0, 0);
+      else mbar_wait(&bars.rc[(c - 1) & 1], ((c - 1) >> 1) & 1);
       tc_fence_after();
       if (quad == 0) TTR(6);
-      tmem_ld32(tlane + C::TM_DV + buf * 64, r);
-      tmem_ld32(tlane + C::TM_DV + buf * 64 + 32, r2);
+      const uint32_t dvx = tlane + C::TM_PAIR + ((c + 1) & 1) * 128;
+      tmem_ld32(dvx, r);
+      tmem_ld32(dvx + 32, r2);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -700,8 +723,8 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.dvfree[buf]);
-      tmem_st32(tlane + C::TM_VB + buf * 32, w);
+      if (lane == 0) mbar_arrive(&bars.dvfree[(c + 1) & 1]);
+      tmem_st32(tlane + C::TM_VB + (c & 1) * 32, w);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -709,6 +732,8 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       if (quad == 0) TTR(7);
       if (c > 0) output(c - 1);
     }
+    mbar_wait(&bars.rc[(NT - 1) & 1], ((NT - 1) >> 1) & 1);
+    tc_fence_after();
     output(NT - 1);
   } else {
     // ------------------------------- state warps (7..14) --------------------------------
@@ -741,11 +766,11 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     };
     publish();
     for (int c = 0; c < NT; ++c) {
-      const int sl = c % C::NL;
-      mbar_wait(&bars.fullL[sl], (c / C::NL) & 1);
-      const float gamma = *reinterpret_cast<const float*>(smem + C::OFF_L + sl * C::LSLOT + C::L_TAIL);
+      const int ss = c % C::NS;
+      mbar_wait(&bars.fullS[ss], (c / C::NS) & 1);
+      const float gamma = *reinterpret_cast<const float*>(smem + C::OFF_S + ss * C::SSLOT + C::S_TAIL);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars.emptyL[sl]);
+      if (lane == 0) mbar_arrive(&bars.emptyS[ss]);
       mbar_wait(&bars.ds, c & 1);
       tc_fence_after();
       if (warp == 8) TTR(8);
@@ -761,9 +786,9 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       if (lane == 0) mbar_arrive(&bars.dsfree);   // DS may be overwritten by the next B part
       if (warp == 8) TTR(9);
       if (c + 1 < NT) {
-        // every product that reads bf16 S_c^T (X part of chunk c+1, O part of chunk c: warp 2 issues them in that
-        // order and commits after the O part) has retired before the operand is overwritten
-        mbar_wait(&bars.oinit[c & 1], (c >> 1) & 1);
+        // the XO part of step c (the only reader of bf16 S_c^T; chunk 0's extra product was committed before it by
+        // the same warp) has retired before the operand is overwritten
+        mbar_wait(&bars.xo[c & 1], (c >> 1) & 1);
         if (warp == 8) TTR(10);
         publish();
         if (warp == 8) TTR(11);

@@ -36,8 +36,8 @@ buf = (ctypes.c_longlong * (64 * 16))()
 lib.ivl_debug_read_ttrace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 assert lib.ivl_debug_read_ttrace(buf, 64 * 16) == 0
 t = np.array(buf[:]).reshape(64, 16).astype(np.int64)
-names2 = ["M1:vb seen", "M1:R issued", "M1:B+C issued", "M2:sb(c+1) seen", "M2:X(c+2)+O(c+1) issued", "M2:U(c+3) issued", "V:dv seen",
-          "V:vb arrived", "S:ds seen", "S:ld+fma done", "S:oinit seen", "S:sb arrived"]
+names2 = ["M1:vb(k) seen", "M1:B+RC issued", "-", "M2:sb(k) seen", "M2:XO(k) issued", "M2:U(k+2) issued", "V:v_new(k) acc seen",
+          "V:vb(k) arrived", "S:ds(k) seen", "S:ld+fma done", "S:xo(k) seen", "S:sb(k+1) arrived"]
 names = ["M:sb seen", "M:W+O issued", "M:vb seen", "M:B+C issued", "M:U(c+1) issued", "V:dv seen", "V:ld done", "V:vb arrived",
          "V:output done", "S:ds seen", "S:ld+fma done", "S:sb arrived"]
 if MODE == "2":
