@@ -113,6 +113,27 @@ __device__ __forceinline__ void norm_row_quarter(const uint4* raw, bool l2norm, 
   }
 }
 
+// Byte offsets of operand-image elements.  MODE 0 / 1 (gdn_scan.cu, first transposed scan): no-swizzle core-matrix
+// tiling (gdn_layout.cuh).  MODE 2 (lag scan): the canonical 128-byte-swizzled layouts -- rows of 128 bytes (64
+// elements of the contiguous dimension), 16-byte chunk index XORed with (row % 8); wider tiles are 64-element panels
+// back to back.  The tensor core reads a no-swizzle B operand at roughly one 16-byte row piece per cycle (an N = 128
+// K = 16 MMA was measured at ~200 cycles on such an image), a swizzled one at full rate.
+template <int MODE>
+__device__ __forceinline__ uint32_t a1_off(int row, int kd) {   // [-Wg ; Qg]: 128 rows x 128 key dims, K-major
+  return MODE == 2 ? (uint32_t)((kd >> 6) * 16384) + swz128((uint32_t)(row * 128 + (kd & 63) * 2))
+                   : (uint32_t)((row >> 3) * 2048 + (kd >> 3) * 128 + (row & 7) * 16 + (kd & 7) * 2);
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t kt_off(int tok, int kd) {   // Kt: 64 tokens x 128 key dims, MN-major (kd contiguous)
+  return MODE == 2 ? (uint32_t)((kd >> 6) * 8192) + swz128((uint32_t)(tok * 128 + (kd & 63) * 2))
+                   : (uint32_t)((kd >> 3) * 1024 + (tok >> 3) * 128 + (tok & 7) * 16 + (kd & 7) * 2);
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t sq_off(int i, int j) {      // P, Au, R: 64 rows x 64, K-major (j contiguous)
+  return MODE == 2 ? swz128((uint32_t)(i * 128 + j * 2))
+                   : (uint32_t)((i >> 3) * 1024 + (j >> 3) * 128 + (i & 7) * 16 + (j & 7) * 2);
+}
+
 #ifdef IVL_TRACE
 __device__ long long ivl_prep_trace[16 * 8];
 __device__ unsigned long long ivl_prep_wait[4];  // cycles waited on the ring, CTAs that waited, poll iterations
@@ -300,13 +321,9 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     const float Gr = s.G[row], Gc = s.G[63];
     const int R = 64 + row;  // Qg occupies rows 64..127 of the stacked [-Wg ; Qg] operand
     norm_row_quarter(rawq, l2norm != 0, __expf(Gr) * scale, &s.qh[row * KH_LD + qt * 32],
-                     blob + BLOB_OFF_A1, [&](int p) {
-                       return (uint32_t)((R >> 3) * 2048 + (qt * 4 + p) * 128 + (R & 7) * 16);
-                     });
+                     blob + BLOB_OFF_A1, [&](int p) { return a1_off<MODE>(R, (qt * 4 + p) * 8); });
     norm_row_quarter(rawk, l2norm != 0, __expf(Gc - Gr), &s.kh[row * KH_LD + qt * 32],
-                     blob + BLOB_OFF_KT, [&](int p) {
-                       return (uint32_t)((qt * 4 + p) * 1024 + (row >> 3) * 128 + (row & 7) * 16);
-                     });
+                     blob + BLOB_OFF_KT, [&](int p) { return kt_off<MODE>(row, (qt * 4 + p) * 8); });
     if (tid == 0) *reinterpret_cast<float*>(blob + BLOB_OFF_TAIL) = __expf(Gc);
   }
   if (LAG && has_prev) {
@@ -399,9 +416,9 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
         p10 = (i1 >= j0) ? cqk[lt][2] * e10 * scale : 0.f;
         p11 = (i1 >= j1) ? cqk[lt][3] * e11 * scale : 0.f;
       }
-      uint8_t* pimg = blob + BLOB_OFF_P + nt * 128 + tq * 4;
-      *reinterpret_cast<uint32_t*>(pimg + (i0 >> 3) * 1024 + (i0 & 7) * 16) = pack_bf16(p00, p01);
-      *reinterpret_cast<uint32_t*>(pimg + (i1 >> 3) * 1024 + (i1 & 7) * 16) = pack_bf16(p10, p11);
+      uint8_t* pimg = blob + BLOB_OFF_P;
+      *reinterpret_cast<uint32_t*>(pimg + sq_off<MODE>(i0, nt * 8 + 2 * tq)) = pack_bf16(p00, p01);
+      *reinterpret_cast<uint32_t*>(pimg + sq_off<MODE>(i1, nt * 8 + 2 * tq)) = pack_bf16(p10, p11);
     }
   }
   __syncthreads();
@@ -517,7 +534,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     // (i/8) * 1024 + (j/8) * 128), 16-byte pieces, eight consecutive threads fill one 128-byte core matrix
     for (int e = tid; e < 512; e += PREP_THREADS) {
       const int r = e & 7, kg = (e >> 3) & 7, rg = e >> 6, i = rg * 8 + r;
-      *reinterpret_cast<uint4*>(ublob + rg * 1024 + kg * 128 + r * 16) =
+      *reinterpret_cast<uint4*>(ublob + sq_off<MODE>(i, kg * 8)) =
           *reinterpret_cast<const uint4*>(&sAu[i * A_LD + kg * 8]);
     }
   }
@@ -549,9 +566,9 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
 #pragma unroll
     for (int lt = 0; lt < 8; ++lt) {
       const int nt = half * 8 + lt;
-      uint8_t* img = blob + BLOB_OFF_A1 + nt * 128 + tq * 4;
-      *reinterpret_cast<uint32_t*>(img + (i0 >> 3) * 2048 + (i0 & 7) * 16) = pack_bf16(wsc * acc[lt][0], wsc * acc[lt][1]);
-      *reinterpret_cast<uint32_t*>(img + (i1 >> 3) * 2048 + (i1 & 7) * 16) = pack_bf16(wsc * acc[lt][2], wsc * acc[lt][3]);
+      uint8_t* img = blob + BLOB_OFF_A1;
+      *reinterpret_cast<uint32_t*>(img + a1_off<MODE>(i0, nt * 8 + 2 * tq)) = pack_bf16(wsc * acc[lt][0], wsc * acc[lt][1]);
+      *reinterpret_cast<uint32_t*>(img + a1_off<MODE>(i1, nt * 8 + 2 * tq)) = pack_bf16(wsc * acc[lt][2], wsc * acc[lt][3]);
       if (LAG) {   // bf16 Wg rows (unscaled) into the dead T tile: the A operand of R
         *reinterpret_cast<uint32_t*>(&s.qh[i0 * KH_LD + nt * 8 + 2 * tq]) = pack_bf16(acc[lt][0], acc[lt][1]);
         *reinterpret_cast<uint32_t*>(&s.qh[i1 * KH_LD + nt * 8 + 2 * tq]) = pack_bf16(acc[lt][2], acc[lt][3]);
@@ -584,9 +601,9 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
 #pragma unroll
       for (int lt = 0; lt < 4; ++lt) {
         const int nt = half * 4 + lt;
-        uint8_t* rimg = ublob + AU_BYTES + nt * 128 + tq * 4;
-        *reinterpret_cast<uint32_t*>(rimg + (i0 >> 3) * 1024 + (i0 & 7) * 16) = pack_bf16(-cr[lt][0], -cr[lt][1]);
-        *reinterpret_cast<uint32_t*>(rimg + (i1 >> 3) * 1024 + (i1 & 7) * 16) = pack_bf16(-cr[lt][2], -cr[lt][3]);
+        uint8_t* rimg = ublob + AU_BYTES;
+        *reinterpret_cast<uint32_t*>(rimg + sq_off<MODE>(i0, nt * 8 + 2 * tq)) = pack_bf16(-cr[lt][0], -cr[lt][1]);
+        *reinterpret_cast<uint32_t*>(rimg + sq_off<MODE>(i1, nt * 8 + 2 * tq)) = pack_bf16(-cr[lt][2], -cr[lt][3]);
       }
     }
 #pragma unroll

@@ -409,11 +409,14 @@ struct T2Cfg {
   static constexpr uint32_t V_PANEL = 8192;
   static constexpr uint32_t U_AU = 16384;                     // Au, 8 KiB
   static constexpr uint32_t USLOT = 24576;
-  static constexpr uint32_t S_XO = 0;                         // rows 0..63: -gamma Wg_{k+1}; rows 64..127: Qg_k (32 KiB)
+  // every operand is a 128-byte-swizzled tile (1 KiB aligned); K-major tiles wider than 64 are two 64-wide panels
+  static constexpr uint32_t S_XO = 0;                         // 2 panels x [rows 0..63: -gamma Wg_{k+1}; rows 64..127: Qg_k] (32 KiB)
+  static constexpr uint32_t XO_PANEL = 16384;
   static constexpr uint32_t S_RC = 32768;                     // rows 0..63: -R_{k+1}; rows 64..127: P_k (16 KiB)
-  static constexpr uint32_t S_KT = 49152;                     // Kt_k (16 KiB) | gamma_k (128 B)
+  static constexpr uint32_t S_KT = 49152;                     // Kt_k: 2 panels of 64 key dims x [64 tok][128 B] | gamma_k (128 B)
+  static constexpr uint32_t KT_PANEL = 8192;
   static constexpr uint32_t S_TAIL = S_KT + KT_BYTES;
-  static constexpr uint32_t SSLOT = S_TAIL + TAIL_BYTES;      // 64 KiB + 128 B (no swizzled tile inside)
+  static constexpr uint32_t SSLOT = S_TAIL + 1024;            // 65 KiB (swizzled tiles: slots stay 1 KiB aligned)
   static constexpr uint32_t OFF_U = 0;
   static constexpr uint32_t OFF_S = NU * USLOT;
   static constexpr uint32_t OFF_BARS = OFF_S + NS * SSLOT;
@@ -423,7 +426,7 @@ struct T2Cfg {
   static constexpr uint32_t TM_PAIR = 192;   // 2 x (64 DV + 64 DO)
   static constexpr uint32_t TM_VB = 448;     // 2 x 32
   static constexpr uint32_t TM_COLS = 512;
-  static_assert(USLOT % 1024 == 0 && OFF_S % 1024 == 0 && SSLOT % 128 == 0, "alignment");
+  static_assert(USLOT % 1024 == 0 && OFF_S % 1024 == 0 && SSLOT % 1024 == 0 && S_RC % 1024 == 0 && S_KT % 1024 == 0, "alignment");
   static_assert(SMEM <= 232448, "exceeds 227 KiB");
 };
 
@@ -549,8 +552,9 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       // has retired
       need(0);
       mbar_arrive_expect_tx_ws(&bars.w0full, 16384);
-      bulk_g2s_ws(smem + C::OFF_S + C::SSLOT + C::S_XO, blob + (size_t)(cb % ring) * BLOB_BYTES + BLOB_OFF_A1, 16384,
-                  &bars.w0full);
+      for (int pn = 0; pn < 2; ++pn)   // rows 0..63 of both 64-wide panels
+        bulk_g2s_ws(smem + C::OFF_S + C::SSLOT + C::S_XO + pn * C::XO_PANEL,
+                    blob + (size_t)(cb % ring) * BLOB_BYTES + BLOB_OFF_A1 + pn * C::XO_PANEL, 8192, &bars.w0full);
       for (int k = 0; k < NT; ++k) {
         const bool last = k + 1 == NT;
         need(last ? k : k + 1);
@@ -567,10 +571,14 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
         uint8_t* sl = smem + C::OFF_S + ss * C::SSLOT;
         mbar_arrive_expect_tx_ws(&bars.fullS[ss], (last ? 0u : 16384u + AU_BYTES) + 16384u + P_BYTES + KT_BYTES + TAIL_BYTES);
         if (!last) {
-          bulk_g2s_ws(sl + C::S_XO, blob + cn * BLOB_BYTES + BLOB_OFF_A1, 16384, &bars.fullS[ss]);
+          for (int pn = 0; pn < 2; ++pn)
+            bulk_g2s_ws(sl + C::S_XO + pn * C::XO_PANEL, blob + cn * BLOB_BYTES + BLOB_OFF_A1 + pn * C::XO_PANEL, 8192,
+                        &bars.fullS[ss]);
           bulk_g2s_ws(sl + C::S_RC, aublob + cn * (GDN_NS * UBLOB_BYTES) + AU_BYTES, AU_BYTES, &bars.fullS[ss]);
         }
-        bulk_g2s_ws(sl + C::S_XO + 16384, blob + cs * BLOB_BYTES + BLOB_OFF_A1 + 16384, 16384, &bars.fullS[ss]);
+        for (int pn = 0; pn < 2; ++pn)
+          bulk_g2s_ws(sl + C::S_XO + pn * C::XO_PANEL + 8192, blob + cs * BLOB_BYTES + BLOB_OFF_A1 + pn * C::XO_PANEL + 8192,
+                      8192, &bars.fullS[ss]);
         bulk_g2s_ws(sl + C::S_RC + AU_BYTES, blob + cs * BLOB_BYTES + BLOB_OFF_P, P_BYTES, &bars.fullS[ss]);
         bulk_g2s_ws(sl + C::S_KT, blob + cs * BLOB_BYTES + BLOB_OFF_KT, KT_BYTES + TAIL_BYTES, &bars.fullS[ss]);
       }
@@ -581,6 +589,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     for (int k = 0; k < NT; ++k) {
       const int ss = k % C::NS, p = k & 1;
+      [[maybe_unused]] const int c = k;   // (timeline probe)
       const bool last = k + 1 == NT;
       const uint32_t sl = sbase + C::OFF_S + ss * C::SSLOT;
       const uint32_t vbk = tm + C::TM_VB + p * 32;
@@ -588,23 +597,23 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       mbar_wait(&bars.vb, k & 1);                                    // bf16 v_new_k^T is in tensor memory
       mbar_wait(&bars.fullS[ss], (k / C::NS) & 1);
       TTR(0);
-      const uint64_t dKt = umma_desc(sl + C::S_KT, 128, 1024, SWZ_NONE);
-      const uint64_t dRC = umma_desc(sl + C::S_RC, 128, 1024, SWZ_NONE);
+      const uint64_t dKt = umma_desc(sl + C::S_KT, C::KT_PANEL, 1024, SWZ_128B);   // MN-major: 16 tokens = 2 KiB per MMA
+      const uint64_t dRC = umma_desc(sl + C::S_RC, 16, 1024, SWZ_128B);            // K-major: 32 B per MMA
       auto issue_b = [&]() {
         if (k >= 1) mbar_wait(&bars.dsfree, (k - 1) & 1);            // the state warps have read DS of step k - 1
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DS, vbk + j * 8, dKt + j * 16, idescB, j > 0);
+        for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DS, vbk + j * 8, dKt + j * 128, idescB, j > 0);
         umma_commit_ws(&bars.ds);
       };
       auto issue_rc = [&]() {
         tc_fence_after();
         if (!last) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(pair, vbk + j * 8, dRC + j * 16, idesc128, 1);
+          for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(pair, vbk + j * 8, dRC + j * 2, idesc128, 1);
         } else {   // no chunk k + 1: only the P half, into the O half of the pair
 #pragma unroll
-          for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(pair + 64, vbk + j * 8, dRC + (AU_BYTES >> 4) + j * 16, idesc64, 1);
+          for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(pair + 64, vbk + j * 8, dRC + (AU_BYTES >> 4) + j * 2, idesc64, 1);
         }
         umma_commit_ws(&bars.rc[p]);
       };
@@ -632,10 +641,10 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       if (c >= 2) mbar_wait(&bars.dvfree[(c + 1) & 1], ((c - 2) >> 1) & 1);   // v_new accumulator of chunk c - 2 has been read
       tc_fence_after();
       const uint64_t dV = umma_desc(us + C::U_V, C::V_PANEL, 1024, SWZ_128B);
-      const uint64_t dAu = umma_desc(us + C::U_AU, 128, 1024, SWZ_NONE);
+      const uint64_t dAu = umma_desc(us + C::U_AU, 16, 1024, SWZ_128B);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        umma_bf16_ws(tm + C::TM_PAIR + ((c + 1) & 1) * 128, dV + j * 128, dAu + j * 16, idescU, j > 0);
+        umma_bf16_ws(tm + C::TM_PAIR + ((c + 1) & 1) * 128, dV + j * 128, dAu + j * 2, idescU, j > 0);
       umma_commit_ws(&bars.emptyU[su]);
     };
     issue_u(0);
@@ -644,28 +653,33 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     mbar_wait(&bars.w0full, 0);
     tc_fence_after();
     {   // v_new_0^T = U_0^T - bf16(S_0^T) Wg_0^T
-      const uint64_t dW0 = umma_desc(sbase + C::OFF_S + C::SSLOT + C::S_XO, 128, 2048, SWZ_NONE);
+      const uint64_t dW0 = umma_desc(sbase + C::OFF_S + C::SSLOT + C::S_XO, 16, 1024, SWZ_128B);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_PAIR + 128, tm + C::TM_SB + j * 8, dW0 + j * 16, idesc64, 1);
+      for (int j = 0; j < 8; ++j)
+        umma_bf16_ts_ws(tm + C::TM_PAIR + 128, tm + C::TM_SB + j * 8, dW0 + (j >> 2) * (C::XO_PANEL >> 4) + (j & 3) * 2, idesc64, 1);
       umma_commit_ws(&bars.dv0);
       umma_commit_ws(&bars.w0done);
     }
     for (int k = 0; k < NT; ++k) {
       const int ss = k % C::NS, p = k & 1;
+      [[maybe_unused]] const int c = k;   // (timeline probe)
       const bool last = k + 1 == NT;
       if (k >= 1) mbar_wait(&bars.sb, k & 1);      // bf16 S_k^T is in tensor memory
       mbar_wait(&bars.fullS[ss], (k / C::NS) & 1);
       if (k >= 2) mbar_wait(&bars.dofree[p], ((k >> 1) - 1) & 1);   // O half of the pair has been read and zeroed
       tc_fence_after();
       TTR(3);
-      const uint64_t dXO = umma_desc(sbase + C::OFF_S + ss * C::SSLOT + C::S_XO, 128, 2048, SWZ_NONE);
+      const uint64_t dXO = umma_desc(sbase + C::OFF_S + ss * C::SSLOT + C::S_XO, 16, 1024, SWZ_128B);
       if (!last) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(tm + C::TM_PAIR + p * 128, tm + C::TM_SB + j * 8, dXO + j * 16, idesc128, 1);
-      } else {
+        for (int j = 0; j < 8; ++j)
+          umma_bf16_ts_ws(tm + C::TM_PAIR + p * 128, tm + C::TM_SB + j * 8, dXO + (j >> 2) * (C::XO_PANEL >> 4) + (j & 3) * 2,
+                          idesc128, 1);
+      } else {   // no chunk k + 1: only the Qg rows (64..127 of each panel), into the O half of the pair
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          umma_bf16_ts_ws(tm + C::TM_PAIR + p * 128 + 64, tm + C::TM_SB + j * 8, dXO + (16384 >> 4) + j * 16, idesc64, 1);
+          umma_bf16_ts_ws(tm + C::TM_PAIR + p * 128 + 64, tm + C::TM_SB + j * 8,
+                          dXO + (8192 >> 4) + (j >> 2) * (C::XO_PANEL >> 4) + (j & 3) * 2, idesc64, 1);
       }
       umma_commit_ws(&bars.xo[p]);
       umma_commit_ws(&bars.emptyS[ss]);
