@@ -602,9 +602,11 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       auto issue_b = [&]() {
         if (k >= 1) mbar_wait(&bars.dsfree, (k - 1) & 1);            // the state warps have read DS of step k - 1
         tc_fence_after();
+        TTR(14);
 #pragma unroll
         for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(tm + C::TM_DS, vbk + j * 8, dKt + j * 128, idescB, j > 0);
         umma_commit_ws(&bars.ds);
+        TTR(2);
       };
       auto issue_rc = [&]() {
         tc_fence_after();
@@ -619,7 +621,7 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       };
       // the RC part is the serial chain, the B part feeds the state: whichever is not blocked goes first (the two
       // write different accumulators, so the order does not change a bit of the result)
-      if (__any_sync(0xffffffffu, mbar_try_wait(&bars.xo[p], (k >> 1) & 1))) {
+      if (__any_sync(0xffffffffu, mbar_test_wait(&bars.xo[p], (k >> 1) & 1))) {
         issue_rc();
         issue_b();
       } else {
@@ -781,7 +783,9 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
     publish();
     for (int c = 0; c < NT; ++c) {
       const int ss = c % C::NS;
+      if (warp == 8) TTR(12);
       mbar_wait(&bars.fullS[ss], (c / C::NS) & 1);
+      if (warp == 8) TTR(13);
       const float gamma = *reinterpret_cast<const float*>(smem + C::OFF_S + ss * C::SSLOT + C::S_TAIL);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.emptyS[ss]);

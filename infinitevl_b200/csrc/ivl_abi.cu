@@ -76,8 +76,11 @@ inline int env_int(const char* name, int dflt) {
 }
 //   IVL_GDN_TSCAN 1 = transposed scan (gdn_scan_t.cu: two CTAs per head, state and v_new as TMEM A operands;
 //                 default), 0 = row-major scan (gdn_scan.cu: 32/64/128-column slices)
-//                 2 = transposed scan, lag form (shortened serial chain; prep also emits R = Wg Kt_prev^T)
-inline int tscan_mode() { const int m = env_int("IVL_GDN_TSCAN", 2); return (m >= 0 && m <= 2) ? m : 2; }
+//                 2 = transposed scan, lag form (shortened serial chain, N = 128 MMA chains over 128B-swizzled stacked
+//                     operands; prep also emits R = Wg Kt_prev^T).  Correct and deterministic, but measured slower
+//                     than form 1 on B200 (1207 vs 977 ns per chunk: tensor-memory reads and ~80-cycle TS-mode MMAs
+//                     bound both; profiles/r02_summary.md), so it is not the default.
+inline int tscan_mode() { const int m = env_int("IVL_GDN_TSCAN", 1); return (m >= 0 && m <= 2) ? m : 1; }
 inline bool tscan() { return tscan_mode() != 0; }
 inline int scan_bv(int dflt) {
   const int bv = env_int("IVL_GDN_BV", dflt);

@@ -36,15 +36,15 @@ buf = (ctypes.c_longlong * (64 * 16))()
 lib.ivl_debug_read_ttrace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 assert lib.ivl_debug_read_ttrace(buf, 64 * 16) == 0
 t = np.array(buf[:]).reshape(64, 16).astype(np.int64)
-names2 = ["M1:vb(k) seen", "M1:B+RC issued", "-", "M2:sb(k) seen", "M2:XO(k) issued", "M2:U(k+2) issued", "V:v_new(k) acc seen",
-          "V:vb(k) arrived", "S:ds(k) seen", "S:ld+fma done", "S:xo(k) seen", "S:sb(k+1) arrived"]
+names2 = ["M1:vb(k) seen", "M1:B+RC issued", "M1:B issued", "M2:sb(k) seen", "M2:XO(k) issued", "M2:U(k+2) issued", "V:v_new(k) acc seen",
+          "V:vb(k) arrived", "S:ds(k) seen", "S:ld+fma done", "S:xo(k) seen", "S:sb(k+1) arrived", "S:loop top", "S:fullS seen", "M1:dsfree seen"]
 names = ["M:sb seen", "M:W+O issued", "M:vb seen", "M:B+C issued", "M:U(c+1) issued", "V:dv seen", "V:ld done", "V:vb arrived",
          "V:output done", "S:ds seen", "S:ld+fma done", "S:sb arrived"]
 if MODE == "2":
     names = names2
 period = np.diff(t[:, 0])
 print("chunk period (cycles): median", np.median(period), "min", period.min(), "max", period.max())
-rel = t[:, :12] - t[:, 0:1]
+rel = t[:, :len(names)] - t[:, 0:1]
 med = np.median(rel[4:60], axis=0)
 for i in np.argsort(med):
     print(f"{names[i]:18s} +{med[i]:8.0f}")
