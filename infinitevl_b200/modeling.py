@@ -495,3 +495,443 @@ class HybridDecoder(nn.Module):
                 h = layer(h, position_ids=position_ids, past_key_values=past_key_values,
                           cache_position=cache_position, position_embeddings=(cos, sin))[0]
         return self.norm(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# model surface: InfiniteVLTextModel / InfiniteVLModel / InfiniteVLQwen2_5_VLForConditionalGeneration
+# (std:1430-1591, 1595-1936, 1980-2322).  Same constructor arguments, module tree (= state-dict keys of the
+# checkpoint: model.language_model.*, lm_head.weight), forward signatures and output fields, so that
+# inference_examples/demo_streaming_inference.py's calls work unchanged.  The vision tower is outside the hot
+# path: a caller attaches its own module as `model.visual`, or passes `inputs_embeds`.
+# ------------------------------------------------------------------------------------------------
+class _Output(dict):
+    """Attribute + key + index access, like transformers' ModelOutput (None fields are skipped when indexing)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __getitem__(self, k):
+        if isinstance(k, int):
+            return [v for v in self.values() if v is not None][k]
+        return dict.__getitem__(self, k)
+
+    def to_tuple(self):
+        return tuple(v for v in self.values() if v is not None)
+
+
+class InfiniteVLConfig:
+    """Minimal stand-in for InfiniteVLConfig (configuration_infinitevl.py): `text_config` (HybridTextConfig or any
+    object with its attributes), the multimodal token ids and the two vision_config fields the text side reads.
+    `from_dict` / `from_json` accept the checkpoint's config.json (text fields at top level or under text_config)."""
+
+    def __init__(self, text_config=None, vision_config=None, image_token_id=151655, video_token_id=151656,
+                 vision_start_token_id=151652, vision_end_token_id=151653, tie_word_embeddings=True, **kw):
+        self.text_config = text_config if text_config is not None else HybridTextConfig()
+        vc = dict(spatial_merge_size=2, tokens_per_second=2)
+        vc.update(vision_config or {})
+        self.vision_config = _Output(vc)
+        self.image_token_id, self.video_token_id = image_token_id, video_token_id
+        self.vision_start_token_id, self.vision_end_token_id = vision_start_token_id, vision_end_token_id
+        self.tie_word_embeddings = tie_word_embeddings
+        for k_, v_ in kw.items():
+            setattr(self, k_, v_)
+
+    def get_text_config(self, decoder=False):
+        return self.text_config
+
+    @classmethod
+    def from_dict(cls, d):
+        d = dict(d)
+        text = dict(d.pop("text_config", None) or {})
+        names = set(vars(HybridTextConfig()).keys()) | {"vocab_size", "pad_token_id", "use_cache"}
+        for k_ in list(d):
+            if k_ in names and k_ not in text:
+                text[k_] = d[k_]
+        if isinstance(text.get("rope_scaling"), dict):
+            text["rope_scaling"] = {"rope_theta": text.get("rope_theta", 1e6), **text["rope_scaling"]}
+        keep = {k_: d[k_] for k_ in ("image_token_id", "video_token_id", "vision_start_token_id", "vision_end_token_id",
+                                     "tie_word_embeddings") if k_ in d}
+        return cls(text_config=HybridTextConfig(**text), vision_config=d.get("vision_config"), **keep)
+
+    @classmethod
+    def from_json(cls, path):
+        import json
+        with open(path) as f:
+            return cls.from_dict(json.load(f))
+
+
+def get_rope_index(config, input_ids=None, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None,
+                   attention_mask=None):
+    """M-RoPE position ids [3, B, T] and per-row deltas [B, 1] for text with image / video placeholders
+    (InfiniteVLModel.get_rope_index, std:1623-1758; index arithmetic: bit-exact).  Text tokens advance all three rows
+    together; the placeholders of a vision block get (t * seconds_per_grid * tokens_per_second, h, w) grid
+    coordinates offset by the position the block starts at; the next text token continues after the block's
+    largest coordinate."""
+    merge = int(config.vision_config.spatial_merge_size)
+    tps = config.vision_config.tokens_per_second
+    if input_ids is None or (image_grid_thw is None and video_grid_thw is None):
+        if attention_mask is not None:
+            pos = attention_mask.long().cumsum(-1) - 1
+            pos.masked_fill_(attention_mask == 0, 1)
+            pos = pos.unsqueeze(0).expand(3, -1, -1).to(attention_mask.device)
+            mx = pos.max(0, keepdim=False)[0].max(-1, keepdim=True)[0]
+            return pos, mx + 1 - attention_mask.shape[-1]
+        B, T = input_ids.shape
+        pos = torch.arange(T, device=input_ids.device).view(1, 1, -1).expand(3, B, -1)
+        return pos, torch.zeros([B, 1], device=input_ids.device, dtype=input_ids.dtype)
+    B, T = input_ids.shape
+    ids_cpu = input_ids.cpu()
+    mask_cpu = (attention_mask == 1).cpu() if attention_mask is not None else None
+    img = image_grid_thw.cpu().tolist() if image_grid_thw is not None else []
+    vid = video_grid_thw.cpu().tolist() if video_grid_thw is not None else []
+    spg = second_per_grid_ts.cpu().tolist() if second_per_grid_ts is not None else None
+    out = torch.ones(3, B, T, dtype=input_ids.dtype)
+    deltas = []
+    n_img = n_vid = 0
+    for b in range(B):
+        row = ids_cpu[b][mask_cpu[b]] if mask_cpu is not None else ids_cpu[b]
+        L = row.numel()
+        starts = torch.nonzero(row == config.vision_start_token_id).squeeze(1)
+        starts = starts[starts + 1 < L]
+        kinds = row[starts + 1]
+        blocks = [(int(s), int(kd)) for s, kd in zip(starts.tolist(), kinds.tolist())
+                  if kd in (config.image_token_id, config.video_token_id)]
+        pieces, st, nxt = [], 0, 0
+        for _, kind in blocks:
+            tok = row[st:]
+            hit = torch.nonzero(tok == kind)
+            ed = st + int(hit[0]) if hit.numel() else L + 1      # first placeholder of this block at or after st
+            if kind == config.image_token_id:
+                t, hh, ww = img[n_img]; n_img += 1
+                sec = 0
+            else:
+                t, hh, ww = vid[n_vid]
+                sec = spg[n_vid] if spg is not None else 1.0
+                n_vid += 1
+            gh, gw = hh // merge, ww // merge
+            text_len = ed - st
+            pieces.append(torch.arange(text_len).view(1, -1).expand(3, -1) + nxt)
+            base = text_len + nxt
+            # the time coordinate goes through the same integer-tensor arithmetic as the reference
+            # (arange (int64) * seconds * tokens_per_second, then .long())
+            rng = torch.arange(t).view(-1, 1).expand(-1, gh * gw)
+            t_idx = (rng * torch.as_tensor(sec, dtype=rng.dtype) * tps).long().flatten()
+            h_idx = torch.arange(gh).view(1, -1, 1).expand(t, -1, gw).flatten()
+            w_idx = torch.arange(gw).view(1, 1, -1).expand(t, gh, -1).flatten()
+            grid = torch.stack([t_idx, h_idx, w_idx]) + base
+            pieces.append(grid)
+            nxt = int(grid.max()) + 1 if grid.numel() else (int(pieces[-2].max()) + 1 if text_len else nxt)
+            st = ed + t * gh * gw
+        if st < L:
+            pieces.append(torch.arange(L - st).view(1, -1).expand(3, -1) + nxt)
+        llm = torch.cat(pieces, dim=1).reshape(3, -1)
+        if mask_cpu is not None:
+            out[:, b, mask_cpu[b]] = llm.to(out.dtype)
+        else:
+            out[:, b, :] = llm.to(out.dtype)
+        deltas.append(int(llm.max()) + 1 - T)
+    return out.to(input_ids.device), torch.tensor(deltas).unsqueeze(1).to(input_ids.device)
+
+
+class InfiniteVLTextModel(nn.Module):
+    """Embeddings + decoder stack + final norm (std:1430-1591)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.padding_idx = getattr(config, "pad_token_id", None)
+        self.vocab_size = getattr(config, "vocab_size", 151936)
+        self.embed_tokens = nn.Embedding(self.vocab_size, config.hidden_size, self.padding_idx)
+        self.layers = nn.ModuleList([InfiniteVLDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.norm = InfiniteVLRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.rotary_emb = InfiniteVLRotaryEmbedding(config=config)
+        self.has_sliding_layers = "sliding_attention" in config.layer_types
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.embed_tokens = value
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                cache_position=None, **kwargs):
+        use_cache = use_cache if use_cache is not None else getattr(self.config, "use_cache", False)
+        return_dict = True if return_dict is None else return_dict
+        if (input_ids is None) ^ (inputs_embeds is not None):
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
+        if output_attentions:
+            raise NotImplementedError("attention weights are never materialised by the B200 kernels")
+        if inputs_embeds is None:
+            inputs_embeds = self.embed_tokens(input_ids)
+        # allocate the static cache on the first forward pass (std:1488-1501)
+        if use_cache and (past_key_values is None or not isinstance(past_key_values, StaticCachePrealloc)):
+            past_key_values = StaticCachePrealloc(config=self.config, batch_size=inputs_embeds.shape[0],
+                                                  dtype=inputs_embeds.dtype, device=inputs_embeds.device)
+        B, T, _ = inputs_embeds.shape
+        if cache_position is None:
+            past = past_key_values.get_seq_length() if past_key_values is not None else 0
+            cache_position = torch.arange(past, past + T, device=inputs_embeds.device)
+        position_ids, text_position_ids = normalize_position_ids(position_ids, cache_position.reshape(-1), B)
+        # The reference builds its mask through create_causal_mask; on its FA2 path that is the 2-D padding mask when
+        # something is padded and None otherwise (causality and the window live in the kernel).  Same here: an
+        # all-ones mask is dropped, a real padding mask travels to the attention operator, which refuses it.
+        if isinstance(attention_mask, dict):
+            attention_mask = attention_mask.get("full_attention")
+        if attention_mask is not None and attention_mask.dim() == 2 and bool(attention_mask.all()):
+            attention_mask = None
+        cos, sin = self.rotary_emb(inputs_embeds, position_ids)
+        cos, sin = mrope_select(cos, sin, self.config.rope_scaling["mrope_section"])
+        h = inputs_embeds
+        all_hidden = () if output_hidden_states else None
+        for layer in self.layers:
+            if output_hidden_states:
+                all_hidden += (h,)
+            h = layer(h, attention_mask=attention_mask, position_ids=text_position_ids,
+                      past_key_values=past_key_values, use_cache=use_cache, cache_position=cache_position,
+                      position_embeddings=(cos, sin))[0]
+        h = self.norm(h)
+        if output_hidden_states:
+            all_hidden += (h,)
+        out = _Output(last_hidden_state=h, past_key_values=past_key_values if use_cache else None,
+                      hidden_states=all_hidden, attentions=None)
+        return out if return_dict else out.to_tuple()
+
+
+class InfiniteVLModel(nn.Module):
+    """language_model (+ an optional caller-supplied `visual`), M-RoPE position bookkeeping (std:1595-1936)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.visual = None           # vision tower: out of the hot path; attach a module with the reference's interface
+        self.language_model = InfiniteVLTextModel(config.text_config)
+        self.rope_deltas = None
+
+    def get_input_embeddings(self):
+        return self.language_model.get_input_embeddings()
+
+    def set_input_embeddings(self, value):
+        self.language_model.set_input_embeddings(value)
+
+    def get_decoder(self):
+        return self.language_model
+
+    def set_decoder(self, decoder):
+        self.language_model = decoder
+
+    def get_rope_index(self, input_ids=None, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None,
+                       attention_mask=None):
+        return get_rope_index(self.config, input_ids, image_grid_thw, video_grid_thw, second_per_grid_ts, attention_mask)
+
+    def _vision_features(self, pixels, grid_thw):
+        if self.visual is None:
+            raise NotImplementedError("no vision tower attached (model.visual is None): pass inputs_embeds with the "
+                                      "image features already scattered in, or attach the reference's vision module")
+        emb = self.visual(pixels.type(next(self.visual.parameters()).dtype), grid_thw=grid_thw)
+        return emb
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None, pixel_values=None,
+                pixel_values_videos=None, image_grid_thw=None, video_grid_thw=None, rope_deltas=None,
+                cache_position=None, second_per_grid_ts=None, **kwargs):
+        return_dict = True if return_dict is None else return_dict
+        if inputs_embeds is None:
+            inputs_embeds = self.get_input_embeddings()(input_ids)
+        for pixels, grid, token in ((pixel_values, image_grid_thw, self.config.image_token_id),
+                                    (pixel_values_videos, video_grid_thw, self.config.video_token_id)):
+            if pixels is None:
+                continue
+            feats = self._vision_features(pixels, grid).to(inputs_embeds.device, inputs_embeds.dtype)
+            if input_ids is None:
+                raise NotImplementedError("scattering vision features needs input_ids to find the placeholders")
+            mask = (input_ids == token).unsqueeze(-1).expand_as(inputs_embeds)
+            if inputs_embeds[mask].numel() != feats.numel():
+                raise ValueError(f"Image features and image tokens do not match: tokens: {int((input_ids == token).sum())}, "
+                                 f"features {feats.shape[0]}")
+            inputs_embeds = inputs_embeds.masked_scatter(mask, feats)
+        if position_ids is None:
+            prefill = (cache_position is not None and int(cache_position.reshape(-1)[0]) == 0) or \
+                      (past_key_values is None or past_key_values.get_seq_length() == 0)
+            if prefill or self.rope_deltas is None:
+                position_ids, rope_deltas = self.get_rope_index(input_ids, image_grid_thw, video_grid_thw,
+                                                                second_per_grid_ts=second_per_grid_ts,
+                                                                attention_mask=attention_mask)
+                self.rope_deltas = rope_deltas
+            else:
+                B, T, _ = inputs_embeds.shape
+                position_ids = torch.arange(T, device=inputs_embeds.device).view(1, 1, -1).expand(3, B, -1)
+                if cache_position is not None:
+                    delta = (cache_position.reshape(-1)[0] + self.rope_deltas).to(inputs_embeds.device)
+                else:
+                    delta = torch.zeros((B, T), device=inputs_embeds.device)
+                delta = delta.repeat_interleave(B // delta.shape[0], dim=1)
+                position_ids = position_ids + delta.to(position_ids.device)
+        out = self.language_model(input_ids=None, position_ids=position_ids, attention_mask=attention_mask,
+                                  past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
+                                  output_attentions=output_attentions, output_hidden_states=output_hidden_states,
+                                  return_dict=True, cache_position=cache_position, **kwargs)
+        res = _Output(last_hidden_state=out.last_hidden_state, past_key_values=out.past_key_values,
+                      hidden_states=out.hidden_states, attentions=None, rope_deltas=self.rope_deltas)
+        return res if return_dict else res.to_tuple()
+
+
+class InfiniteVLQwen2_5_VLForConditionalGeneration(nn.Module):
+    """model + lm_head (std:1980-2322).  forward(...).logits, allocate_inference_cache(batch_size), a greedy
+    generate(); `from_pretrained(dir)` loads the language-model weights of a checkpoint directory (config.json +
+    *.safetensors), ignoring the vision tower's."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.model = InfiniteVLModel(config)
+        tc = config.text_config
+        self.lm_head = nn.Linear(tc.hidden_size, getattr(tc, "vocab_size", 151936), bias=False)
+        if getattr(config, "tie_word_embeddings", True):
+            self.lm_head.weight = self.model.language_model.embed_tokens.weight
+
+    @property
+    def language_model(self):
+        return self.model.language_model
+
+    @property
+    def visual(self):
+        return self.model.visual
+
+    def get_input_embeddings(self):
+        return self.model.get_input_embeddings()
+
+    def get_decoder(self):
+        return self.model.get_decoder()
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    def allocate_inference_cache(self, batch_size, **kw):
+        """std:2316-2322 (extension: keyword arguments of StaticCachePrealloc, e.g. state_dtype=torch.float32)."""
+        return StaticCachePrealloc(config=self.config.text_config, batch_size=batch_size, dtype=self.dtype,
+                                   device=self.device, **kw)
+
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, pixel_values=None,
+                pixel_values_videos=None, image_grid_thw=None, video_grid_thw=None, rope_deltas=None,
+                cache_position=None, second_per_grid_ts=None, logits_to_keep=0, return_dict=True, **kwargs):
+        out = self.model(input_ids=input_ids, pixel_values=pixel_values, pixel_values_videos=pixel_values_videos,
+                         image_grid_thw=image_grid_thw, video_grid_thw=video_grid_thw,
+                         second_per_grid_ts=second_per_grid_ts, position_ids=position_ids,
+                         attention_mask=attention_mask, past_key_values=past_key_values, inputs_embeds=inputs_embeds,
+                         use_cache=use_cache, output_attentions=output_attentions,
+                         output_hidden_states=output_hidden_states, return_dict=True, cache_position=cache_position,
+                         **kwargs)
+        h = out.last_hidden_state
+        # logits_to_keep = 0 keeps every position (slice(-0, None)), as in the reference (std:2091-2092)
+        idx = slice(-logits_to_keep, None) if isinstance(logits_to_keep, int) else logits_to_keep
+        logits = self.lm_head(h[:, idx, :])
+        loss = None
+        if labels is not None:
+            lg = logits.float()
+            loss = F.cross_entropy(lg[:, :-1].reshape(-1, lg.shape[-1]), labels[:, 1:].reshape(-1), ignore_index=-100)
+        res = _Output(loss=loss, logits=logits, past_key_values=out.past_key_values, hidden_states=out.hidden_states,
+                      attentions=None, rope_deltas=out.rope_deltas)
+        return res if return_dict else res.to_tuple()
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, inputs_embeds=None, position_ids=None, max_new_tokens=32, eos_token_id=None,
+                 past_key_values=None, use_cuda_graph=False, **kwargs):
+        """Greedy decoding: one prefill call, then single-token steps through the static cache (what the demo's QA
+        branch does by hand, demo_streaming_inference.py:389-421).  With use_cuda_graph the decode step is captured
+        once and replayed (ring caches keep their counters on the device, so the replay is exact)."""
+        dev = self.device
+        B = (input_ids if input_ids is not None else inputs_embeds).shape[0]
+        cache = past_key_values if past_key_values is not None else self.allocate_inference_cache(B)
+        past = cache.get_seq_length()
+        T = (input_ids if input_ids is not None else inputs_embeds).shape[1]
+        cp = torch.arange(past, past + T, device=dev)
+        out = self(input_ids=input_ids, inputs_embeds=inputs_embeds, position_ids=position_ids, past_key_values=cache,
+                   use_cache=True, cache_position=cp, logits_to_keep=1, **kwargs)
+        nxt = out.logits[:, -1].argmax(-1, keepdim=True)
+        pos_next = (position_ids.max() + 1 if position_ids is not None else torch.tensor(past + T, device=dev)).reshape(())
+        tokens = [nxt]
+        static_tok = nxt.clone()
+        static_cp = torch.zeros(1, dtype=torch.long, device=dev)
+        static_pos = torch.zeros(3, B, 1, dtype=torch.long, device=dev)
+
+        def step():
+            return self(input_ids=static_tok, position_ids=static_pos, past_key_values=cache, use_cache=True,
+                        cache_position=static_cp, logits_to_keep=1).logits[:, -1].argmax(-1, keepdim=True)
+
+        graph = None
+        finished = torch.zeros(B, dtype=torch.bool, device=dev)
+        for i in range(1, max_new_tokens):
+            if eos_token_id is not None:
+                finished |= nxt.view(-1) == eos_token_id
+                if bool(finished.all()):
+                    break
+            static_tok.copy_(nxt)
+            static_cp.fill_(past + T + i - 1)
+            static_pos.copy_((pos_next + (i - 1)).expand(3, B, 1))
+            if use_cuda_graph and graph is None and i >= 2:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        static_out = step()
+                torch.cuda.current_stream().wait_stream(side)
+                graph.replay()
+                nxt = static_out.clone()
+            elif graph is not None:
+                graph.replay()
+                nxt = static_out.clone()
+            else:
+                nxt = step()
+            tokens.append(nxt)
+        return torch.cat(tokens, dim=1)
+
+    # -- checkpoints ---------------------------------------------------------------------------------------------
+    def hf_state_dict(self):
+        """State dict under the checkpoint's names (model.language_model.*, lm_head.weight); the tied lm_head is
+        omitted as in the published checkpoint."""
+        sd = {k_: v_ for k_, v_ in self.state_dict().items() if not k_.startswith("model.visual.")}
+        if getattr(self.config, "tie_word_embeddings", True):
+            sd.pop("lm_head.weight", None)
+        return sd
+
+    @classmethod
+    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device="cuda", **kwargs):
+        import glob
+        import os as _os
+        cfg = InfiniteVLConfig.from_json(_os.path.join(path, "config.json"))
+        model = cls(cfg)
+        files = sorted(glob.glob(_os.path.join(path, "*.safetensors")))
+        if not files:
+            raise FileNotFoundError(f"no *.safetensors under {path}")
+        from safetensors.torch import load_file
+        sd = {}
+        for f in files:
+            sd.update(load_file(f))
+        # old checkpoints store the text model directly under `model.` (std:1597 _checkpoint_conversion_mapping)
+        fixed = {}
+        for k_, v_ in sd.items():
+            if k_.startswith("visual.") or k_.startswith("model.visual."):
+                continue
+            if k_.startswith("model.") and not k_.startswith("model.language_model."):
+                k_ = "model.language_model." + k_[len("model."):]
+            fixed[k_] = v_
+        missing, unexpected = model.load_state_dict(fixed, strict=False)
+        missing = [m for m in missing if not (m == "lm_head.weight" and cfg.tie_word_embeddings)
+                   and not m.endswith("rotary_emb.inv_freq")]
+        if missing or unexpected:
+            raise RuntimeError(f"checkpoint does not match the model: missing {missing[:5]}, unexpected {unexpected[:5]}")
+        return model.to(device=device, dtype=torch_dtype).eval()

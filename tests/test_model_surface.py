@@ -1,0 +1,106 @@
+"""CPU tests of the model surface (SURVEY.md section 8 rows a-T, b-6, f-4): module tree = checkpoint state-dict
+names, config.json parsing, get_rope_index bit-exact against the reference's own function, checkpoint round trip,
+argument rules of the text model.  (The forward passes need the CUDA kernels: tests/test_model_gpu.py.)"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from infinitevl_b200 import modeling as M
+
+from golden.make_golden_rope_index import cases
+
+
+def _small(layers=4, vocab=512):
+    return M.InfiniteVLConfig(text_config=M.HybridTextConfig(num_hidden_layers=layers, vocab_size=vocab))
+
+
+def test_module_tree_matches_checkpoint_names():
+    m = M.InfiniteVLQwen2_5_VLForConditionalGeneration(_small())
+    keys = set(m.state_dict())
+    for k in ("model.language_model.embed_tokens.weight", "model.language_model.norm.weight", "lm_head.weight",
+              "model.language_model.layers.0.self_attn.q_proj.bias", "model.language_model.layers.0.self_attn.o_proj.weight",
+              "model.language_model.layers.1.self_attn.A_log", "model.language_model.layers.1.self_attn.dt_bias",
+              "model.language_model.layers.1.self_attn.q_conv1d.weight", "model.language_model.layers.1.self_attn.o_norm.weight",
+              "model.language_model.layers.1.self_attn.g_proj.weight", "model.language_model.layers.1.mlp.down_proj.weight",
+              "model.language_model.layers.3.post_attention_layernorm.weight"):
+        assert k in keys, k
+    # tied head: one tensor, and the exported dict omits it as the published checkpoint does
+    assert m.lm_head.weight is m.model.language_model.embed_tokens.weight
+    assert "lm_head.weight" not in m.hf_state_dict()
+    assert m.model.language_model.layers[0].attention_type == "sliding_attention"
+    assert m.model.language_model.layers[1].attention_type == "linear_attention"
+
+
+def test_config_from_reference_style_json(tmp_path):
+    d = {"hidden_size": 2048, "intermediate_size": 11008, "num_hidden_layers": 36, "num_attention_heads": 16,
+         "num_key_value_heads": 2, "rms_norm_eps": 1e-6, "rope_theta": 1e6, "sliding_window": 8192,
+         "use_sliding_window": True, "tie_word_embeddings": True, "vocab_size": 151936, "image_token_id": 151655,
+         "video_token_id": 151656, "vision_start_token_id": 151652,
+         "rope_scaling": {"mrope_section": [16, 24, 24], "rope_type": "default", "type": "default"},
+         "vision_config": {"spatial_merge_size": 2, "tokens_per_second": 2, "depth": 32}}
+    p = tmp_path / "config.json"
+    p.write_text(json.dumps(d))
+    cfg = M.InfiniteVLConfig.from_json(str(p))
+    tc = cfg.text_config
+    assert (tc.num_hidden_layers, tc.sliding_window, tc.vocab_size, tc.num_linear_heads) == (36, 8192, 151936, 16)
+    assert tc.layer_types[:5] == ["sliding_attention", "linear_attention", "linear_attention", "linear_attention",
+                                  "sliding_attention"]
+    assert tc.rope_scaling["mrope_section"] == [16, 24, 24] and tc.rope_scaling["rope_theta"] == 1e6
+    assert cfg.vision_config.spatial_merge_size == 2 and cfg.image_token_id == 151655
+
+
+def test_get_rope_index_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_rope_index.npz"))
+    cfg = _small()
+    for i, c in enumerate(cases()):
+        t = lambda x, dt=torch.long: None if x is None else torch.tensor(x, dtype=dt)
+        pos, delta = M.get_rope_index(cfg, t(c["ids"]), t(c["img"]), t(c["vid"]), t(c["spg"], torch.float32), t(c["mask"]))
+        assert np.array_equal(pos.numpy(), z[f"pos{i}"]), i
+        assert np.array_equal(delta.numpy(), z[f"delta{i}"]), i
+    # text only: arange on all three rows, zero deltas; with a padding mask: cumsum rule
+    ids = torch.arange(12).view(2, 6)
+    pos, delta = M.get_rope_index(cfg, ids)
+    assert torch.equal(pos, torch.arange(6).view(1, 1, 6).expand(3, 2, 6)) and int(delta.abs().sum()) == 0
+    mask = torch.tensor([[0, 0, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1]])
+    pos, delta = M.get_rope_index(cfg, ids, attention_mask=mask)
+    assert pos[0, 0].tolist() == [1, 1, 0, 1, 2, 3] and delta.view(-1).tolist() == [-2, 0]
+
+
+def test_checkpoint_round_trip(tmp_path):
+    st = pytest.importorskip("safetensors.torch")
+    cfg = _small(layers=4, vocab=256)
+    torch.manual_seed(0)
+    m = M.InfiniteVLQwen2_5_VLForConditionalGeneration(cfg).bfloat16()
+    sd = {k: v.contiguous() for k, v in m.hf_state_dict().items()}
+    sd["model.visual.blocks.0.attn.qkv.weight"] = torch.zeros(4, 4)      # the vision tower's weights are ignored
+    st.save_file(sd, str(tmp_path / "model-00001-of-00001.safetensors"))
+    d = {"num_hidden_layers": 4, "vocab_size": 256, "tie_word_embeddings": True,
+         "rope_scaling": {"mrope_section": [16, 24, 24], "rope_type": "default"}}
+    (tmp_path / "config.json").write_text(json.dumps(d))
+    m2 = M.InfiniteVLQwen2_5_VLForConditionalGeneration.from_pretrained(str(tmp_path), device="cpu")
+    a, b = m.state_dict(), m2.state_dict()
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # a key that matches nothing is an error, not silently dropped
+    sd["model.language_model.layers.0.self_attn.bogus"] = torch.zeros(1)
+    st.save_file(sd, str(tmp_path / "model-00001-of-00001.safetensors"))
+    with pytest.raises(RuntimeError):
+        M.InfiniteVLQwen2_5_VLForConditionalGeneration.from_pretrained(str(tmp_path), device="cpu")
+
+
+def test_text_model_argument_rules():
+    tm = M.InfiniteVLTextModel(M.HybridTextConfig(num_hidden_layers=2, vocab_size=64))
+    with pytest.raises(ValueError):
+        tm(input_ids=None, inputs_embeds=None)
+    with pytest.raises(ValueError):
+        tm(input_ids=torch.zeros(1, 4, dtype=torch.long), inputs_embeds=torch.zeros(1, 4, 2048))
+    with pytest.raises(NotImplementedError):
+        tm(input_ids=torch.zeros(1, 4, dtype=torch.long), output_attentions=True)
+    model = M.InfiniteVLModel(_small(layers=2, vocab=64))
+    with pytest.raises(NotImplementedError):   # no vision tower attached
+        model(input_ids=torch.zeros(1, 4, dtype=torch.long), pixel_values=torch.zeros(4, 8),
+              image_grid_thw=torch.tensor([[1, 2, 2]]))
