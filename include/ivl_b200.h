@@ -168,6 +168,34 @@ IVL_API int ivl_swa_decode_fwd(const void* q, const void* k, const int64_t* k_st
                                int window, float scale, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Ring-buffer window cache for the sliding-window layers.  Replaces the O(W) roll of
+ * StaticSlidingWindowLayerPrealloc.update (std:142-173: two concatenations + two copies of the whole 8191-token
+ * window per call) and keeps the token counter in DEVICE memory, so a captured CUDA graph of a decode step or of
+ * a streamed frame replays correctly (the reference's Python counters freeze under replay).
+ *   ring_k, ring_v  bf16 [B, 2R, Hkv, 128] contiguous; token t lives in slots t % R and t % R + R, so the last
+ *                   n <= R tokens are one contiguous run.  R >= window (decode) / >= window - 1 + Tq (ivl_swa_ring_fwd).
+ *   state           int32[ivl_swa_ring_state_bytes / 4], zero-initialised by the owner: [0] = tokens appended so far.
+ * ivl_swa_ring_decode  ONE launch per layer and decoded token: appends the token's K/V (k_new, v_new: [B,1,Hkv,128]
+ *                   projection outputs, {batch, head} strides), attends over the last min(cum + 1, window) tokens,
+ *                   combines the split-KV partials and advances the counter.  q, o: bf16 [B,1,Hq,128] contiguous.
+ * ivl_swa_ring_append  appends Tq tokens ([B,Tq,Hkv,128], {batch,time,head} strides) and advances the counter.
+ * ivl_swa_ring_fwd  prefill-style attention of the Tq tokens just appended against the ring: query i of the call sees
+ *                   the keys of the last window tokens up to and including its own (same rule as ivl_swa_fwd).
+ * ---------------------------------------------------------------------------------- */
+IVL_API size_t ivl_swa_ring_workspace_bytes(int B, int Hq, int window);
+IVL_API size_t ivl_swa_ring_state_bytes(int B, int Hkv);
+IVL_API int ivl_swa_ring_append(const void* k, const int64_t* k_strides, const void* v, const int64_t* v_strides,
+                                void* ring_k, void* ring_v, int32_t* state, int B, int Tq, int Hkv, int D, int R,
+                                void* stream);
+IVL_API int ivl_swa_ring_decode(const void* q, const void* k_new, const int64_t* k_new_strides, const void* v_new,
+                                const int64_t* v_new_strides, void* ring_k, void* ring_v, int32_t* state, void* o, int B,
+                                int Hq, int Hkv, int D, int window, int R, float scale, void* workspace,
+                                size_t workspace_bytes, void* stream);
+IVL_API int ivl_swa_ring_fwd(const void* q, const int64_t* q_strides, const void* ring_k, const void* ring_v,
+                             const int32_t* state, void* o, const int64_t* o_strides, int B, int Tq, int Hq, int Hkv,
+                             int D, int window, int R, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Element-wise pieces of the two mixers (each one coalesced streaming launch).
  * ---------------------------------------------------------------------------------- */
 

@@ -39,6 +39,11 @@ SIGNATURES = {
     "ivl_swa_fwd": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, c_void_p]),
     "ivl_swa_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ivl_swa_decode_fwd": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
+    "ivl_swa_ring_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ivl_swa_ring_state_bytes": (c_size_t, [c_int, c_int]),
+    "ivl_swa_ring_append": (c_int, [c_void_p] * 7 + [c_int] * 5 + [c_void_p]),
+    "ivl_swa_ring_decode": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
+    "ivl_swa_ring_fwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_void_p]),
     "ivl_short_conv_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "ivl_gdn_gate_fwd": (c_int, [c_void_p] * 6 + [ctypes.c_int64, c_int, c_void_p]),
     "ivl_rmsnorm_gated_fwd": (c_int, [c_void_p] * 4 + [ctypes.c_int64, c_int, c_float, c_void_p]),

@@ -33,7 +33,14 @@ cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, co
                                  float scale, int l2norm, cudaStream_t stream);
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
-                           int window, float scale, cudaStream_t stream);
+                           int window, float scale, const int* ring_state, int ring_R, cudaStream_t stream);
+size_t swa_ring_decode_workspace_bytes(int B, int Hq, int window);
+cudaError_t launch_swa_ring_decode(const void* q, const void* knew, long long kn_sb, long long kn_sh, const void* vnew,
+                                   long long vn_sb, long long vn_sh, void* ring_k, void* ring_v, int* state,
+                                   void* workspace, void* o, int B, int Hq, int Hkv, int R, int window, float scale,
+                                   cudaStream_t stream);
+cudaError_t launch_swa_ring_append(const void* k, const long long* ks, const void* v, const long long* vs, void* ring_k,
+                                   void* ring_v, int* state, int B, int Tq, int Hkv, int R, cudaStream_t stream);
 cudaError_t launch_short_conv(const void* x, const void* w, const void* cache_in, void* y, void* cache_out, int B,
                               int T, int D, int act, cudaStream_t stream);
 cudaError_t launch_gdn_gate(const void* a, const void* b, const float* A_log, const float* dt_bias, float* g,
@@ -421,7 +428,74 @@ int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const in
     return IVL_ERR_BAD_SHAPE;
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
   IVL_ARCH();
-  cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, B, Tq, Tk, Hq, Hkv, window, sc,
+  cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, B, Tq, Tk, Hq, Hkv, window, sc, nullptr, 0,
+                                      static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+// ---- ring-buffer window cache -------------------------------------------------------------------------------
+size_t ivl_swa_ring_workspace_bytes(int B, int Hq, int window) {
+  if (B <= 0 || Hq <= 0 || window <= 0) return 0;
+  return ivl::swa_ring_decode_workspace_bytes(B, Hq, window);
+}
+
+size_t ivl_swa_ring_state_bytes(int B, int Hkv) {
+  if (B <= 0 || Hkv <= 0) return 0;
+  return (size_t)(2 + B * Hkv) * sizeof(int32_t);
+}
+
+static inline int check_ring(int B, int Hq, int Hkv, int D, int window, int R) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || Hq / Hkv > 8 || D != 128 || B > 65535) return IVL_ERR_BAD_SHAPE;
+  if (window <= 0 || R < window) return IVL_ERR_BAD_SHAPE;
+  return IVL_OK;
+}
+
+int ivl_swa_ring_append(const void* k, const int64_t* k_strides, const void* v, const int64_t* v_strides, void* ring_k,
+                        void* ring_v, int32_t* state, int B, int Tq, int Hkv, int D, int R, void* stream) {
+  if (B <= 0 || Tq <= 0 || Hkv <= 0 || D != 128 || R <= 0) return IVL_ERR_BAD_SHAPE;
+  if (!k || !v || !k_strides || !v_strides || !ring_k || !ring_v || !state) return IVL_ERR_NULL;
+  long long ks[3], vs[3];
+  for (int i = 0; i < 3; ++i) {
+    ks[i] = k_strides[i]; vs[i] = v_strides[i];
+    if ((ks[i] | vs[i]) & 7) return IVL_ERR_BAD_SHAPE;
+  }
+  IVL_ARCH();
+  IVL_CUDA(ivl::launch_swa_ring_append(k, ks, v, vs, ring_k, ring_v, state, B, Tq, Hkv, R, static_cast<cudaStream_t>(stream)));
+  return IVL_OK;
+}
+
+int ivl_swa_ring_decode(const void* q, const void* k_new, const int64_t* k_new_strides, const void* v_new,
+                        const int64_t* v_new_strides, void* ring_k, void* ring_v, int32_t* state, void* o, int B, int Hq,
+                        int Hkv, int D, int window, int R, float scale, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  if (int e = check_ring(B, Hq, Hkv, D, window, R)) return e;
+  if (!q || !k_new || !v_new || !k_new_strides || !v_new_strides || !ring_k || !ring_v || !state || !o || !workspace)
+    return IVL_ERR_NULL;
+  if (workspace_bytes < ivl::swa_ring_decode_workspace_bytes(B, Hq, window)) return IVL_ERR_WORKSPACE;
+  if ((k_new_strides[0] | k_new_strides[1] | v_new_strides[0] | v_new_strides[1]) & 7) return IVL_ERR_BAD_SHAPE;
+  IVL_ARCH();
+  const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  IVL_CUDA(ivl::launch_swa_ring_decode(q, k_new, k_new_strides[0], k_new_strides[1], v_new, v_new_strides[0],
+                                       v_new_strides[1], ring_k, ring_v, state, workspace, o, B, Hq, Hkv, R, window, sc,
+                                       static_cast<cudaStream_t>(stream)));
+  return IVL_OK;
+}
+
+int ivl_swa_ring_fwd(const void* q, const int64_t* q_strides, const void* ring_k, const void* ring_v,
+                     const int32_t* state, void* o, const int64_t* o_strides, int B, int Tq, int Hq, int Hkv, int D,
+                     int window, int R, float scale, void* stream) {
+  if (int e = check_ring(B, Hq, Hkv, D, window, R)) return e;
+  if (Tq <= 0 || (Tq + 127) / 128 > 65535 || R < window - 1 + Tq) return IVL_ERR_BAD_SHAPE;
+  if (!q || !q_strides || !ring_k || !ring_v || !state || !o || !o_strides) return IVL_ERR_NULL;
+  long long qs[3], os[3];
+  for (int i = 0; i < 3; ++i) {
+    qs[i] = q_strides[i]; os[i] = o_strides[i];
+    if ((qs[i] | os[i]) & 7) return IVL_ERR_BAD_SHAPE;
+  }
+  const long long rs[3] = {2ll * R * Hkv * D, (long long)Hkv * D, (long long)D};
+  IVL_ARCH();
+  const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  cudaError_t e = ivl::launch_swa_fwd(q, qs, ring_k, rs, ring_v, rs, o, os, B, Tq, 2 * R, Hq, Hkv, window, sc, state, R,
                                       static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }

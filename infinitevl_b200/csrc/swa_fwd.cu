@@ -62,6 +62,11 @@ struct SwaArgs {
   int Tq, Tk, Hq, group;       // group = Hq / Hkv
   int window;                  // 0 = none
   float scale_log2;            // softmax scale * log2(e)
+  // ring-buffer window cache (swa_misc.cu): K / V maps cover the physical ring [B, 2R, Hkv, D]; the number of cached
+  // tokens is read from DEVICE memory (after the append of this call's tokens), so a CUDA-graph replay follows the
+  // stream: Tk = min(cum, W - 1 + Tq), the keys start at ring slot (cum - Tk) % R
+  const int* ring_state;       // nullptr: plain [B, Tk, Hkv, D] keys
+  int ring_R, ring_W;
 };
 
 // 2^x for a pair of values on the FMA pipe instead of the XU pipe (two MUFU.EX2): Cody-Waite range reduction
@@ -97,6 +102,13 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int h = blockIdx.x, mt = blockIdx.y, b = blockIdx.z;
   const int hk = h / a.group;
   const int i0 = mt * BM;
+  int koff = 0;
+  if (a.ring_state != nullptr) {
+    const int cum = *reinterpret_cast<const volatile int*>(a.ring_state);
+    a.Tk = min(cum, a.ring_W - 1 + a.Tq);
+    koff = (cum - a.Tk) % a.ring_R;
+    a.window = a.Tk > a.ring_W ? a.ring_W : 0;             // the window rule of the HF glue, evaluated on the device
+  }
   const int shift = a.Tk - a.Tq;                           // bottom-right alignment
   const int p_first = i0 + shift;
   const int p_last = min(i0 + BM - 1, a.Tq - 1) + shift;
@@ -132,8 +144,8 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int j0 = (t_lo + t) * BN;
       uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullK[s], KT_BYTES_);
-      tma_load_4d_ws(kd, &tmK, 0, hk, j0, b, &bars.fullK[s]);
-      tma_load_4d_ws(kd + KT_BYTES_ / 2, &tmK, 64, hk, j0, b, &bars.fullK[s]);
+      tma_load_4d_ws(kd, &tmK, 0, hk, koff + j0, b, &bars.fullK[s]);
+      tma_load_4d_ws(kd + KT_BYTES_ / 2, &tmK, 64, hk, koff + j0, b, &bars.fullK[s]);
     };
     auto load_v = [&](int t) {
       const int s = t & 1;
@@ -141,8 +153,8 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int j0 = (t_lo + t) * BN;
       uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullV[s], KT_BYTES_);
-      tma_load_4d_ws(vd, &tmV, 0, hk, j0, b, &bars.fullV[s]);
-      tma_load_4d_ws(vd + KT_BYTES_ / 2, &tmV, 64, hk, j0, b, &bars.fullV[s]);
+      tma_load_4d_ws(vd, &tmV, 0, hk, koff + j0, b, &bars.fullV[s]);
+      tma_load_4d_ws(vd + KT_BYTES_ / 2, &tmV, 64, hk, koff + j0, b, &bars.fullV[s]);
     };
     load_k(0);
     for (int t = 1; t < n_tiles; ++t) {
@@ -348,9 +360,11 @@ bool make_map(CUtensorMap* m, const void* ptr, int B, int T, int Hn, long long s
 }  // namespace
 
 // q [B,Tq,Hq,128], k/v [B,Tk,Hkv,128], o [B,Tq,Hq,128]; strides in elements (batch, time, head).
+// ring_state != nullptr: k, v are the physical rings [B, Tk = 2R, Hkv, 128] of a ring-buffer window cache and the
+// visible keys are derived on the device (SwaArgs::ring_state); window must be > 0.
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
-                           int window, float scale, cudaStream_t stream) {
+                           int window, float scale, const int* ring_state, int ring_R, cudaStream_t stream) {
   // IVL_SWA_POLY (developer knob): pairs out of 8 whose exponentials run on the FMA pipe
   int poly = SWA_POLY_DEFAULT;
   if (const char* e = getenv("IVL_SWA_POLY")) poly = atoi(e);
@@ -378,6 +392,7 @@ cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, co
   a.o_sb = os[0]; a.o_st = os[1]; a.o_sh = os[2];
   a.Tq = Tq; a.Tk = Tk; a.Hq = Hq; a.group = Hq / Hkv;
   a.window = (window > 0 && Tk > window) ? window : 0;  // HF glue passes the window only when key_len > W
+  a.ring_state = ring_state; a.ring_R = ring_R; a.ring_W = window;
   a.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(Hq, (Tq + BM - 1) / BM, B);
   kern<<<grid, SWA_THREADS, SWA_SMEM, stream>>>(tq, tk, tv, a);

@@ -93,26 +93,25 @@ __device__ __forceinline__ void dec_mma16816(float* c, const uint32_t* a, uint32
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(128)
-swa_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, long long k_sb,
-                          long long k_st, long long k_sh, const __nv_bfloat16* __restrict__ v, long long v_sb,
-                          long long v_st, long long v_sh, float* __restrict__ part, int Tk, int Hq, int group,
-                          int first_key, float scale_log2) {
-  extern __shared__ __align__(16) uint8_t dsm[];
-  DecSmem& s = *reinterpret_cast<DecSmem*>(dsm);
+// One 128-key slice of the split-KV decode attention for the `group` q-heads of kv-head hk: stages the slice
+// (rows(r, &kg, &vg) yields the global K / V row of slice row r), computes scores, probabilities and the partial
+// output and writes the record [m, l, o[128]] of (b, q-head, split).  nk = valid rows of the slice (<= 0: none).
+template <class Rows>
+__device__ __forceinline__ void dec_partial_body(DecSmem& s, const __nv_bfloat16* __restrict__ q, Rows rows,
+                                                 float* __restrict__ part, int nk, int Hq, int group, int split,
+                                                 int nsplit, int hk, int b, float scale_log2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;   // mma fragment coordinates: row (= q-head) and column pair
-  const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z, nsplit = gridDim.x;
-  const int j0 = first_key + split * DEC_KEYS;
-  const int nk = min(DEC_KEYS, Tk - j0);
   // stage the K and V slices (16-byte async copies, rows past the end zeroed) and the group's queries
   for (int i = tid; i < DEC_KEYS * 16; i += 128) {
     const int r = i >> 4, c = i & 15;
     __nv_bfloat16* kd = s.k + r * DEC_LD + c * 8;
     __nv_bfloat16* vd = s.v + r * DEC_LD + c * 8;
     if (r < nk) {
-      const __nv_bfloat16* kg = k + b * k_sb + (long long)(j0 + r) * k_st + hk * k_sh + c * 8;
-      const __nv_bfloat16* vg = v + b * v_sb + (long long)(j0 + r) * v_st + hk * v_sh + c * 8;
+      const __nv_bfloat16 *kg, *vg;
+      rows(r, kg, vg);
+      kg += c * 8;
+      vg += c * 8;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(kd)), "l"(kg));
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(vd)), "l"(vg));
     } else {
@@ -212,20 +211,142 @@ swa_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
 }
 
 __global__ void __launch_bounds__(128)
+swa_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, long long k_sb,
+                          long long k_st, long long k_sh, const __nv_bfloat16* __restrict__ v, long long v_sb,
+                          long long v_st, long long v_sh, float* __restrict__ part, int Tk, int Hq, int group,
+                          int first_key, float scale_log2) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  DecSmem& s = *reinterpret_cast<DecSmem*>(dsm);
+  const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z, nsplit = gridDim.x;
+  const int j0 = first_key + split * DEC_KEYS;
+  const int nk = min(DEC_KEYS, Tk - j0);
+  dec_partial_body(s, q, [&](int r, const __nv_bfloat16*& kg, const __nv_bfloat16*& vg) {
+    kg = k + b * k_sb + (long long)(j0 + r) * k_st + hk * k_sh;
+    vg = v + b * v_sb + (long long)(j0 + r) * v_st + hk * v_sh;
+  }, part, nk, Hq, group, split, nsplit, hk, b, scale_log2);
+}
+
+// log-sum-exp combine of the partial records of one (b, q-head); thread tid owns head dim tid
+__device__ __forceinline__ void dec_combine(const float* rec, __nv_bfloat16* o_row, int nsplit, int tid) {
+  float M = -INFINITY;
+  for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(rec + sp * 130));
+  float L = 0.f, acc = 0.f;
+  for (int sp = 0; sp < nsplit; ++sp) {
+    const float m = __ldcg(rec + sp * 130);
+    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
+    L = fmaf(w, __ldcg(rec + sp * 130 + 1), L);
+    acc = fmaf(w, __ldcg(rec + sp * 130 + 2 + tid), acc);
+  }
+  o_row[tid] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ring-buffer window cache (replaces the O(W) roll of
+// StaticSlidingWindowLayerPrealloc.update, std:142-173).  Storage [B, 2R, Hkv, 128]: token t lives in slot t % R AND
+// in slot t % R + R, so the last n <= R tokens are always one contiguous run starting at ((cum - n) % R).  The
+// token counter lives in DEVICE memory (state[0]), so a captured CUDA graph replays correctly -- the reference
+// keeps it in Python integers, which a replay cannot advance.
+//   state (int32): [0] tokens appended so far, [1] blocks-done counter of the running launch,
+//                  [2 + b * Hkv + hk] slice-done counters of the decode kernel.
+// ---------------------------------------------------------------------------------------------
+
+// Decode step in ONE launch: append the new token's K/V to the ring, attend over the last min(cum + 1, W) tokens
+// (split-KV partials), combine (the last slice block of a (b, kv-head) to finish) and advance the counter (the
+// last block of the launch).  knew / vnew: [B, 1, Hkv, 128] projection outputs with (batch, head) strides.
+__global__ void __launch_bounds__(128)
+swa_ring_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ knew, long long kn_sb,
+                       long long kn_sh, const __nv_bfloat16* __restrict__ vnew, long long vn_sb, long long vn_sh,
+                       __nv_bfloat16* __restrict__ ring_k, __nv_bfloat16* __restrict__ ring_v, int* __restrict__ state,
+                       float* __restrict__ part, __nv_bfloat16* __restrict__ o, int Hq, int Hkv, int group, int R, int W,
+                       float scale_log2) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  DecSmem& s = *reinterpret_cast<DecSmem*>(dsm);
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z, nsplit = gridDim.x;
+  const int cum = *reinterpret_cast<volatile int*>(state);      // tokens in the ring before this step
+  const int n = min(cum + 1, W);                                 // window incl. the new token
+  const int base_tok = cum + 1 - n;                              // oldest visible token
+  const int phys0 = base_tok % R;
+  const int j0 = split * DEC_KEYS;
+  const int nk = min(DEC_KEYS, n - j0);
+  const long long t_st = (long long)Hkv * 128, b_st = 2ll * R * t_st;
+  __nv_bfloat16* rk = ring_k + b * b_st + hk * 128;
+  __nv_bfloat16* rv = ring_v + b * b_st + hk * 128;
+  const __nv_bfloat16* kn = knew + b * kn_sb + hk * kn_sh;
+  const __nv_bfloat16* vn = vnew + b * vn_sb + hk * vn_sh;
+  if (nk > 0 && j0 + nk == n && tid < 32) {
+    // this slice ends with the new token: store it into both of its ring slots for the steps to come
+    const int slot = cum % R, c = tid & 15;
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>((tid < 16 ? kn : vn) + c * 8));
+    __nv_bfloat16* dst = (tid < 16 ? rk : rv) + c * 8;
+    *reinterpret_cast<uint4*>(dst + slot * t_st) = val;
+    *reinterpret_cast<uint4*>(dst + (slot + R) * t_st) = val;
+  }
+  dec_partial_body(s, q, [&](int r, const __nv_bfloat16*& kg, const __nv_bfloat16*& vg) {
+    if (j0 + r == n - 1) { kg = kn; vg = vn; }                  // the new token comes from the projection output
+    else { kg = rk + (long long)(phys0 + j0 + r) * t_st; vg = rv + (long long)(phys0 + j0 + r) * t_st; }
+  }, part, nk, Hq, group, split, nsplit, hk, b, scale_log2);
+  // ---- last slice block of this (b, kv-head): combine; last block of the launch: advance the counter ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(state + 2 + b * Hkv + hk, 1) == nsplit - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int gh = 0; gh < group; ++gh) {
+    const long long bh = (long long)b * Hq + hk * group + gh;
+    dec_combine(part + bh * nsplit * 130, o + bh * 128, nsplit, tid);
+  }
+  if (tid == 0) {
+    state[2 + b * Hkv + hk] = 0;                                 // ready for the next launch / graph replay
+    if (atomicAdd(state + 1, 1) == (int)(gridDim.y * gridDim.z) - 1) {
+      state[1] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile int*>(state) = cum + 1;
+    }
+  }
+}
+
+// Append Tq new tokens (k, v: [B, Tq, Hkv, 128] with (batch, time, head) strides) to the ring; the last block to
+// finish advances the counter.  Tokens older than the last R of the append are skipped.
+__global__ void __launch_bounds__(256)
+swa_ring_append_kernel(const __nv_bfloat16* __restrict__ k, long long k_sb, long long k_st, long long k_sh,
+                       const __nv_bfloat16* __restrict__ v, long long v_sb, long long v_st, long long v_sh,
+                       __nv_bfloat16* __restrict__ ring_k, __nv_bfloat16* __restrict__ ring_v, int* __restrict__ state,
+                       int B, int Tq, int Hkv, int R) {
+  const int cum = *reinterpret_cast<volatile int*>(state);
+  const long long total = (long long)B * Tq * Hkv * 16;
+  const long long t_st = (long long)Hkv * 128, b_st = 2ll * R * t_st;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 15);
+    const int hk = (int)((i >> 4) % Hkv);
+    const int t = (int)((i >> 4) / Hkv % Tq);
+    const int b = (int)((i >> 4) / Hkv / Tq);
+    if (t < Tq - R) continue;
+    const int slot = (int)(((long long)cum + t) % R);
+    const uint4 kv = __ldg(reinterpret_cast<const uint4*>(k + b * k_sb + (long long)t * k_st + hk * k_sh + c * 8));
+    const uint4 vv = __ldg(reinterpret_cast<const uint4*>(v + b * v_sb + (long long)t * v_st + hk * v_sh + c * 8));
+    __nv_bfloat16* dk = ring_k + b * b_st + hk * 128 + c * 8;
+    __nv_bfloat16* dv = ring_v + b * b_st + hk * 128 + c * 8;
+    *reinterpret_cast<uint4*>(dk + slot * t_st) = kv;
+    *reinterpret_cast<uint4*>(dk + (slot + R) * t_st) = kv;
+    *reinterpret_cast<uint4*>(dv + slot * t_st) = vv;
+    *reinterpret_cast<uint4*>(dv + (slot + R) * t_st) = vv;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
+    state[1] = 0;
+    __threadfence();
+    *reinterpret_cast<volatile int*>(state) = cum + Tq;
+  }
+}
+
+__global__ void __launch_bounds__(128)
 swa_decode_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ o, int nsplit) {
   const long long bh = blockIdx.x;  // b * Hq + h
-  const int tid = threadIdx.x;
-  const float* rec = part + bh * nsplit * 130;
-  float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, rec[s * 130]);
-  float L = 0.f, acc = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float m = rec[s * 130];
-    const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
-    L = fmaf(w, rec[s * 130 + 1], L);
-    acc = fmaf(w, rec[s * 130 + 2 + tid], acc);
-  }
-  o[bh * 128 + tid] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
+  dec_combine(part + bh * nsplit * 130, o + bh * 128, nsplit, threadIdx.x);
 }
 
 }  // namespace
@@ -261,6 +382,51 @@ cudaError_t launch_swa_decode(const void* q, const void* k, const long long* ks,
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   swa_decode_combine_kernel<<<B * Hq, 128, 0, stream>>>(part, static_cast<__nv_bfloat16*>(o), nsplit);
+  return cudaGetLastError();
+}
+
+static cudaError_t configure_decode_kernels() {
+  static std::atomic<bool> configured_dev[64];
+  int dev_ = 0;
+  if (cudaError_t e = cudaGetDevice(&dev_)) return e;
+  if (dev_ < 0 || dev_ >= 64) return cudaErrorInvalidDevice;
+  if (!configured_dev[dev_].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(swa_ring_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(DecSmem));
+    if (e != cudaSuccess) return e;
+    configured_dev[dev_].store(true, std::memory_order_release);
+  }
+  return cudaSuccess;
+}
+
+size_t swa_ring_decode_workspace_bytes(int B, int Hq, int window) {
+  const int nsplit = (window + DEC_KEYS - 1) / DEC_KEYS;
+  return (size_t)B * Hq * nsplit * 130 * sizeof(float);
+}
+
+cudaError_t launch_swa_ring_decode(const void* q, const void* knew, long long kn_sb, long long kn_sh, const void* vnew,
+                                   long long vn_sb, long long vn_sh, void* ring_k, void* ring_v, int* state,
+                                   void* workspace, void* o, int B, int Hq, int Hkv, int R, int window, float scale,
+                                   cudaStream_t stream) {
+  if (cudaError_t e = configure_decode_kernels()) return e;
+  const int nsplit = (window + DEC_KEYS - 1) / DEC_KEYS;
+  dim3 grid(nsplit, Hkv, B);
+  swa_ring_decode_kernel<<<grid, 128, (int)sizeof(DecSmem), stream>>>(
+      static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(knew), kn_sb, kn_sh,
+      static_cast<const __nv_bfloat16*>(vnew), vn_sb, vn_sh, static_cast<__nv_bfloat16*>(ring_k),
+      static_cast<__nv_bfloat16*>(ring_v), state, static_cast<float*>(workspace), static_cast<__nv_bfloat16*>(o), Hq, Hkv,
+      Hq / Hkv, R, window, scale * 1.4426950408889634f);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_swa_ring_append(const void* k, const long long* ks, const void* v, const long long* vs, void* ring_k,
+                                   void* ring_v, int* state, int B, int Tq, int Hkv, int R, cudaStream_t stream) {
+  const long long total = (long long)B * Tq * Hkv * 16;
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  swa_ring_append_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(k), ks[0], ks[1], ks[2],
+                                                     static_cast<const __nv_bfloat16*>(v), vs[0], vs[1], vs[2],
+                                                     static_cast<__nv_bfloat16*>(ring_k),
+                                                     static_cast<__nv_bfloat16*>(ring_v), state, B, Tq, Hkv, R);
   return cudaGetLastError();
 }
 

@@ -351,14 +351,22 @@ class InfiniteVLSelfAttention(nn.Module):
         mrope_apply_(q, cos, sin)
         mrope_apply_(k, cos, sin)
         key_states, value_states = k.transpose(1, 2), v.transpose(1, 2)  # [B,H,T,D] views, as the cache expects
+        layer = past_key_values.layers[self.layer_idx] if past_key_values is not None else None
+        if attention_mask is not None and attention_mask.dim() != 2:
+            attention_mask = None   # 4-D additive masks are an eager/SDPA concept; the FA2 path builds none
+        if layer is not None and getattr(layer, "is_ring", False) and q.is_cuda:
+            # ring-buffer window cache: append + attention without concatenating or rolling the window
+            if attention_mask is not None and not bool(attention_mask.all()):
+                raise NotImplementedError("padded batches are not supported by the B200 SWA kernel")
+            out = layer.attend(q, k, v, self.scaling, self.sliding_window)
+            out = self.o_proj(out.reshape(B, q_len, self.num_heads * self.head_dim))
+            return out, None
         if past_key_values is not None:
             key_states, value_states = past_key_values.update(
                 layer_idx=self.layer_idx, key_states=key_states, value_states=value_states, conv_state=None,
                 recurrent_state=None, cache_kwargs={"sin": sin, "cos": cos, "cache_position": cache_position})
         # crop a 2-D padding mask to the visible keys exactly as the reference does before FA2 (std:1080-1090);
         # the operator then refuses masks that really pad (it has no unpad path)
-        if attention_mask is not None and attention_mask.dim() != 2:
-            attention_mask = None   # 4-D additive masks are an eager/SDPA concept; the FA2 path builds none
         if past_key_values is not None and self.sliding_window is not None and attention_mask is not None:
             kv_len, kv_offset = past_key_values.layers[self.layer_idx].get_mask_sizes(cache_position)
             attention_mask = None if kv_offset != 0 else attention_mask[:, kv_offset:kv_offset + kv_len]
@@ -472,10 +480,10 @@ class HybridDecoder(nn.Module):
         self.rotary_emb = InfiniteVLRotaryEmbedding(config=config)
         self.mixers_only = mixers_only
 
-    def allocate_inference_cache(self, batch_size: int, device=None, dtype=None, state_dtype=None):
+    def allocate_inference_cache(self, batch_size: int, device=None, dtype=None, state_dtype=None, **kw):
         p = next(self.parameters())
         return StaticCachePrealloc(config=self.config, batch_size=batch_size, device=device or p.device,
-                                   dtype=dtype or p.dtype, state_dtype=state_dtype)
+                                   dtype=dtype or p.dtype, state_dtype=state_dtype, **kw)
 
     @torch.no_grad()
     def forward(self, inputs_embeds, position_ids=None, past_key_values=None, cache_position=None, use_cache=None):

@@ -138,3 +138,51 @@ def test_demo_import_alias_resolves_to_the_b200_caches():
     finally:
         sys.path.remove(compat)
         sys.modules.pop("modeling_qwen2_5_vl", None)
+
+
+def test_ring_layer_equals_reference_layer_on_the_reference_trace():
+    """RingSlidingWindowLayer against the reference-semantics layer on the trace the golden fixture
+    was made with: same returned [tail ; new] tensors, same `keys` / `_buf_keys` views, same integers -- and it is an
+    HF Cache layer like the reference's classes."""
+    import torch
+    from infinitevl_b200.cache import RingSlidingWindowLayer, StaticCachePrealloc, StaticSlidingWindowLayerPrealloc
+    from infinitevl_b200.modeling import HybridTextConfig
+    cfg = HybridTextConfig(num_hidden_layers=4, sliding_window=8, num_key_value_heads=1, num_attention_heads=2, hidden_size=8)
+    cfg.head_dim = 4
+    mk = lambda ring: StaticSlidingWindowLayerPrealloc(config=cfg, batch_size=1, dtype=torch.float32, zero_init=True,
+                                                      ring=ring, max_append=4)
+    ref, rng = mk(False), mk(True)
+    assert isinstance(rng, RingSlidingWindowLayer) and not isinstance(ref, RingSlidingWindowLayer) and rng.R == 11
+    base = 0
+    for n in [3, 1, 1, 5, 1, 9, 2, 1, 1, 20, 1]:
+        kk = torch.arange(base, base + n, dtype=torch.float32)[None, None, :, None].expand(1, 1, n, 4).contiguous()
+        a, b = ref.update(kk, kk * 2), rng.update(kk, kk * 2)
+        base += n
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert (ref.size, ref.cumulative_length) == (rng.size, rng.cumulative_length)
+        assert torch.equal(ref.keys, rng.keys) and torch.equal(ref.values, rng.values)
+        assert torch.equal(ref._buf_keys[:, :, :ref.size], rng._buf_keys[:, :, :rng.size])
+        assert ref.get_mask_sizes(torch.arange(n)) == rng.get_mask_sizes(torch.arange(n))
+    assert int(rng._state[0]) == base
+    # the demo's clone protocol (demo_streaming_inference.py:111-160) on ring layers
+    dst = mk(True)
+    dst.size, dst.cumulative_length = rng.size, rng.cumulative_length
+    L = rng.size
+    dst._buf_keys[:, :, :L, :].copy_(rng._buf_keys[:, :, :L, :])
+    dst._buf_values[:, :, :L, :].copy_(rng._buf_values[:, :, :L, :])
+    dst.keys, dst.values = dst._buf_keys[:, :, :L, :], dst._buf_values[:, :, :L, :]
+    kk = torch.full((1, 1, 2, 4), 99.0)
+    a, b = rng.update(kk, kk), dst.update(kk, kk)
+    assert torch.equal(a[0], b[0]) and torch.equal(rng.keys, dst.keys) and int(dst._state[0]) == int(rng._state[0])
+    # snapshot / restore
+    again = mk(True)
+    again.load_state_dict(rng.state_dict())
+    assert torch.equal(again.keys, rng.keys) and again.cumulative_length == rng.cumulative_length
+    with pytest.raises(ValueError):
+        rng.crop(2)     # the window is full: cropping is forbidden, as in the reference
+    try:
+        from transformers.cache_utils import Cache, CacheLayerMixin
+    except Exception:  # noqa: BLE001
+        return
+    cache = StaticCachePrealloc(config=cfg, batch_size=1)
+    assert isinstance(cache, Cache) and all(isinstance(l, CacheLayerMixin) for l in cache.layers)

@@ -44,11 +44,12 @@ def _frames(n, first=300, seed=42):
     return x, cuts
 
 
-def test_eager_stream_matches_oracle(M):
+@pytest.mark.parametrize("ring", [False, True])
+def test_eager_stream_matches_oracle(M, ring):
     cfg, dec = _decoder(M)
     p = _params(dec)
     x, cuts = _frames(6)
-    cache = dec.allocate_inference_cache(1)
+    cache = dec.allocate_inference_cache(1, ring=ring)
     rcaches = [SlidingWindowCacheRef(WINDOW) if lt == "sliding_attention" else {} for lt in cfg.layer_types]
     outs, refs = [], []
     for a, b in cuts:
@@ -94,7 +95,7 @@ def test_graph_replay_of_the_decoder_forward(M):
         return dec(xs[:, a:b] if xin is None else xin, position_ids=pos, past_key_values=cache,
                    cache_position=torch.arange(a, b, device="cuda"))
 
-    caches = [dec.allocate_inference_cache(1) for _ in range(2)]   # [0]: graph, [1]: eager twin
+    caches = [dec.allocate_inference_cache(1, ring=False) for _ in range(2)]   # [0]: graph, [1]: eager twin
     for c in caches:
         for a, b in cuts[:3]:    # prompt + two frames, eagerly
             run_eager(c, a, b)
@@ -138,3 +139,66 @@ def test_graph_replay_of_the_decoder_forward(M):
             assert torch.equal(lg._buf_keys, le._buf_keys)
     assert torch.isfinite(static_out).all()
     assert mem[10] == mem[-1], "streaming must not grow memory (BASELINE.json config 3)"
+
+
+def test_ring_cache_graph_stream_equals_eager(M):
+    """Ring-buffer window cache: the token counter the kernels address by lives on the device, so
+    ONE captured forward replayed for 64 frames of 256 tokens equals eager streaming of the same frames bit for bit
+    -- the window really slides (the 1023-token window wraps the 1279-slot ring many times) -- with flat memory.
+    Then decode steps continue from the replayed cache."""
+    from infinitevl_b200 import ops
+    cfg, dec = _decoder(M)
+    n_frames = 64
+    x, cuts = _frames(n_frames + 2)
+    xs = x.cuda()
+
+    def run_eager(cache, a, b):
+        pos = torch.arange(a, b, device="cuda")[None, None].expand(3, 1, -1)
+        return dec(xs[:, a:b], position_ids=pos, past_key_values=cache, cache_position=torch.arange(a, b, device="cuda"))
+
+    caches = [dec.allocate_inference_cache(1, ring=True) for _ in range(2)]
+    assert caches[0].layers[0].is_ring and caches[0].layers[0].R == WINDOW - 1 + 256
+    for c in caches:
+        for a, b in cuts[:3]:
+            run_eager(c, a, b)
+    static_x = torch.empty(1, FRAME, 2048, dtype=torch.bfloat16, device="cuda")
+    static_pos = torch.empty(3, 1, FRAME, dtype=torch.long, device="cuda")
+    static_cp = torch.empty(FRAME, dtype=torch.long, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    snap = caches[0].layers[0]._state.clone()
+    with torch.cuda.stream(side):
+        ops.gdn_workspace(1, FRAME, cfg.num_linear_heads, "cuda")
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            static_out = dec(static_x, position_ids=static_pos, past_key_values=caches[0], cache_position=static_cp)
+    torch.cuda.current_stream().wait_stream(side)
+    assert torch.equal(caches[0].layers[0]._state, snap)   # capturing ran no kernel: the device counter did not move
+    mem = []
+    for i, (a, b) in enumerate(cuts[3:3 + n_frames]):
+        static_x.copy_(xs[:, a:b]); static_cp.copy_(torch.arange(a, b, device="cuda"))
+        static_pos.copy_(static_cp[None, None].expand(3, 1, -1))
+        graph.replay()
+        got = static_out.clone()
+        want = run_eager(caches[1], a, b)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), f"frame {i}"
+        mem.append(torch.cuda.memory_allocated())
+    assert mem[10] == mem[-1], "streaming must not grow memory (BASELINE.json config 3)"
+    caches[0].sync_from_device()
+    for lg, le in zip(caches[0].layers, caches[1].layers):
+        if lg.is_sliding:
+            assert (lg.size, lg.cumulative_length) == (le.size, le.cumulative_length) == (WINDOW - 1, cuts[2 + n_frames][1])
+            assert torch.equal(lg.keys, le.keys) and torch.equal(lg.values, le.values)
+        else:
+            assert torch.equal(lg.recurrent_state, le.recurrent_state)
+    # decode continues from the replayed cache exactly as from the eager one
+    T0 = cuts[2 + n_frames][1]
+    tok = torch.randn(1, 8, 2048, generator=gen(77)).bfloat16().cuda()
+    for j in range(8):
+        outs = []
+        for c in caches:
+            pos = torch.full((3, 1, 1), T0 + j, device="cuda")
+            outs.append(dec(tok[:, j:j + 1], position_ids=pos, past_key_values=c,
+                            cache_position=torch.tensor([T0 + j], device="cuda")))
+        assert torch.equal(outs[0], outs[1]), j

@@ -101,3 +101,36 @@ def test_swa_window_property_at_full_size(swa):
     ref = swa_attention_ref(q[:, :, T - 64:].cpu(), k[:, :, T - 64 - (W - 1):].cpu(), v[:, :, T - 64 - (W - 1):].cpu(),
                             window=W)
     assert err_ratio(ref, full[:, T - 64:].float().cpu()) < 5e-3
+
+
+@pytest.mark.parametrize("B,window,max_append", [(1, 512, 256), (2, 8192, 256), (1, 96, 32)])
+def test_ring_cache_attention_matches_oracle(swa, B, window, max_append):
+    """Ring-buffer window cache (ivl_swa_ring_append / ivl_swa_ring_fwd / ivl_swa_ring_decode): a
+    stream of appends of mixed lengths -- long prefill chunks (general path), frames (append + attention over the
+    ring) and single tokens (the one-launch decode step) -- against the oracle attending over the true window."""
+    from infinitevl_b200.cache import StaticSlidingWindowLayerPrealloc
+    from infinitevl_b200.modeling import HybridTextConfig
+    cfg = HybridTextConfig(num_hidden_layers=4, sliding_window=window)
+    layer = StaticSlidingWindowLayerPrealloc(config=cfg, batch_size=B, device="cuda", dtype=torch.bfloat16,
+                                             max_append=max_append)
+    assert layer.is_ring
+    steps = [max_append + 40, 1, 1, max_append, 7, 1, max_append, max_append, 1, 1, 1, max_append // 2, 1]
+    if window > 1000:
+        steps = [5000, 3000, 256, 1, 1, 256, 200, 1, 1, 1]      # crosses the 8191-token capacity and wraps the ring
+    T = sum(steps)
+    q, k, v = _qkv(B, 16, 2, T, T, seed=window + B)
+    pos = 0
+    worst = 0.0
+    for n in steps:
+        qs, ks, vs = (x[:, :, pos:pos + n].transpose(1, 2).contiguous().cuda() for x in (q, k, v))   # [B, n, H, D]
+        out = layer.attend(qs, ks, vs, 128 ** -0.5, window)
+        lo = max(0, pos - (window - 1))
+        ref = swa_attention_ref(q[:, :, pos:pos + n], k[:, :, lo:pos + n], v[:, :, lo:pos + n], window=window)
+        worst = max(worst, err_ratio(ref, out.float().cpu()))
+        pos += n
+        assert layer.cumulative_length == pos and layer.size == min(pos, window - 1)
+    assert worst < 5e-3
+    layer.sync_from_device()
+    assert layer.cumulative_length == T
+    lo = T - layer.size
+    assert torch.equal(layer.keys.cpu(), k[:, :, lo:T]) and torch.equal(layer.values.cpu(), v[:, :, lo:T])
