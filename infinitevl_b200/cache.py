@@ -170,9 +170,10 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
         self.max_append = max(int(max_append), 1)
         self.R = self.capacity + self.max_append
         shape = (self.batch_size, 2 * self.R, self.num_kv_heads, self.head_dim)
-        alloc = torch.zeros if zero_init else torch.empty
-        self._ring_k = alloc(shape, dtype=self.dtype, device=self.device)
-        self._ring_v = alloc(shape, dtype=self.dtype, device=self.device)
+        # always zero-initialised: the attention kernels fetch whole 64-key tiles of the ring, and a masked key
+        # contributes 0 * v -- which must not meet a NaN bit pattern left in never-written slots
+        self._ring_k = torch.zeros(shape, dtype=self.dtype, device=self.device)
+        self._ring_v = torch.zeros(shape, dtype=self.dtype, device=self.device)
         self._state = torch.zeros(2 + self.batch_size * self.num_kv_heads, dtype=torch.int32, device=self.device)
         self._size = 0
         self._cum = 0
