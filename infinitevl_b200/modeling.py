@@ -766,7 +766,12 @@ class InfiniteVLModel(nn.Module):
         if position_ids is None:
             prefill = (cache_position is not None and int(cache_position.reshape(-1)[0]) == 0) or \
                       (past_key_values is None or past_key_values.get_seq_length() == 0)
-            if prefill or self.rope_deltas is None:
+            if (prefill or self.rope_deltas is None) and input_ids is None and attention_mask is None:
+                # embeddings only (the reference needs input_ids here): plain text positions
+                B, T, _ = inputs_embeds.shape
+                position_ids = torch.arange(T, device=inputs_embeds.device).view(1, 1, -1).expand(3, B, -1)
+                self.rope_deltas = torch.zeros(B, 1, dtype=torch.long, device=inputs_embeds.device)
+            elif prefill or self.rope_deltas is None:
                 position_ids, rope_deltas = self.get_rope_index(input_ids, image_grid_thw, video_grid_thw,
                                                                 second_per_grid_ts=second_per_grid_ts,
                                                                 attention_mask=attention_mask)
