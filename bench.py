@@ -375,13 +375,15 @@ def run_ours(args):
     # ---- end-to-end through the public operator API with HOST buffers ---------------------------
     decode = None
     e2e = run_e2e(hp, args, world, dev)
-    gpu_ref = config2 = None
+    gpu_ref = config2 = config3 = None
     if world == 1 and hp.has_swa:
         decode = run_decode(dev, peaks)
         if not args.no_gpu_reference:
             gpu_ref = gpu_reference(hp, T, ms_step)
         if T != 32768 and not args.no_config2:
             config2 = run_config2(dev, peaks)
+        if not args.no_config3:
+            config3 = run_config3(dev, peaks, n_frames=args.stream_frames)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -399,7 +401,7 @@ def run_ours(args):
                        "parallelism": f"sequence-chunk x{world}" if world > 1 else "single GPU",
                        "l2": "inputs (>3 GB per layer) exceed the 126 MB L2; no flush needed"},
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "decode": decode,
-            "gpu_reference": gpu_ref, "config2_32k": config2, "dist": dist_info,
+            "gpu_reference": gpu_ref, "config2_32k": config2, "config3_stream": config3, "dist": dist_info,
             "gpu_launches": hp.launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -531,6 +533,89 @@ def run_sweep(args):
         dist.destroy_process_group()
 
 
+def run_config3(dev, peaks, n_frames=2048, frame=256, decode_steps=256):
+    """BASELINE.json config 3: stream n_frames x 256-token frames (= 524 288 tokens) through the
+    36-layer decoder stack with the inference cache -- ONE captured CUDA graph replayed per frame, as
+    inference_examples/demo_streaming_inference.py:453-489 does -- assert that memory stays flat, then time
+    single-token decode steps under a graph from the state the stream left: (i) token mixers only (the hot path with
+    its projections), (ii) the whole decoder (norms + MLPs too).  Random-init weights of the 3B shapes."""
+    from infinitevl_b200 import modeling, ops
+    res = {"frames": n_frames, "frame_tokens": frame, "context_tokens": n_frames * frame}
+    for name, mixers_only in (("mixers_only", True), ("whole_decoder", False)):
+        torch.manual_seed(0)
+        cfg = modeling.HybridTextConfig()
+        dec = modeling.HybridDecoder(cfg, mixers_only=mixers_only)
+        for p_ in dec.parameters():
+            if p_.dim() >= 2:
+                torch.nn.init.normal_(p_, std=0.02)
+        dec = dec.to(dev, torch.bfloat16).eval()
+        cache = dec.allocate_inference_cache(1)
+        gen = torch.Generator().manual_seed(3)
+        x = torch.randn(1, frame, cfg.hidden_size, generator=gen).bfloat16().to(dev)
+        sx = x.clone()
+        spos = torch.zeros(3, 1, frame, dtype=torch.long, device=dev)
+        scp = torch.zeros(frame, dtype=torch.long, device=dev)
+        ar = torch.arange(frame, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.gdn_workspace(1, frame, cfg.num_linear_heads, dev)
+            for i in range(2):      # eager warm-up frames (also start every cache layer)
+                scp.copy_(ar + i * frame); spos.copy_(scp[None, None].expand(3, 1, -1))
+                dec(sx, position_ids=spos, past_key_values=cache, cache_position=scp)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                out = dec(sx, position_ids=spos, past_key_values=cache, cache_position=scp)
+        torch.cuda.current_stream().wait_stream(side)
+        mem10 = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(2, n_frames):
+            if i == 12:
+                torch.cuda.synchronize()
+                mem10 = torch.cuda.memory_allocated()
+                e0.record()
+            scp.copy_(ar + i * frame); spos.copy_(scp[None, None].expand(3, 1, -1))
+            sx.copy_(x)
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        frame_ms = e0.elapsed_time(e1) / (n_frames - 12)
+        flat = torch.cuda.memory_allocated() == mem10
+        assert flat, "streaming grew device memory"
+        assert torch.isfinite(out).all()
+        # ---- decode steps from the streamed state
+        tok = torch.randn(1, 1, cfg.hidden_size, generator=gen).bfloat16().to(dev)
+        dpos = torch.zeros(3, 1, 1, dtype=torch.long, device=dev)
+        dcp = torch.zeros(1, dtype=torch.long, device=dev)
+        T0 = n_frames * frame
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(2):
+                dcp.fill_(T0 + i); dpos.fill_(T0 + i)
+                dec(tok, position_ids=dpos, past_key_values=cache, cache_position=dcp)
+            gd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gd, stream=side):
+                dout = dec(tok, position_ids=dpos, past_key_values=cache, cache_position=dcp)
+        torch.cuda.current_stream().wait_stream(side)
+        ts = []
+        for i in range(decode_steps):
+            dcp.fill_(T0 + 2 + i); dpos.fill_(T0 + 2 + i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); gd.replay(); b.record()
+            ts.append((a, b))
+        torch.cuda.synchronize()
+        tt = sorted(a.elapsed_time(b) for a, b in ts)
+        assert torch.isfinite(dout).all()
+        res[name] = {"frame_ms": round(frame_ms, 4), "frame_tokens_per_s": round(frame / (frame_ms * 1e-3), 1),
+                     "decode_step_ms_median": round(tt[len(tt) // 2], 4), "memory_flat": bool(flat),
+                     "memory_allocated_mb": round(torch.cuda.memory_allocated() / 2**20, 1)}
+        del dec, cache, g, gd, out, dout
+        torch.cuda.empty_cache()
+    res["what"] = ("HybridDecoder (36 layers, 3B shapes, random init) with the ring-buffer / static inference cache; one "
+                   "CUDA graph per frame shape, replayed; decode = 256 single-token graph replays after the stream")
+    return res
+
+
 def gdn_mixer_core_decode(dev, steps=50):
     """Everything between the input projections and o_proj of the 27 GDN mixers for one decode token (conv steps,
     gates, recurrence, gated norm, cache updates): the kernel-by-kernel chain against the one-launch fused step
@@ -604,17 +689,24 @@ def run_decode(dev, peaks, context=524288, steps=50):
     q, k, v, g, beta, h0 = gdn_inputs(T=1, H=H, seed=5, device=dev)
     states = [h0.to(torch.bfloat16).clone() for _ in range(N_GDN_LAYERS)]
     gen = torch.Generator().manual_seed(6)
-    kc = [torch.randn(1, WINDOW, HKV, D, generator=gen).bfloat16().to(dev) for _ in range(N_SWA_LAYERS)]
-    vc = [torch.randn(1, WINDOW, HKV, D, generator=gen).bfloat16().to(dev) for _ in range(N_SWA_LAYERS)]
+    from infinitevl_b200.cache import StaticSlidingWindowLayerPrealloc
+    from infinitevl_b200.modeling import HybridTextConfig
+    cfg = HybridTextConfig()
+    rings = [StaticSlidingWindowLayerPrealloc(config=cfg, batch_size=1, device=dev, dtype=torch.bfloat16)
+             for _ in range(N_SWA_LAYERS)]
+    fill = torch.randn(1, WINDOW + 300, HKV, D, generator=gen).bfloat16().to(dev)
+    for r in rings:      # full windows, ring wrapped once: the steady state of a long stream
+        for a in range(0, fill.shape[1], 256):
+            r._append(fill[:, a:a + 256], fill[:, a:a + 256])
     sq = torch.randn(1, 1, HQ, D, generator=gen).bfloat16().to(dev)
-    so = torch.empty_like(sq)
+    sk = torch.randn(1, 1, HKV, D, generator=gen).bfloat16().to(dev)
 
     def step():
         for st in states:
             ops.fused_recurrent_gated_delta_rule(q, k, v, g, beta, initial_state=st, output_final_state=True,
                                                  use_qk_l2norm_in_kernel=True, state_out=st)
-        for kk, vv in zip(kc, vc):
-            swa.swa_attention_bthd(sq, kk, vv, window=WINDOW, out=so)
+        for r in rings:      # append the token's K/V + attention over the window + combine: one launch per layer
+            r.attend(sq, sk, sk, D ** -0.5, WINDOW)
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -637,11 +729,13 @@ def run_decode(dev, peaks, context=524288, steps=50):
     ms = a.elapsed_time(b) / steps
     alg = N_GDN_LAYERS * 2 * H * K * V * 2 + N_SWA_LAYERS * 2 * HKV * WINDOW * D * 2
     core = gdn_mixer_core_decode(dev)
-    return {"step_ms": round(ms, 4), "gdn_mixer_core": core, "context_tokens": context, "launches_per_step": N_GDN_LAYERS + 2 * N_SWA_LAYERS,
+    return {"step_ms": round(ms, 4), "gdn_mixer_core": core, "context_tokens": context, "launches_per_step": N_GDN_LAYERS + N_SWA_LAYERS,
             "algorithmic_bytes": alg, "achieved_gbs": round(alg / (ms * 1e-3) / 1e9, 1),
             "hbm_frac": round(alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-            "what": "27x GDN token recurrence (bf16 state in place) + 9x SWA split-KV decode over an 8192-key window, "
-                    "one CUDA graph; state size is independent of the context length"}
+            "what": "mixer kernels only: 27x GDN token recurrence (bf16 state in place) + 9x ring-cache SWA decode step "
+                    "(K/V append + split-KV attention over the 8192-token window + combine in one launch), one CUDA "
+                    "graph; state size is independent of the context length.  config3_stream has the step through the "
+                    "decoder modules (projections, cache classes) after a real 512K-token stream"}
 
 
 def run_e2e(hp, args, world=1, dev=None):
@@ -802,6 +896,8 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-config2", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--stream-frames", type=int, default=2048)
     ap.add_argument("--sweep", default=None, nargs="?", const="4096,8192,16384,32768,65536,131072,262144,524288,1048576",
                     help="comma-separated sequence lengths: run the config-5 sweep instead of the bench line")
     args = ap.parse_args()
