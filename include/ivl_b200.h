@@ -113,6 +113,25 @@ IVL_API int ivl_gdn_chunk_scan(const void* v, const void* h0, int h0_dtype, void
                        int T, int H, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Gated DeltaNet backward (training).  Replaces chunk_gated_delta_rule_bwd --
+ * fla/ops/gated_delta_rule/chunk.py:74-177,237-269 (kernels wy_fast.py:432-620, common/chunk_delta_h.py:143-244,
+ * common/chunk_o.py:131-454) -- with the exact fp32 gradient of the token recurrence the operator is defined by
+ * (fused_recurrent.py:85-108), recomputing states from checkpoints instead of storing them.
+ *   qn, kn   fp32 [B,T,H,128]: the rows the forward used (L2-normalised and rounded to bf16 when l2norm_qk was set);
+ *            the caller applies the chain rule through the normalisation to d_qn / d_kn (element-wise).
+ *   v, d_o   bf16 [B,T,H,256];  g, beta fp32 [B,T,H];  h0, d_ht fp32 [B,H,128,256] or NULL (zeros).
+ *   d_qn, d_kn fp32 [B,T,H,128];  d_v fp32 [B,T,H,256];  d_g, d_beta fp32 [B,T,H];  d_h0 fp32 [B,H,128,256] or NULL.
+ *   workspace: ivl_gdn_bwd_workspace_bytes(B,T,H) bytes (state checkpoints every 16 tokens: 8 KiB per token per head
+ *   ... / 16), 16-byte aligned.  d_qn, d_kn, d_g, d_beta are summed with atomics: results are reproducible to
+ *   fp32 rounding of a sum of 16 terms, not bit for bit.
+ * ---------------------------------------------------------------------------------- */
+IVL_API size_t ivl_gdn_bwd_workspace_bytes(int B, int T, int H);
+IVL_API int ivl_gdn_bwd(const float* qn, const float* kn, const void* v, const float* g, const float* beta,
+                        const void* d_o, const float* h0, const float* d_ht, float* d_qn, float* d_kn, float* d_v,
+                        float* d_g, float* d_beta, float* d_h0, int B, int T, int H, int K, int V, float scale,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Gated DeltaNet, ONE decode step of the whole mixer core in one launch: everything between the input
  * projections and o_proj of GatedDeltaNet.forward for q_len == 1 (std:1263-1342): the three
  * ShortConvolution steps (fla/modules/convolution.py:224-293), the gate math (std:1293-1294), the

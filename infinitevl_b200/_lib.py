@@ -33,6 +33,8 @@ SIGNATURES = {
     "ivl_gdn_chunk_prep": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "ivl_gdn_chunk_scan": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int] + [c_int] * 3
                            + [c_void_p, c_size_t, c_void_p]),
+    "ivl_gdn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ivl_gdn_bwd": (c_int, [c_void_p] * 14 + [c_int] * 5 + [c_float, c_void_p, c_size_t, c_void_p]),
     "ivl_gdn_decode_step": (c_int, [c_void_p] * 16 + [c_int, c_void_p] + [c_int] * 4 + [c_float, c_float, c_void_p]),
     "ivl_gdn_recurrent_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
                               + [c_float, c_int, c_void_p]),

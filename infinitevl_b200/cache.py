@@ -278,7 +278,7 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
         if self._dirty:
             self._resync()
         W = self.sliding_window
-        if window is None or int(window) != W or Tq > self.max_append or Hq // self.num_kv_heads > 8:
+        if window is None or int(window) != W or Tq > self.max_append or Hq // self.num_kv_heads > 8 or W > 8192:
             # general case (long prefill into a cache, no window): the reference's concatenate-and-attend
             fk, fv = self.update(k_bthd.transpose(1, 2), v_bthd.transpose(1, 2))
             return swa.swa_attention_bthd(q_bthd, fk.transpose(1, 2), fv.transpose(1, 2), window=window, scale=scale)

@@ -41,6 +41,11 @@ cudaError_t launch_swa_ring_decode(const void* q, const void* knew, long long kn
                                    cudaStream_t stream);
 cudaError_t launch_swa_ring_append(const void* k, const long long* ks, const void* v, const long long* vs, void* ring_k,
                                    void* ring_v, int* state, int B, int Tq, int Hkv, int R, cudaStream_t stream);
+size_t gdn_bwd_workspace_bytes(int B, int T, int H);
+cudaError_t launch_gdn_bwd(const float* qn, const float* kn, const void* v, const float* g, const float* beta,
+                           const void* dout, const float* h0, const float* dht, float* dqn, float* dkn, float* dv,
+                           float* dg, float* dbeta, float* dh0, float* workspace, int B, int T, int H, float scale,
+                           cudaStream_t stream);
 cudaError_t launch_short_conv(const void* x, const void* w, const void* cache_in, void* y, void* cache_out, int B,
                               int T, int D, int act, cudaStream_t stream);
 cudaError_t launch_gdn_gate(const void* a, const void* b, const float* A_log, const float* dt_bias, float* g,
@@ -393,6 +398,33 @@ int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, const flo
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 
+size_t ivl_gdn_bwd_workspace_bytes(int B, int T, int H) {
+  if (B <= 0 || T <= 0 || H <= 0) return 0;
+  return ivl::gdn_bwd_workspace_bytes(B, T, H);
+}
+
+int ivl_gdn_bwd(const float* qn, const float* kn, const void* v, const float* g, const float* beta, const void* d_o,
+                const float* h0, const float* d_ht, float* d_qn, float* d_kn, float* d_v, float* d_g, float* d_beta,
+                float* d_h0, int B, int T, int H, int K, int V, float scale, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  if (int e = check_gdn_shape(B, T, H, K, V)) return e;
+  if (!qn || !kn || !v || !g || !beta || !d_o || !d_qn || !d_kn || !d_v || !d_g || !d_beta || !workspace)
+    return IVL_ERR_NULL;
+  if (workspace_bytes < ivl::gdn_bwd_workspace_bytes(B, T, H) || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return IVL_ERR_WORKSPACE;
+  IVL_ARCH();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * T * H;
+  // dq, dk, dg, dbeta are accumulated across the value slices with atomics
+  IVL_CUDA(cudaMemsetAsync(d_qn, 0, n * K * sizeof(float), st));
+  IVL_CUDA(cudaMemsetAsync(d_kn, 0, n * K * sizeof(float), st));
+  IVL_CUDA(cudaMemsetAsync(d_g, 0, n * sizeof(float), st));
+  IVL_CUDA(cudaMemsetAsync(d_beta, 0, n * sizeof(float), st));
+  IVL_CUDA(ivl::launch_gdn_bwd(qn, kn, v, g, beta, d_o, h0, d_ht, d_qn, d_kn, d_v, d_g, d_beta, d_h0,
+                               static_cast<float*>(workspace), B, T, H, default_scale(scale, K), st));
+  return IVL_OK;
+}
+
 int ivl_gdn_decode_step(const void* q_in, const void* k_in, const void* v_in, const void* a_in, const void* b_in,
                         const void* gate_in, const void* conv_weight_q, const void* conv_weight_k,
                         const void* conv_weight_v, const float* A_log, const float* dt_bias, const void* norm_weight,
@@ -472,6 +504,7 @@ int ivl_swa_ring_decode(const void* q, const void* k_new, const int64_t* k_new_s
   if (!q || !k_new || !v_new || !k_new_strides || !v_new_strides || !ring_k || !ring_v || !state || !o || !workspace)
     return IVL_ERR_NULL;
   if (workspace_bytes < ivl::swa_ring_decode_workspace_bytes(B, Hq, window)) return IVL_ERR_WORKSPACE;
+  if (window > 8192) return IVL_ERR_BAD_SHAPE;   // the fused combine holds at most 64 slices of 128 keys
   if ((k_new_strides[0] | k_new_strides[1] | v_new_strides[0] | v_new_strides[1]) & 7) return IVL_ERR_BAD_SHAPE;
   IVL_ARCH();
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);

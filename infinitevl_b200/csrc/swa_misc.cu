@@ -69,6 +69,8 @@ __global__ void mrope_kernel(__nv_bfloat16* __restrict__ x, long long sb, long l
 constexpr int DEC_KEYS = 128;     // keys per CTA
 constexpr int DEC_MAXG = 8;       // q-heads per kv-head supported
 constexpr int DEC_LD = 136;       // padded smem row (bf16 elements): 272 B, conflict-free ldmatrix
+constexpr int DEC_REC = 132;      // floats per partial record: [m, l, -, -, o[128]] (o 16-byte aligned)
+constexpr int DEC_O = 4;
 
 struct DecSmem {
   __nv_bfloat16 k[DEC_KEYS * DEC_LD];
@@ -197,12 +199,12 @@ __device__ __forceinline__ void dec_partial_body(DecSmem& s, const __nv_bfloat16
       dec_mma16816(acc[2 * ntp + 1], a, b2, b3);
     }
   }
-  // partial record per (b, q-head, split): [m, l, o[128]]
+  // partial record per (b, q-head, split): [m, l, -, -, o[128]]
   if (gq < group) {
-    float* rec = part + (((long long)b * Hq + hk * group + gq) * nsplit + split) * 130;
+    float* rec = part + (((long long)b * Hq + hk * group + gq) * nsplit + split) * DEC_REC;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
-      *reinterpret_cast<float2*>(rec + 2 + warp * 32 + nt * 8 + 2 * tq) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(rec + DEC_O + warp * 32 + nt * 8 + 2 * tq) = make_float2(acc[nt][0], acc[nt][1]);
     if (warp == 0 && tq == 0) {
       rec[0] = m;
       rec[1] = s.red_l[gq][0] + s.red_l[gq][1] + s.red_l[gq][2] + s.red_l[gq][3];
@@ -229,13 +231,13 @@ swa_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
 // log-sum-exp combine of the partial records of one (b, q-head); thread tid owns head dim tid
 __device__ __forceinline__ void dec_combine(const float* rec, __nv_bfloat16* o_row, int nsplit, int tid) {
   float M = -INFINITY;
-  for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(rec + sp * 130));
+  for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(rec + sp * DEC_REC));
   float L = 0.f, acc = 0.f;
   for (int sp = 0; sp < nsplit; ++sp) {
-    const float m = __ldcg(rec + sp * 130);
+    const float m = __ldcg(rec + sp * DEC_REC);
     const float w = (m == -INFINITY) ? 0.f : exp2f(m - M);
-    L = fmaf(w, __ldcg(rec + sp * 130 + 1), L);
-    acc = fmaf(w, __ldcg(rec + sp * 130 + 2 + tid), acc);
+    L = fmaf(w, __ldcg(rec + sp * DEC_REC + 1), L);
+    acc = fmaf(w, __ldcg(rec + sp * DEC_REC + DEC_O + tid), acc);
   }
   o_row[tid] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
 }
@@ -294,9 +296,69 @@ swa_ring_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int gh = 0; gh < group; ++gh) {
-    const long long bh = (long long)b * Hq + hk * group + gh;
-    dec_combine(part + bh * nsplit * 130, o + bh * 128, nsplit, tid);
+  // Block-parallel log-sum-exp combine of the group's records (up to 8 heads x 64 slices x 528 B = 270 KB): the
+  // slice maxima / sums first (one load per thread and record), then four heads at a time, one float4 of the output
+  // per thread and slice with eight loads in flight.  (A loop of dependent loads per head, as in the stand-alone
+  // combine kernel, costs ~70 us here: one block would walk 8 heads x 64 slices serially.)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    float* sm_m = reinterpret_cast<float*>(dsm);              // [8][64]  (the slice staging area is dead)
+    float* sm_w = sm_m + DEC_MAXG * 64;                      // [8][64]
+    const float* recs = part + ((long long)b * Hq + hk * group) * nsplit * DEC_REC;
+    for (int i = tid; i < group * nsplit; i += 128) {
+      sm_m[(i / nsplit) * 64 + i % nsplit] = __ldcg(recs + (long long)i * DEC_REC);
+      sm_w[(i / nsplit) * 64 + i % nsplit] = __ldcg(recs + (long long)i * DEC_REC + 1);
+    }
+    __syncthreads();
+    float Linv[2] = {0.f, 0.f};
+    for (int pass = 0; pass < 2; ++pass) {
+      const int gh = warp + 4 * pass;                        // warp w normalises heads w and w + 4
+      if (gh < group) {
+        const float m0 = lane < nsplit ? sm_m[gh * 64 + lane] : -INFINITY;
+        const float m1 = lane + 32 < nsplit ? sm_m[gh * 64 + lane + 32] : -INFINITY;
+        float M = fmaxf(m0, m1);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, d));
+        const float w0 = m0 == -INFINITY ? 0.f : exp2f(m0 - M), w1 = m1 == -INFINITY ? 0.f : exp2f(m1 - M);
+        float L = (lane < nsplit ? w0 * sm_w[gh * 64 + lane] : 0.f) + (lane + 32 < nsplit ? w1 * sm_w[gh * 64 + lane + 32] : 0.f);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) L += __shfl_xor_sync(0xffffffffu, L, d);
+        if (lane < nsplit) sm_w[gh * 64 + lane] = w0;
+        if (lane + 32 < nsplit) sm_w[gh * 64 + lane + 32] = w1;
+        if (lane == 0) sm_m[gh * 64] = L > 0.f ? 1.f / L : 0.f;   // slot 0 of the maxima now holds 1 / L
+      }
+    }
+    __syncthreads();
+    (void)Linv;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int gh = warp + 4 * pass;                        // warp w sums heads w and w + 4: lane = 4 head dims
+      if (gh < group) {
+        const float* r = recs + (long long)gh * nsplit * DEC_REC + DEC_O + 4 * lane;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int sp = 0;
+        for (; sp + 8 <= nsplit; sp += 8) {
+          float4 x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __ldcg(reinterpret_cast<const float4*>(r + (long long)(sp + j) * DEC_REC));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float w = sm_w[gh * 64 + sp + j];
+            acc.x = fmaf(w, x[j].x, acc.x); acc.y = fmaf(w, x[j].y, acc.y);
+            acc.z = fmaf(w, x[j].z, acc.z); acc.w = fmaf(w, x[j].w, acc.w);
+          }
+        }
+        for (; sp < nsplit; ++sp) {
+          const float4 x = __ldcg(reinterpret_cast<const float4*>(r + (long long)sp * DEC_REC));
+          const float w = sm_w[gh * 64 + sp];
+          acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y); acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+        }
+        const float inv = sm_m[gh * 64];
+        uint2 out;
+        out.x = pack_bf16(acc.x * inv, acc.y * inv);
+        out.y = pack_bf16(acc.z * inv, acc.w * inv);
+        *reinterpret_cast<uint2*>(o + ((long long)b * Hq + hk * group + gh) * 128 + 4 * lane) = out;
+      }
+    }
   }
   if (tid == 0) {
     state[2 + b * Hkv + hk] = 0;                                 // ready for the next launch / graph replay
@@ -346,14 +408,14 @@ swa_ring_append_kernel(const __nv_bfloat16* __restrict__ k, long long k_sb, long
 __global__ void __launch_bounds__(128)
 swa_decode_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ o, int nsplit) {
   const long long bh = blockIdx.x;  // b * Hq + h
-  dec_combine(part + bh * nsplit * 130, o + bh * 128, nsplit, threadIdx.x);
+  dec_combine(part + bh * nsplit * DEC_REC, o + bh * 128, nsplit, threadIdx.x);
 }
 
 }  // namespace
 
 size_t swa_decode_workspace_bytes(int B, int Tk, int Hq) {
   const int nsplit = (Tk + DEC_KEYS - 1) / DEC_KEYS;
-  return (size_t)B * Hq * nsplit * 130 * sizeof(float);
+  return (size_t)B * Hq * nsplit * DEC_REC * sizeof(float);
 }
 
 // q, o [B,1,Hq,128] contiguous; k, v [B,Tk,Hkv,128] with element strides (batch, time, head)
@@ -401,7 +463,7 @@ static cudaError_t configure_decode_kernels() {
 
 size_t swa_ring_decode_workspace_bytes(int B, int Hq, int window) {
   const int nsplit = (window + DEC_KEYS - 1) / DEC_KEYS;
-  return (size_t)B * Hq * nsplit * 130 * sizeof(float);
+  return (size_t)B * Hq * nsplit * DEC_REC * sizeof(float);
 }
 
 cudaError_t launch_swa_ring_decode(const void* q, const void* knew, long long kn_sb, long long kn_sh, const void* vnew,

@@ -195,7 +195,6 @@ def _run_chunk_varlen(q, k, v, g, beta, scale, h0, ht, o, l2norm, bounds):
     _lib.check(code, "ivl_gdn_chunk_fwd_varlen")
 
 
-@torch.no_grad()
 def chunk_gated_delta_rule(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -225,8 +224,19 @@ def chunk_gated_delta_rule(
     else:
         assert scale > 0, "Scale must be positive."
     out_dtype = q.dtype
-    o, ht = _gated_delta_rule(_run_chunk, q, k, v, g, beta, scale, initial_state, output_final_state, cu_seqlens,
-                              use_qk_l2norm_in_kernel, state_out)
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (q, k, v, g, beta, initial_state))
+    if needs_grad:
+        # training: the reference's ChunkGatedDeltaRuleFunction (fla/ops/gated_delta_rule/chunk.py:180-269)
+        if state_out is not None:
+            raise ValueError("state_out (in-place final state) is an inference extension; not available with autograd")
+        o, ht = _chunk_autograd(q, k, v, g, beta, scale, initial_state, output_final_state, cu_seqlens,
+                                use_qk_l2norm_in_kernel)
+        o = o.to(out_dtype)
+        return (o.transpose(1, 2) if head_first else o), ht
+    with torch.no_grad():
+        o, ht = _gated_delta_rule(_run_chunk, q, k, v, g, beta, scale, initial_state, output_final_state, cu_seqlens,
+                                  use_qk_l2norm_in_kernel, state_out)
     o = o.to(out_dtype)
     if head_first:
         o = o.transpose(1, 2)
@@ -268,3 +278,93 @@ def fused_recurrent_gated_delta_rule(
     if head_first:
         o = o.transpose(1, 2)
     return o, ht
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd (training drop-in)
+# ------------------------------------------------------------------------------------------------
+def _normalised_rows(x: torch.Tensor, l2norm: bool):
+    """The rows the forward kernels multiply with: fp32 L2-normalisation rounded to bf16 (l2norm.py:42), as fp32.
+    Returns (rows, rstd | None)."""
+    xf = x.float()
+    if not l2norm:
+        return xf.contiguous(), None
+    rstd = torch.rsqrt(xf.pow(2).sum(-1, keepdim=True) + 1e-6)
+    return (xf * rstd).to(torch.bfloat16).float().contiguous(), rstd
+
+
+class ChunkGatedDeltaRuleFunction(torch.autograd.Function):
+    """Forward: the chunk kernels (ivl_gdn_chunk_fwd).  Backward: ivl_gdn_bwd -- the exact fp32 gradient of the
+    recurrence with recomputed states (the reference recomputes w, u, h and runs its chunked backward kernels,
+    fla/ops/gated_delta_rule/chunk.py:237-269)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, g, beta, scale, initial_state, output_final_state, l2norm):
+        with torch.no_grad():
+            o, ht = _gated_delta_rule(_run_chunk, q, k, v, g, beta, scale, initial_state, output_final_state, None,
+                                      l2norm, None)
+        ctx.save_for_backward(q, k, v, g, beta, initial_state)
+        ctx.scale, ctx.l2norm = float(scale), bool(l2norm)
+        return o, ht
+
+    @staticmethod
+    def backward(ctx, d_o, d_ht):
+        q, k, v, g, beta, h0 = ctx.saved_tensors
+        lib = _lib.load()
+        B, T, H, K = q.shape
+        V = v.shape[-1]
+        dev = q.device
+        qn, rq = _normalised_rows(q, ctx.l2norm)
+        kn, rk = _normalised_rows(k, ctx.l2norm)
+        vb = v.to(torch.bfloat16).contiguous()
+        gf = g.float().contiguous()
+        bf = beta.float().contiguous()
+        dob = d_o.to(torch.bfloat16).contiguous()
+        h0f = None if h0 is None else h0.float().contiguous()
+        dht = None if d_ht is None else d_ht.float().contiguous()
+        dqn = torch.empty(B, T, H, K, dtype=torch.float32, device=dev)
+        dkn = torch.empty_like(dqn)
+        dv = torch.empty(B, T, H, V, dtype=torch.float32, device=dev)
+        dg = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        db = torch.empty_like(dg)
+        dh0 = torch.empty(B, H, K, V, dtype=torch.float32, device=dev) if h0 is not None else None
+        ws = torch.empty(lib.ivl_gdn_bwd_workspace_bytes(B, T, H), dtype=torch.uint8, device=dev)
+        code = lib.ivl_gdn_bwd(qn.data_ptr(), kn.data_ptr(), vb.data_ptr(), gf.data_ptr(), bf.data_ptr(), dob.data_ptr(),
+                               _ptr(h0f), _ptr(dht), dqn.data_ptr(), dkn.data_ptr(), dv.data_ptr(), dg.data_ptr(),
+                               db.data_ptr(), _ptr(dh0), B, T, H, K, V, ctx.scale, ws.data_ptr(), ws.numel(),
+                               _stream_ptr(dev))
+        _lib.check(code, "ivl_gdn_bwd")
+
+        def through_norm(dy, x, rstd):      # y = x rsqrt(sum x^2 + eps):  dx = rstd (dy - y (y . dy))
+            if rstd is None:
+                return dy
+            y = x.float() * rstd
+            return rstd * (dy - y * (y * dy).sum(-1, keepdim=True))
+
+        dq = through_norm(dqn, q, rq).to(q.dtype)
+        dk = through_norm(dkn, k, rk).to(k.dtype)
+        return (dq, dk, dv.to(v.dtype), dg.to(g.dtype), db.to(beta.dtype), None,
+                None if h0 is None else dh0.to(h0.dtype), None, None)
+
+
+def _chunk_autograd(q, k, v, g, beta, scale, initial_state, output_final_state, cu_seqlens, l2norm):
+    if cu_seqlens is None:
+        return ChunkGatedDeltaRuleFunction.apply(q, k, v, g, beta, scale, initial_state, output_final_state, l2norm)
+    # packed sequences: one differentiable call per sequence (the backward kernel takes dense rows)
+    bounds = [int(x) for x in cu_seqlens.tolist()]
+    outs, states = [], []
+    for n in range(len(bounds) - 1):
+        s0, e0 = bounds[n], bounds[n + 1]
+        h0 = None if initial_state is None else initial_state[n:n + 1]
+        if e0 <= s0:
+            states.append(h0.float() if h0 is not None else
+                          torch.zeros(1, q.shape[2], q.shape[3], v.shape[3], device=q.device))
+            continue
+        o, ht = ChunkGatedDeltaRuleFunction.apply(q[:, s0:e0], k[:, s0:e0], v[:, s0:e0], g[:, s0:e0], beta[:, s0:e0],
+                                                  scale, h0, output_final_state, l2norm)
+        outs.append(o)
+        states.append(ht)
+    o = torch.cat(outs, dim=1)
+    if bounds[-1] < q.shape[1]:
+        o = torch.cat([o, o.new_zeros(1, q.shape[1] - bounds[-1], *o.shape[2:])], dim=1)
+    return o, (torch.cat(states, dim=0) if output_final_state else None)
