@@ -74,22 +74,45 @@ def test_backward_without_l2norm_and_final_state_grad_only(ops):
         assert err_ratio(r, x.float().cpu()) < TOL, name
 
 
-def test_backward_against_live_reference_triton(ops):
-    fla = pytest.importorskip("fla.ops.gated_delta_rule")
+_FLA_BWD = """
+import sys, torch
+sys.path.insert(0, {tests!r})
+from inputs import gdn_inputs
+from fla.ops.gated_delta_rule import chunk_gated_delta_rule
+q, k, v, g, beta, h0 = (x.cuda() for x in gdn_inputs(T=2048, H=16, seed=77))
+do = torch.randn(1, 2048, 16, 256, generator=torch.Generator().manual_seed(1)).bfloat16().cuda()
+leaves = [x.clone().requires_grad_(True) for x in (q, k, v, g, beta, h0)]
+o, S = chunk_gated_delta_rule(*leaves[:5], initial_state=leaves[5], output_final_state=True, use_qk_l2norm_in_kernel=True)
+(o.float() * do.float()).sum().backward()
+torch.cuda.synchronize()
+torch.save([l.grad.float().cpu() for l in leaves], {out!r})
+"""
+
+
+def test_backward_against_live_reference_triton(ops, tmp_path):
+    """The reference's own GPU backward (pip flash-linear-attention) on the same inputs.  It runs in a child process:
+    a crash inside the dependency's kernels (seen on sm_100: misaligned address) would otherwise poison this
+    process's CUDA context; a child that fails means "reference backward unavailable here" and the test is skipped."""
+    import os
+    import subprocess
+    import sys
+    pytest.importorskip("fla.ops.gated_delta_rule")
+    out = str(tmp_path / "fla_grads.pt")
+    code = _FLA_BWD.format(tests=os.path.dirname(os.path.abspath(__file__)), out=out)
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    except subprocess.TimeoutExpired:
+        pytest.skip("reference Triton backward timed out")
+    if r.returncode != 0 or not os.path.exists(out):
+        pytest.skip(f"reference Triton backward unavailable: {r.stderr[-300:]}")
+    ref = torch.load(out)
     q, k, v, g, beta, h0 = (x.cuda() for x in gdn_inputs(T=2048, H=16, seed=77))
     do = torch.randn(1, 2048, 16, 256, generator=torch.Generator().manual_seed(1)).bfloat16().cuda()
-    grads = {}
-    for name, fn in (("ours", ops.chunk_gated_delta_rule), ("fla", fla.chunk_gated_delta_rule)):
-        leaves = [x.clone().requires_grad_(True) for x in (q, k, v, g, beta, h0)]
-        try:
-            o, S = fn(*leaves[:5], initial_state=leaves[5], output_final_state=True, use_qk_l2norm_in_kernel=True)
-            (o.float() * do.float()).sum().backward()
-        except Exception as e:  # noqa: BLE001  (Triton toolchain problems are not ours)
-            if name == "fla":
-                pytest.skip(f"reference Triton path unavailable: {e!r}")
-            raise
-        grads[name] = [l.grad.float() for l in leaves]
-    for name, a, b in zip(("dq", "dk", "dv", "dg", "dbeta", "dh0"), grads["fla"], grads["ours"]):
+    leaves = [x.clone().requires_grad_(True) for x in (q, k, v, g, beta, h0)]
+    o, S = ops.chunk_gated_delta_rule(*leaves[:5], initial_state=leaves[5], output_final_state=True,
+                                      use_qk_l2norm_in_kernel=True)
+    (o.float() * do.float()).sum().backward()
+    for name, a, b in zip(("dq", "dk", "dv", "dg", "dbeta", "dh0"), ref, [l.grad.float().cpu() for l in leaves]):
         assert err_ratio(a, b) < 2e-2, (name, err_ratio(a, b))
 
 
