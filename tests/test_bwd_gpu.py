@@ -96,6 +96,9 @@ def test_backward_against_live_reference_triton(ops, tmp_path):
     import os
     import subprocess
     import sys
+    if os.environ.get("IVL_TEST_FLA_BWD", "0") != "1":
+        pytest.skip("set IVL_TEST_FLA_BWD=1 to run the reference's Triton backward (minutes of JIT compilation; on the "
+                    "B200 image its kernels fail with 'misaligned address', profiles/r02_summary.md)")
     pytest.importorskip("fla.ops.gated_delta_rule")
     out = str(tmp_path / "fla_grads.pt")
     code = _FLA_BWD.format(tests=os.path.dirname(os.path.abspath(__file__)), out=out)
