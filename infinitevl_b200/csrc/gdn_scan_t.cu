@@ -29,6 +29,7 @@
 // are the v_new / output epilogue, warps 6..13 own the state (TMEM lane quadrant = warp % 4 in both groups; two
 // state warps per quadrant split the 128 key dims).
 #include <atomic>
+#include <mutex>
 #include <cuda.h>
 
 #include "gdn_layout.cuh"
@@ -40,7 +41,10 @@ namespace {
 
 struct TCfg {
   static constexpr int THREADS = 448;   // 14 warps: copy, MMA, 4 v_new/output, 8 state
-  static constexpr int NA = 2, NK = 2;
+#ifndef IVL_TSCAN_NA
+#define IVL_TSCAN_NA 2
+#endif
+  static constexpr int NA = IVL_TSCAN_NA, NK = 2;   // NA: 2 or 3 A slots (developer knob, tools/dev_tscan.py)
   // A slot: operands that are dead once the W and O parts have retired (early in the step)
   static constexpr uint32_t A_BW = 0;                         // [-Wg ; Qg]  32 KiB, K-major, no swizzle
   static constexpr uint32_t A_V = A1_BYTES;                   // value tile: 2 panels [64 tok][64 val], 128B swizzle
@@ -82,7 +86,7 @@ __device__ long long ivl_ttrace_buf[64 * 16];
 #endif
 
 struct TBars {
-  uint64_t fullA[2], emptyA[2], fullK[2], emptyK[2];
+  uint64_t fullA[3], emptyA[3], fullK[2], emptyK[2];
   uint64_t sb, vb, ds, dv[2], dofull[2], dofree[2];
   uint32_t tmem_base;
 };
@@ -133,8 +137,8 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
   const uint8_t* aublob = ws.ublob + slot0 * (GDN_NS * UBLOB_BYTES);
 
   if (tid == 0) {
+    for (int s = 0; s < C::NA; ++s) { mbar_init(&bars.fullA[s], 1); mbar_init(&bars.emptyA[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars.fullA[s], 1); mbar_init(&bars.emptyA[s], 1);
       mbar_init(&bars.fullK[s], 1);
       mbar_init(&bars.emptyK[s], 1 + 8);   // the C part has retired + the eight state warps have read gamma
       mbar_init(&bars.dv[s], 1); mbar_init(&bars.dofull[s], 1); mbar_init(&bars.dofree[s], 4);
@@ -829,6 +833,355 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   if (warp == 1) tmem_dealloc<C::TM_COLS>(tmem);
 }
 
+// =====================================================================================================
+// Pipelined form of the transposed scan (the default): same operands, same arithmetic per product as
+// gdn_scan_t_kernel, but the two tensor <-> epilogue hand-offs of the serial chain are PIPELINED over the contraction
+// dimension, and the output products leave the chain.
+//
+// Timeline of gdn_scan_t_kernel (clock64 probe, cycles per chunk ~1900): W part done +466, epi V +310, B part +456
+// (it queues behind the O part on the in-order tensor pipe), epi S +736 (TMEM -> registers moves 64 B/cycle per
+// quadrant: 256 cycles for the 128 fp32 columns of DS alone, then pack / store / fence / arrive).  Here
+//   * sixteen state warps (four per TMEM lane quadrant) own 32 key dims each and publish their quarter of bf16 S^T on
+//     their own barrier; the MMA warp issues the two K = 16 slabs of the W part that read that quarter as soon as
+//     it arrives, so the W part overlaps the state epilogue instead of following it;
+//   * the v_new warps publish bf16 v_new^T in two halves of 32 tokens, the B part follows half by half;
+//   * bf16 S^T is double-buffered in tensor memory (the v_new accumulator is single-buffered instead: its U part is
+//     only issued after v_new has been read anyway), so the O part may read S_c while S_{c+1} is being published: the
+//     O and C parts are issued AFTER the B part and run on the tensor pipe while the state epilogue works.
+// Serial chain per chunk: state quarter 3 -> last W slabs -> epi V half 1 -> last B slabs.  Three A slots: the slot
+// of chunk c is released after the O part, late in the step.
+// =====================================================================================================
+struct T3Cfg {
+  static constexpr int THREADS = 704;   // 22 warps: copy, MMA, 4 v_new/output, 16 state
+  static constexpr int NA = 3, NK = 2;
+  static constexpr uint32_t A_BW = 0;                         // [-Wg ; Qg]  32 KiB, K-major, no swizzle
+  static constexpr uint32_t A_V = A1_BYTES;                   // value tile: 2 panels [64 tok][64 val], 128B swizzle
+  static constexpr uint32_t V_PANEL = 64 * 64 * 2;
+  static constexpr uint32_t A_AU = A1_BYTES + 2 * V_PANEL;    // Au 8 KiB, K-major, no swizzle
+  static constexpr uint32_t ASLOT = A_AU + AU_BYTES;          // 56 KiB
+  static constexpr uint32_t A_TX = ASLOT;
+  static constexpr uint32_t K_P = 0;
+  static constexpr uint32_t K_KT = P_BYTES;
+  static constexpr uint32_t K_TAIL = P_BYTES + KT_BYTES;
+  static constexpr uint32_t K_TX = P_BYTES + KT_BYTES + TAIL_BYTES;
+  static constexpr uint32_t KSLOT = P_BYTES + KT_BYTES + 1024;   // 25 KiB
+  static constexpr uint32_t OFF_A = 0;
+  static constexpr uint32_t OFF_K = NA * ASLOT;
+  static constexpr uint32_t OFF_BARS = OFF_K + NK * KSLOT;
+  static constexpr uint32_t SMEM = OFF_BARS + 512 + 1024;
+  static constexpr uint32_t TM_DS = 0;       // 128: v_new^T Kt (state increment)
+  static constexpr uint32_t TM_SB = 128;     // 2 x 64: bf16 S^T of even / odd chunks (A operand, K = 128)
+  static constexpr uint32_t TM_DV = 256;     //  64: v_new^T accumulator
+  static constexpr uint32_t TM_VB = 320;     //  32: bf16 v_new^T (A operand, K = 64)
+  static constexpr uint32_t TM_DO = 384;     // 2 x 64: O^T accumulators
+  static constexpr uint32_t TM_COLS = 512;
+  static_assert(ASLOT % 1024 == 0 && KSLOT % 1024 == 0 && A_V % 1024 == 0, "swizzled tiles need 1 KiB alignment");
+  static_assert(SMEM <= 232448, "exceeds 227 KiB");
+};
+
+struct T3Bars {
+  uint64_t fullA[3], emptyA[3], fullK[2], emptyK[2];
+  uint64_t sb[4], vb[2], ds, dv, dofull[2], dofree[2];
+  uint32_t tmem_base;
+};
+
+// 704 threads: 65536 / 704 -> 88 registers per thread; a state thread keeps 32 fp32 state entries for the whole
+// sequence plus one 32-column staging buffer, the v_new / output threads work in halves of 32 columns
+__global__ void __launch_bounds__(T3Cfg::THREADS, 1)
+gdn_scan_t3_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnVarlen vl, const void* __restrict__ h0,
+                   int h0_dtype, __nv_bfloat16* __restrict__ o, void* __restrict__ ht, int ht_dtype, int T, int H,
+                   int NTROW) {
+  using C = T3Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  T3Bars& bars = *reinterpret_cast<T3Bars*>(smem + C::OFF_BARS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int vh = blockIdx.x, h = blockIdx.y;               // value half, head
+  const bool varlen = vl.chunk_tok0 != nullptr;
+  const int b = varlen ? 0 : blockIdx.z;
+  const int seq = blockIdx.z;
+  const int cb = varlen ? __ldg(vl.seq_chunk_begin + seq) : 0;
+  const int NT = varlen ? __ldg(vl.seq_chunk_begin + seq + 1) - cb : NTROW;
+  const size_t ch0 = ((size_t)b * H + h) * NTROW + cb;
+  const size_t slot0 = ((size_t)b * H + h) * ws.ring;
+  const int ring = ws.ring;
+  const int col0 = vh * 128;
+  if (NT <= 0) {
+    // empty sequence: the final state is the initial state
+    if (ht != nullptr) {
+      const size_t base = ((size_t)seq * H + h) * GDN_K * GDN_V;
+      for (int i = tid; i < GDN_K * 128; i += C::THREADS) {
+        const size_t off = base + (size_t)(i >> 7) * GDN_V + col0 + (i & 127);
+        const float x = h0 == nullptr ? 0.f
+                        : (h0_dtype == 0 ? static_cast<const float*>(h0)[off]
+                                         : __bfloat162float(static_cast<const __nv_bfloat16*>(h0)[off]));
+        if (ht_dtype == 0) static_cast<float*>(ht)[off] = x;
+        else static_cast<__nv_bfloat16*>(ht)[off] = __float2bfloat16(x);
+      }
+    }
+    return;
+  }
+  const uint8_t* blob = ws.blob + slot0 * BLOB_BYTES;
+  const uint8_t* aublob = ws.ublob + slot0 * (GDN_NS * UBLOB_BYTES);
+
+  if (tid == 0) {
+    for (int s = 0; s < C::NA; ++s) { mbar_init(&bars.fullA[s], 1); mbar_init(&bars.emptyA[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.fullK[s], 1);
+      mbar_init(&bars.emptyK[s], 1 + 16);   // the C part has retired + the sixteen state warps have read gamma
+      mbar_init(&bars.dofull[s], 1); mbar_init(&bars.dofree[s], 4);
+      mbar_init(&bars.vb[s], 4);
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(&bars.sb[s], 4);
+    mbar_init(&bars.ds, 1); mbar_init(&bars.dv, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) tmem_alloc<C::TM_COLS>(&bars.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------- copy warp (TMA engine) ---------------------------
+    const uint32_t* ready = ws.ready + ch0;
+    uint32_t* progress = ws.progress + ((size_t)b * H + h) * GDN_NS + vh;
+    int known = 0;  // chunks [0, known) are published
+    for (int c = 0; c < NT; ++c) {
+      if (c >= known) {
+        long long spins = 0;
+        do {
+          const int idx = known + lane;
+          const uint32_t f = (idx < NT) ? ld_acquire_gpu_t(ready + idx) : 0u;
+          const uint32_t m = __ballot_sync(0xffffffffu, f != 0u);
+          known += (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);
+          if (c >= known) {
+            __nanosleep(200);
+            if (++spins > (1ll << 24)) asm volatile("trap;");  // the pre-pass never ran: fail loudly, do not hang
+          }
+        } while (c >= known);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      const int sa = c % C::NA, sk = c % C::NK;
+      const size_t cs = (size_t)((cb + c) % ring);  // image slot of chunk c
+      const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
+      if (c >= C::NA) mbar_wait(&bars.emptyA[sa], (c / C::NA - 1) & 1);
+      uint8_t* as = smem + C::OFF_A + sa * C::ASLOT;
+      mbar_arrive_expect_tx_ws(&bars.fullA[sa], C::A_TX);
+      bulk_g2s_ws(as + C::A_BW, blob + cs * BLOB_BYTES + BLOB_OFF_A1, A1_BYTES, &bars.fullA[sa]);
+      bulk_g2s_ws(as + C::A_AU, aublob + cs * (GDN_NS * UBLOB_BYTES), AU_BYTES, &bars.fullA[sa]);
+      tma_load_4d_ws(as + C::A_V, &tmV, col0, h, tok0, b, &bars.fullA[sa]);
+      tma_load_4d_ws(as + C::A_V + C::V_PANEL, &tmV, col0 + 64, h, tok0, b, &bars.fullA[sa]);
+      if (c >= C::NK) {
+        mbar_wait(&bars.emptyK[sk], (c / C::NK - 1) & 1);
+        // every product that read the K slot of chunk c - NK has retired, and -- the O part of a chunk is issued
+        // before its C part -- so has every product that read its A slot: the image slot may be overwritten
+        if (lane == 0 && ring < NTROW)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(progress), "r"((uint32_t)(c - C::NK + 1)) : "memory");
+      }
+      uint8_t* ks = smem + C::OFF_K + sk * C::KSLOT;
+      mbar_arrive_expect_tx_ws(&bars.fullK[sk], C::K_TX);
+      bulk_g2s_ws(ks + C::K_P, blob + cs * BLOB_BYTES + BLOB_OFF_P, C::K_TX, &bars.fullK[sk]);
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------------
+    constexpr uint32_t idescU = umma_idesc_bf16(128, 64, /*a_mn=*/1, /*b_mn=*/0);
+    constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idescB = umma_idesc_bf16(128, 128, 0, /*b_mn=*/1);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    auto issue_u = [&](int c) {   // DV = V^T Au^T
+      const uint32_t as = sbase + C::OFF_A + (c % C::NA) * C::ASLOT;
+      const uint64_t dV = umma_desc(as + C::A_V, C::V_PANEL, 1024, SWZ_128B);
+      const uint64_t dAu = umma_desc(as + C::A_AU, 128, 1024, SWZ_NONE);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma_bf16_ws(tm + C::TM_DV, dV + j * 128, dAu + j * 16, idescU, j > 0);
+    };
+    mbar_wait(&bars.fullA[0], 0);
+    tc_fence_after();
+    issue_u(0);
+    for (int c = 0; c < NT; ++c) {
+      const int sa = c % C::NA, sk = c % C::NK, buf = c & 1;
+      const uint32_t as = sbase + C::OFF_A + sa * C::ASLOT, ks = sbase + C::OFF_K + sk * C::KSLOT;
+      const uint64_t dW = umma_desc(as + C::A_BW, 128, 2048, SWZ_NONE);            // rows 0..63: -Wg
+      const uint64_t dQ = umma_desc(as + C::A_BW + 8 * 2048, 128, 2048, SWZ_NONE); // rows 64..127: Qg
+      const uint64_t dKt = umma_desc(ks + C::K_KT, 128, 1024, SWZ_NONE);
+      const uint64_t dP = umma_desc(ks + C::K_P, 128, 1024, SWZ_NONE);
+      const uint32_t sbt = tm + C::TM_SB + buf * 64, dob = tm + C::TM_DO + buf * 64;
+      // W part, key quarter by key quarter as the state warps publish bf16 S_c^T
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mbar_wait(&bars.sb[q], c & 1);
+        tc_fence_after();
+        if (q == 0) TTR(0);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = 2 * q + jj;
+          umma_bf16_ts_ws(tm + C::TM_DV, sbt + j * 8, dW + j * 16, idesc64, 1);
+        }
+      }
+      umma_commit_ws(&bars.dv);
+      TTR(1);
+      // B part, token half by token half as the v_new warps publish bf16 v_new^T
+      mbar_wait(&bars.fullK[sk], (c / C::NK) & 1);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        mbar_wait(&bars.vb[hh], c & 1);
+        tc_fence_after();
+        if (hh == 0) TTR(2);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = 2 * hh + jj;
+          umma_bf16_ts_ws(tm + C::TM_DS, tm + C::TM_VB + j * 8, dKt + j * 16, idescB, j > 0);
+        }
+      }
+      umma_commit_ws(&bars.ds);
+      TTR(3);
+      // O and C parts: off the serial chain, on the tensor pipe while the state epilogue works
+      if (c >= 2) {
+        mbar_wait(&bars.dofree[buf], ((c >> 1) - 1) & 1);   // O accumulator of chunk c - 2 has been read
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) umma_bf16_ts_ws(dob, sbt + j * 8, dQ + j * 16, idesc64, j > 0);
+      umma_commit_ws(&bars.emptyA[sa]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) umma_bf16_ts_ws(dob, tm + C::TM_VB + j * 8, dP + j * 16, idesc64, 1);
+      umma_commit_ws(&bars.dofull[buf]);
+      umma_commit_ws(&bars.emptyK[sk]);
+      TTR(4);
+      if (c + 1 < NT) {
+        // the v_new accumulator is free: both halves of v_new_c were read before they were published
+        mbar_wait(&bars.fullA[(c + 1) % C::NA], ((c + 1) / C::NA) & 1);
+        tc_fence_after();
+        issue_u(c + 1);
+      }
+      TTR(5);
+    }
+  } else if (warp < 6) {
+    // ------------------------------- v_new / output epilogue --------------------------
+    const int quad = warp & 3;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const int col = col0 + quad * 32 + lane;     // this thread's value column
+    uint32_t r[32], w[16];
+    auto output = [&](int c) {
+      const int buf = c & 1;
+      mbar_wait(&bars.dofull[buf], (c >> 1) & 1);
+      tc_fence_after();
+      const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
+      const int valid = varlen ? __ldg(vl.chunk_valid + cb + c) : min(GDN_C, T - tok0);
+      const size_t tstride = (size_t)H * GDN_V;
+      __nv_bfloat16* p0 = o + (((size_t)b * T + tok0) * H + h) * GDN_V + col;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        tmem_ld32(tlane + C::TM_DO + buf * 64 + hh * 32, r);
+        tmem_ld_wait();
+        if (hh == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.dofree[buf]);
+        }
+        // one 64-byte row segment per warp and token (the pointer advances by one token row)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (hh * 32 + i < valid) *p0 = __float2bfloat16(__uint_as_float(r[i]));
+          asm volatile("" : "+l"(p0));   // keep the increments serial
+          p0 += tstride;
+        }
+      }
+    };
+    for (int c = 0; c < NT; ++c) {
+      mbar_wait(&bars.dv, c & 1);
+      tc_fence_after();
+      if (quad == 0) TTR(6);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        tmem_ld32(tlane + C::TM_DV + hh * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        tmem_st16(tlane + C::TM_VB + hh * 16, w);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.vb[hh]);
+        if (quad == 0) TTR(7 + hh);
+      }
+      if (c > 0) output(c - 1);
+    }
+    output(NT - 1);
+  } else {
+    // ------------------------------- state warps ---------------------------------------
+    // four warps per TMEM lane quadrant: warp (quad, kq) owns key dims 32 * kq .. + 31 of its 32 value columns
+    const int quad = warp & 3, kq = (warp - 6) >> 2;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const int col = col0 + quad * 32 + lane;
+    float S[32];                                 // a quarter row of S^T (this value column, 32 key dims), fp32
+    const size_t sbase_off = (((size_t)seq * H + h) * GDN_K + kq * 32) * GDN_V + col;
+    if (h0 == nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) S[i] = 0.f;
+    } else if (h0_dtype == 0) {
+      const float* p = static_cast<const float*>(h0) + sbase_off;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) S[i] = __ldg(p + (size_t)i * GDN_V);
+    } else {
+      const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(h0) + sbase_off;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) S[i] = __bfloat162float(p[(size_t)i * GDN_V]);
+    }
+    uint32_t r[32];
+    auto publish = [&](int n) {   // bf16 S_n^T -> TMEM A operand of chunk n (word i = key dims 2i, 2i+1)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = pack_bf16(S[2 * i], S[2 * i + 1]);
+      tmem_st16(tlane + C::TM_SB + (n & 1) * 64 + kq * 16, r);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.sb[kq]);
+    };
+    publish(0);
+    for (int c = 0; c < NT; ++c) {
+      const int sk = c % C::NK;
+      mbar_wait(&bars.fullK[sk], (c / C::NK) & 1);
+      const float gamma = *reinterpret_cast<const float*>(smem + C::OFF_K + sk * C::KSLOT + C::K_TAIL);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.emptyK[sk]);
+      mbar_wait(&bars.ds, c & 1);
+      tc_fence_after();
+      if (warp == 8) TTR(9);
+      tmem_ld32(tlane + C::TM_DS + kq * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) S[i] = fmaf(gamma, S[i], __uint_as_float(r[i]));
+      if (warp == 8) TTR(10);
+      if (c + 1 < NT) {
+        // bf16 S_{c+1}^T goes into the other operand buffer: its last readers (W and O parts of chunk c - 1) were
+        // issued before the B part of chunk c, whose commit this warp has just seen
+        publish(c + 1);
+      } else {
+        tc_fence_before();
+      }
+      if (warp == 8) TTR(11);
+    }
+    if (ht != nullptr) {
+      if (ht_dtype == 0) {
+        float* p = static_cast<float*>(ht) + sbase_off;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[(size_t)i * GDN_V] = S[i];
+      } else {
+        __nv_bfloat16* p = static_cast<__nv_bfloat16*>(ht) + sbase_off;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[(size_t)i * GDN_V] = __float2bfloat16(S[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TM_COLS>(tmem);
+}
+
 typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -853,7 +1206,7 @@ EncodeTiledFnT encode_fn_t() {
 // v: the caller's value tensor [B, T, H, 256] bf16 (dense).  The scan reads its tiles directly (box = 64 value
 // columns x 64 tokens, 128-byte swizzle); rows past T are zero-filled by the TMA engine.
 cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, int B,
-                              const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int lag,
+                              const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int form,
                               cudaStream_t stream) {
   using C = TCfg;
   static std::atomic<bool> configured[64];
@@ -865,21 +1218,45 @@ cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVa
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gdn_scan_t2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg::SMEM);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gdn_scan_t3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3Cfg::SMEM);
+    if (e != cudaSuccess) return e;
     configured[dev].store(true, std::memory_order_release);
   }
-  EncodeTiledFnT enc = encode_fn_t();
-  if (!enc) return cudaErrorNotSupported;
+  // The value tensor's map is a pure function of (pointer, B, T, H): the last few are kept, so a layer that is called
+  // again with the same buffer (every step of a served model) does not re-encode -- and `ncu --replay-mode range`,
+  // which refuses cuTensorMapEncodeTiled inside a range, can profile a warmed-up call
+  struct MapKey { const void* v; int B, T, H; CUtensorMap tm; };
+  static std::mutex map_mu;
+  static MapKey map_cache[8];
+  static unsigned map_next = 0;
   CUtensorMap tm;
-  cuuint64_t dims[4] = {(cuuint64_t)GDN_V, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)GDN_V * 2, (cuuint64_t)H * GDN_V * 2, (cuuint64_t)T * H * GDN_V * 2};
-  cuuint32_t box[4] = {64, 1, 64, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v), dims, strides, box, estr,
-          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return cudaErrorInvalidValue;
+  bool hit = false;
+  {
+    std::lock_guard<std::mutex> lock(map_mu);
+    for (const MapKey& e : map_cache)
+      if (e.v == v && e.B == B && e.T == T && e.H == H) { tm = e.tm; hit = true; break; }
+  }
+  if (!hit) {
+    EncodeTiledFnT enc = encode_fn_t();
+    if (!enc) return cudaErrorNotSupported;
+    cuuint64_t dims[4] = {(cuuint64_t)GDN_V, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)GDN_V * 2, (cuuint64_t)H * GDN_V * 2, (cuuint64_t)T * H * GDN_V * 2};
+    cuuint32_t box[4] = {64, 1, 64, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lock(map_mu);
+    MapKey& e = map_cache[map_next++ % 8];
+    e.v = v; e.B = B; e.T = T; e.H = H; e.tm = tm;
+  }
   dim3 grid(2, H, nseq);
-  if (lag)
+  if (form == 3)
+    gdn_scan_t3_kernel<<<grid, T3Cfg::THREADS, T3Cfg::SMEM, stream>>>(tm, ws, vl, h0, h0_dtype,
+                                                                      static_cast<__nv_bfloat16*>(o), ht, ht_dtype, T, H,
+                                                                      ntrow);
+  else if (form == 2)
     gdn_scan_t2_kernel<<<grid, T2Cfg::THREADS, T2Cfg::SMEM, stream>>>(tm, ws, vl, h0, h0_dtype,
                                                                       static_cast<__nv_bfloat16*>(o), ht, ht_dtype, T, H,
                                                                       ntrow);

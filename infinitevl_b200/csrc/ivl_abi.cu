@@ -86,13 +86,17 @@ inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
-//   IVL_GDN_TSCAN 1 = transposed scan (gdn_scan_t.cu: two CTAs per head, state and v_new as TMEM A operands;
-//                 default), 0 = row-major scan (gdn_scan.cu: 32/64/128-column slices)
+//   IVL_GDN_TSCAN 1 = transposed scan (gdn_scan_t.cu: two CTAs per head, state and v_new as TMEM A operands),
+//                 0 = row-major scan (gdn_scan.cu: 32/64/128-column slices)
 //                 2 = transposed scan, lag form (shortened serial chain, N = 128 MMA chains over 128B-swizzled stacked
 //                     operands; prep also emits R = Wg Kt_prev^T).  Correct and deterministic, but measured slower
 //                     than form 1 on B200 (1207 vs 977 ns per chunk: tensor-memory reads and ~80-cycle TS-mode MMAs
 //                     bound both; profiles/r02_summary.md), so it is not the default.
-inline int tscan_mode() { const int m = env_int("IVL_GDN_TSCAN", 1); return (m >= 0 && m <= 2) ? m : 1; }
+//                 3 = transposed scan, pipelined form (default): the operands of form 1, but the state / v_new hand-offs
+//                     to the tensor pipe are pipelined over the contraction dimension and the output products leave
+//                     the serial chain (gdn_scan_t3_kernel)
+inline int tscan_mode() { const int m = env_int("IVL_GDN_TSCAN", 3); return (m >= 0 && m <= 3) ? m : 3; }
+inline int prep_mode(int tscan) { return tscan == 3 ? 1 : tscan; }   // form 3 reads the images of form 1
 inline bool tscan() { return tscan_mode() != 0; }
 inline int scan_bv(int dflt) {
   const int bv = env_int("IVL_GDN_BV", dflt);
@@ -240,7 +244,7 @@ int ivl_gdn_chunk_prep(const void* q, const void* k, const void* v, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T, H), st));
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, T, H,
-                                default_scale(scale, ivl::GDN_K), l2norm_qk, 0, tscan_mode(), st));
+                                default_scale(scale, ivl::GDN_K), l2norm_qk, 0, prep_mode(tscan_mode()), st));
   return IVL_OK;
 }
 
@@ -255,7 +259,7 @@ int ivl_gdn_chunk_scan(const void* v, const void* h0, int h0_dtype, void* o, voi
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T, H, /*ring=*/0);
   if (tscan())
     IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, B, h0, h0_dtype, o, ht, ht_dtype,
-                                    T, H, tscan_mode() == 2, static_cast<cudaStream_t>(stream)));
+                                    T, H, tscan_mode(), static_cast<cudaStream_t>(stream)));
   else
     IVL_CUDA(ivl::launch_gdn_scan(ws, ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, h0, h0_dtype, o, ht, ht_dtype, T, H,
                                   scan_bv(32), static_cast<cudaStream_t>(stream)));
@@ -309,9 +313,9 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   if (first || !fits || env_int("IVL_GDN_PIPE", overlap_default) == 0) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, trm, st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, prep_mode(trm), st));
     if (tr)
-      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm == 2, st));
+      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm, st));
     else
       IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
     return IVL_OK;
@@ -327,9 +331,9 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   if (other_busy) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, trm, st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, prep_mode(trm), st));
     if (tr)
-      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm == 2, st));
+      IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm, st));
     else
       IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
     return IVL_OK;
@@ -349,12 +353,12 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   IVL_CUDA(cudaEventRecord(fj->fork, st));
   IVL_CUDA(cudaStreamWaitEvent(fj->aux, fj->fork, 0));
   if (tr)
-    IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm == 2, st));
+    IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm, st));
   else
     IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, bv, st));
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv,
-                                trm, fj->aux));
+                                prep_mode(trm), fj->aux));
   IVL_CUDA(cudaEventRecord(fj->join, fj->aux));
   IVL_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   if (cap == cudaStreamCaptureStatusNone) {

@@ -116,7 +116,7 @@ def test_split_scan_is_bit_identical_at_full_size(ops):
     assert err_ratio(ro, o[:, T - tail:].float().cpu()) < TOL_O and err_ratio(rs, s.cpu()) < TOL_S
 
 
-@pytest.mark.parametrize("tscan", ["2", "1", "0"])
+@pytest.mark.parametrize("tscan", ["3", "2", "1", "0"])
 @pytest.mark.parametrize("T,H", [(2048, 16), (4160, 4), (100, 2)])
 def test_overlapped_and_sliced_variants_are_bit_identical(ops, monkeypatch, T, H, tscan):
     """ivl_gdn_chunk_fwd either runs prep then scan on the caller's stream or overlaps them on two streams
@@ -175,13 +175,16 @@ def test_transposed_and_row_major_scans_agree(ops, monkeypatch):
     rounded to bf16): they agree with each other far inside the oracle tolerance."""
     q, k, v, g, beta, h0 = _cuda(gdn_inputs(T=1536, H=4, seed=17))
     outs = {}
-    for tscan in ("2", "1", "0"):
+    for tscan in ("3", "2", "1", "0"):
         monkeypatch.setenv("IVL_GDN_TSCAN", tscan)
         outs[tscan] = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
                                                  use_qk_l2norm_in_kernel=True)
-    for a in ("1", "2"):
+    for a in ("1", "2", "3"):
         assert err_ratio(outs["0"][0].float(), outs[a][0].float()) < 5e-3
         assert err_ratio(outs["0"][1], outs[a][1]) < 5e-3
+    # the pipelined form (3, the default) issues the products of form 1 in a different order on the tensor pipe but
+    # sums every accumulator in the same order: bit-identical
+    assert torch.equal(outs["1"][0], outs["3"][0]) and torch.equal(outs["1"][1], outs["3"][1])
 
 
 def test_chunk_then_recurrent_streaming(ops):

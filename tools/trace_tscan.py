@@ -10,7 +10,7 @@ CS = os.path.join(ROOT, "infinitevl_b200", "csrc")
 out = "/tmp/libivl_trace.so"
 srcs = [os.path.join(CS, f) for f in B.SOURCES]
 subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC",
-                "--expt-relaxed-constexpr", "-DIVL_BUILDING_DLL", "-DIVL_TRACE", "-shared", "-I", os.path.join(ROOT, "include"), "-o", out] + srcs, check=True)
+                "--expt-relaxed-constexpr", "-DIVL_BUILDING_DLL", "-DIVL_TRACE", *os.environ.get("IVL_NVCC_EXTRA", "").split(), "-shared", "-I", os.path.join(ROOT, "include"), "-o", out] + srcs, check=True)
 lib = ctypes.CDLL(out)
 from inputs import gdn_inputs
 T = 131072
@@ -32,6 +32,12 @@ for _ in range(3):
     assert lib.ivl_gdn_chunk_prep(q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(), 1, T, 16, 0.0, 1, ws.data_ptr(), need, st) == 0
     assert lib.ivl_gdn_chunk_scan(v.data_ptr(), h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, 16, ws.data_ptr(), need, st) == 0
 torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record()
+for _ in range(5):
+    assert lib.ivl_gdn_chunk_scan(v.data_ptr(), h0.data_ptr(), 0, o.data_ptr(), ht.data_ptr(), 0, 1, T, 16, ws.data_ptr(), need, st) == 0
+ev[1].record(); torch.cuda.synchronize()
+print(f"scan alone (traced build, {os.environ.get('IVL_NVCC_EXTRA', '')}): {ev[0].elapsed_time(ev[1]) / 5:.3f} ms")
 buf = (ctypes.c_longlong * (64 * 16))()
 lib.ivl_debug_read_ttrace.argtypes = [ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
 assert lib.ivl_debug_read_ttrace(buf, 64 * 16) == 0
@@ -40,8 +46,12 @@ names2 = ["M1:vb(k) seen", "M1:B+RC issued", "M1:B issued", "M2:sb(k) seen", "M2
           "V:vb(k) arrived", "S:ds(k) seen", "S:ld+fma done", "S:xo(k) seen", "S:sb(k+1) arrived", "S:loop top", "S:fullS seen", "M1:dsfree seen"]
 names = ["M:sb seen", "M:W+O issued", "M:vb seen", "M:B+C issued", "M:U(c+1) issued", "V:dv seen", "V:ld done", "V:vb arrived",
          "V:output done", "S:ds seen", "S:ld+fma done", "S:sb arrived"]
+names3 = ["M:sb[0] seen", "M:W issued", "M:vb[0] seen", "M:B issued", "M:O+C issued", "M:U(c+1) issued", "V:dv seen", "V:vb[0] arrived",
+          "V:vb[1] arrived", "S:ds seen", "S:ld+fma done", "S:sb arrived"]
 if MODE == "2":
     names = names2
+if MODE == "3":
+    names = names3
 period = np.diff(t[:, 0])
 print("chunk period (cycles): median", np.median(period), "min", period.min(), "max", period.max())
 rel = t[:, :len(names)] - t[:, 0:1]
