@@ -32,10 +32,10 @@ HQ, HKV, D, WINDOW = 16, 2, 128, 8192
 GDN_BYTES_PER_TOKEN = 24672          # q,k,v,g,beta read + o written, per token per layer
 GDN_STATE_BYTES = 2 * H * K * V * 4  # h0 read + hT written, per sequence per layer
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE overlapped ivl_gdn_chunk_fwd call at T = 131072 (prep + scan
-# running concurrently), from the committed ncu range-replay capture profiles/r01h_range_overlapped.csv
-# (6 972 059 904 read + 4 007 053 568 written; an earlier build of the same design measured 9.42 GB -- how much of
-# the image traffic hits L2 depends on how far prep runs ahead); refreshed whenever the kernels change
-GDN_DRAM_TRAFFIC_NCU = 10979113472
+# running concurrently), from the committed ncu range-replay capture profiles/r02d_range_overlapped.csv
+# (transposed scan: 4 769 495 552 read + 3 204 179 200 written; the round-1 row-major scan with U slices measured
+# 10.98 GB, profiles/r01h_range_overlapped.csv); refreshed whenever the kernels change
+GDN_DRAM_TRAFFIC_NCU = 7973674752
 
 
 def swa_flops(T, Tk_prefix=0):
@@ -355,12 +355,13 @@ def run_ours(args):
         alg_bytes = GDN_BYTES_PER_TOKEN * T_local + GDN_STATE_BYTES
         achieved = alg_bytes / (t_layer * 1e-3) / 1e9
         roof = {"bound": "hbm",
-                "kernel": "gdn_chunk = gdn_prep_kernel + gdn_scan_kernel (one GDN layer; "
+                "kernel": "gdn_chunk = gdn_prep_kernel + gdn_scan_t3_kernel (one GDN layer; "
                           + ("overlapped on two streams, timed as one operator call" if world == 1 else "back to back") + ")",
                 "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": GDN_DRAM_TRAFFIC_NCU if (T_local == 131072 and world == 1) else None,
                 "traffic_note": "ncu --replay-mode range over one overlapped operator call (kernel replay would serialise "
-                                "the two kernels); back to back the two kernels move 6.46 + 4.03 GB; see profiles/r01e_summary.md",
+                                "the two kernels): prep reads q, k, g, beta and writes 64 KiB of operand images per chunk and head, the "
+                                "scan reads them back plus v and writes o; see profiles/r02_summary.md",
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg_bytes}
         kernels = {"gdn_layer_ms": round(t_layer, 4), "gdn_prep_alone_ms": round(t_prep, 4),
                    "gdn_scan_alone_ms": round(t_scan, 4)}
