@@ -253,7 +253,8 @@ class HotPath:
                 pending.wait()
             if n_out > self.T:
                 self.ho.post_send([kb[:, Hh + self.T - n_out:], vb[:, Hh + self.T - n_out:]])
-            self.swa.swa_attention_bthd(self.sq, kb[:, Hh - n_in:], vb[:, Hh - n_in:], window=WINDOW, out=self.so)
+            self.swa.swa_attention_bthd(self.sq, kb[:, Hh - n_in:], vb[:, Hh - n_in:], window=WINDOW, out=self.so,
+                                        key_pos0=self.rank * self.T - n_in)
             return 1
         self.swa.swa_attention_bthd(self.sq, self.sk, self.sv, window=WINDOW, out=self.so)
         return 1

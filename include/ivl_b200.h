@@ -177,6 +177,15 @@ IVL_API int ivl_gdn_recurrent_fwd(const void* q, const void* k, const void* v, c
 IVL_API int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides,
                         const void* v, const int64_t* v_strides, void* o, const int64_t* o_strides, int B,
                         int Tq, int Tk, int Hq, int Hkv, int D, int window, float scale, void* stream);
+/* Same, with the position of key 0 in its sequence (key_pos0 >= 0; ivl_swa_fwd passes 0).  The kernel anchors its
+ * 64-key tiles at absolute positions that are multiples of 64, so the result for a query does not depend on how its
+ * keys were delivered: cache + new tokens (key_pos0 = tokens seen before - cached keys), halo + local shard of a
+ * sequence-sharded prefill, or one long prefill all give BIT-IDENTICAL outputs (the sharded-vs-single parity gate of
+ * BASELINE.md 3c).  The ring-cache entry point derives the position from its device-side counter. */
+IVL_API int ivl_swa_fwd_pos(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides,
+                            const void* v, const int64_t* v_strides, void* o, const int64_t* o_strides, int B,
+                            int Tq, int Tk, int Hq, int Hkv, int D, int window, float scale, int64_t key_pos0,
+                            void* stream);
 
 /* Decode step of the same attention: ONE new query token per sequence (Tq == 1) against the
  * cached window, split over the key axis (HBM-bound).  q, o bf16 [B,1,Hq,128] contiguous; k, v as

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ivl_gdn_recurrent_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
                               + [c_float, c_int, c_void_p]),
     "ivl_swa_fwd": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, c_void_p]),
+    "ivl_swa_fwd_pos": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, ctypes.c_int64, c_void_p]),
     "ivl_swa_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ivl_swa_decode_fwd": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
     "ivl_swa_ring_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

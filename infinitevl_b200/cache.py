@@ -280,8 +280,10 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
         W = self.sliding_window
         if window is None or int(window) != W or Tq > self.max_append or Hq // self.num_kv_heads > 8 or W > 8192:
             # general case (long prefill into a cache, no window): the reference's concatenate-and-attend
+            pos0 = max(0, int(self.cumulative_length) - int(self.size))   # position of the first cached key
             fk, fv = self.update(k_bthd.transpose(1, 2), v_bthd.transpose(1, 2))
-            return swa.swa_attention_bthd(q_bthd, fk.transpose(1, 2), fv.transpose(1, 2), window=window, scale=scale)
+            return swa.swa_attention_bthd(q_bthd, fk.transpose(1, 2), fv.transpose(1, 2), window=window, scale=scale,
+                                          key_pos0=pos0)
         lib = _lib.load()
         stream = torch.cuda.current_stream(q_bthd.device).cuda_stream
         st3 = lambda t: (ctypes.c_int64 * 3)(t.stride(0), t.stride(1), t.stride(2))

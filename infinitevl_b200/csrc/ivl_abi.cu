@@ -33,7 +33,8 @@ cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, co
                                  float scale, int l2norm, cudaStream_t stream);
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
-                           int window, float scale, const int* ring_state, int ring_R, cudaStream_t stream);
+                           int window, float scale, const int* ring_state, int ring_R, long long key_pos0,
+                           cudaStream_t stream);
 size_t swa_ring_decode_workspace_bytes(int B, int Hq, int window);
 cudaError_t launch_swa_ring_decode(const void* q, const void* knew, long long kn_sb, long long kn_sh, const void* vnew,
                                    long long vn_sb, long long vn_sh, void* ring_k, void* ring_v, int* state,
@@ -185,7 +186,7 @@ inline ForkJoin* fork_join(cudaStream_t caller, bool* other_busy) {
 
 extern "C" {
 
-int ivl_abi_version(void) { return 2; }
+int ivl_abi_version(void) { return 3; }
 
 int ivl_stream_init(void* stream) {
   IVL_ARCH();
@@ -450,6 +451,14 @@ int ivl_gdn_decode_step(const void* q_in, const void* k_in, const void* v_in, co
 int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides, const void* v,
                 const int64_t* v_strides, void* o, const int64_t* o_strides, int B, int Tq, int Tk, int Hq, int Hkv,
                 int D, int window, float scale, void* stream) {
+  return ivl_swa_fwd_pos(q, q_strides, k, k_strides, v, v_strides, o, o_strides, B, Tq, Tk, Hq, Hkv, D, window, scale,
+                         0, stream);
+}
+
+int ivl_swa_fwd_pos(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides, const void* v,
+                    const int64_t* v_strides, void* o, const int64_t* o_strides, int B, int Tq, int Tk, int Hq, int Hkv,
+                    int D, int window, float scale, int64_t key_pos0, void* stream) {
+  if (key_pos0 < 0) return IVL_ERR_BAD_SHAPE;
   if (B <= 0 || Tq <= 0 || Tk < Tq || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || D != 128 || B > 65535)
     return IVL_ERR_BAD_SHAPE;
   if ((Tq + 127) / 128 > 65535) return IVL_ERR_BAD_SHAPE;
@@ -465,7 +474,7 @@ int ivl_swa_fwd(const void* q, const int64_t* q_strides, const void* k, const in
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
   IVL_ARCH();
   cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, B, Tq, Tk, Hq, Hkv, window, sc, nullptr, 0,
-                                      static_cast<cudaStream_t>(stream));
+                                      (long long)key_pos0, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 
@@ -533,7 +542,7 @@ int ivl_swa_ring_fwd(const void* q, const int64_t* q_strides, const void* ring_k
   IVL_ARCH();
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
   cudaError_t e = ivl::launch_swa_fwd(q, qs, ring_k, rs, ring_v, rs, o, os, B, Tq, 2 * R, Hq, Hkv, window, sc, state, R,
-                                      static_cast<cudaStream_t>(stream));
+                                      0, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 

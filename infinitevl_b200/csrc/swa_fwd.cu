@@ -67,6 +67,12 @@ struct SwaArgs {
   // stream: Tk = min(cum, W - 1 + Tq), the keys start at ring slot (cum - Tk) % R
   const int* ring_state;       // nullptr: plain [B, Tk, Hkv, D] keys
   int ring_R, ring_W;
+  // Position of key 0 in its sequence, modulo the key tile (ring cache: derived from the device counter).  The key
+  // tiles are anchored at ABSOLUTE multiples of 64, so a query sees the same tiles -- the same running maxima, the same
+  // bf16 roundings of P, the same summation order -- whether its keys arrive as one long prefill, as cache + new
+  // tokens, or as halo + local shard: chunked, streamed and sequence-sharded prefills are bit-identical to the
+  // one-shot prefill.  The partial first tile starts before key 0 (TMA zero-fills, the mask hides it).
+  int kalign;
 };
 
 // 2^x for a pair of values on the FMA pipe instead of the XU pipe (two MUFU.EX2): Cody-Waite range reduction
@@ -102,18 +108,19 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int h = blockIdx.x, mt = blockIdx.y, b = blockIdx.z;
   const int hk = h / a.group;
   const int i0 = mt * BM;
-  int koff = 0;
+  int koff = 0, kal = a.kalign;
   if (a.ring_state != nullptr) {
     const int cum = *reinterpret_cast<const volatile int*>(a.ring_state);
     a.Tk = min(cum, a.ring_W - 1 + a.Tq);
     koff = (cum - a.Tk) % a.ring_R;
+    kal = (cum - a.Tk) & (BN - 1);
     a.window = a.Tk > a.ring_W ? a.ring_W : 0;             // the window rule of the HF glue, evaluated on the device
   }
   const int shift = a.Tk - a.Tq;                           // bottom-right alignment
   const int p_first = i0 + shift;
   const int p_last = min(i0 + BM - 1, a.Tq - 1) + shift;
   const int lo_key = a.window > 0 ? max(0, p_first - a.window + 1) : 0;
-  const int t_lo = lo_key / BN, t_hi = min(p_last, a.Tk - 1) / BN;
+  const int t_lo = (lo_key + kal) / BN, t_hi = (min(p_last, a.Tk - 1) + kal) / BN;   // tiles of the ALIGNED key axis
   const int n_tiles = t_hi - t_lo + 1;
 
   if (tid == 0) {
@@ -141,7 +148,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto load_k = [&](int t) {
       const int s = t & 1;
       if (t >= 2) mbar_wait(&bars.emptyK[s], ((t >> 1) - 1) & 1);
-      const int j0 = (t_lo + t) * BN;
+      const int j0 = (t_lo + t) * BN - kal;   // may be negative for the first tile: zero-filled, masked
       uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullK[s], KT_BYTES_);
       tma_load_4d_ws(kd, &tmK, 0, hk, koff + j0, b, &bars.fullK[s]);
@@ -150,7 +157,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto load_v = [&](int t) {
       const int s = t & 1;
       if (t >= 2) mbar_wait(&bars.emptyV[s], ((t >> 1) - 1) & 1);
-      const int j0 = (t_lo + t) * BN;
+      const int j0 = (t_lo + t) * BN - kal;
       uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullV[s], KT_BYTES_);
       tma_load_4d_ws(vd, &tmV, 0, hk, koff + j0, b, &bars.fullV[s]);
@@ -218,7 +225,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint32_t r[32], r2[32];          // raw scores of keys 0..31 / 32..63 of the tile
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t & 1;
-      const int j0 = (t_lo + t) * BN;
+      const int j0 = (t_lo + t) * BN - kal;
       mbar_wait(&bars.s[s], (t >> 1) & 1);
       tc_fence_after();
       tmem_ld32(tlane + TM_S + s * BN, r);
@@ -229,13 +236,13 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&bars.sfree[s]);
       // masks only on boundary tiles (CTA-uniform test)
       const bool need_mask = (j0 + BN - 1 > p_first) || (a.window > 0 && j0 < p_last - a.window + 1) ||
-                             (j0 + BN > a.Tk);
+                             (j0 + BN > a.Tk) || (j0 < 0);
       if (need_mask) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int ja = j0 + i, jb = j0 + 32 + i;
-          const bool va = (ja <= pos) && (ja < a.Tk) && (a.window <= 0 || pos - ja < a.window);
-          const bool vb = (jb <= pos) && (jb < a.Tk) && (a.window <= 0 || pos - jb < a.window);
+          const bool va = (ja >= 0) && (ja <= pos) && (ja < a.Tk) && (a.window <= 0 || pos - ja < a.window);
+          const bool vb = (jb >= 0) && (jb <= pos) && (jb < a.Tk) && (a.window <= 0 || pos - jb < a.window);
           r[i] = va ? r[i] : 0xff800000u;   // -inf
           r2[i] = vb ? r2[i] : 0xff800000u;
         }
@@ -364,7 +371,8 @@ bool make_map(CUtensorMap* m, const void* ptr, int B, int T, int Hn, long long s
 // visible keys are derived on the device (SwaArgs::ring_state); window must be > 0.
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
-                           int window, float scale, const int* ring_state, int ring_R, cudaStream_t stream) {
+                           int window, float scale, const int* ring_state, int ring_R, long long key_pos0,
+                           cudaStream_t stream) {
   // IVL_SWA_POLY (developer knob): pairs out of 8 whose exponentials run on the FMA pipe
   int poly = SWA_POLY_DEFAULT;
   if (const char* e = getenv("IVL_SWA_POLY")) poly = atoi(e);
@@ -393,6 +401,7 @@ cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, co
   a.Tq = Tq; a.Tk = Tk; a.Hq = Hq; a.group = Hq / Hkv;
   a.window = (window > 0 && Tk > window) ? window : 0;  // HF glue passes the window only when key_len > W
   a.ring_state = ring_state; a.ring_R = ring_R; a.ring_W = window;
+  a.kalign = (int)(key_pos0 & (BN - 1));
   a.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(Hq, (Tq + BM - 1) / BM, B);
   kern<<<grid, SWA_THREADS, SWA_SMEM, stream>>>(tq, tk, tv, a);

@@ -361,7 +361,11 @@ class InfiniteVLSelfAttention(nn.Module):
             out = layer.attend(q, k, v, self.scaling, self.sliding_window)
             out = self.o_proj(out.reshape(B, q_len, self.num_heads * self.head_dim))
             return out, None
+        key_pos0 = 0
         if past_key_values is not None:
+            # position of the first visible key = tokens seen before this call - cached keys (Python integers of
+            # the cache, as in the reference): anchors the kernel's key tiles at absolute positions
+            key_pos0 = max(0, int(getattr(layer, "cumulative_length", 0)) - int(getattr(layer, "size", 0)))
             key_states, value_states = past_key_values.update(
                 layer_idx=self.layer_idx, key_states=key_states, value_states=value_states, conv_state=None,
                 recurrent_state=None, cache_kwargs={"sin": sin, "cos": cos, "cache_position": cache_position})
@@ -372,7 +376,7 @@ class InfiniteVLSelfAttention(nn.Module):
             attention_mask = None if kv_offset != 0 else attention_mask[:, kv_offset:kv_offset + kv_len]
         out, _ = swa.sliding_window_attention_forward(self, q.transpose(1, 2), key_states, value_states,
                                                       attention_mask, dropout=0.0, scaling=self.scaling,
-                                                      sliding_window=self.sliding_window)
+                                                      sliding_window=self.sliding_window, key_position_offset=key_pos0)
         out = self.o_proj(out.reshape(B, q_len, self.num_heads * self.head_dim))
         return out, None
 

@@ -25,9 +25,12 @@ def _strides3(t: torch.Tensor):
 
 
 def swa_attention_bthd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window: Optional[int] = None,
-                       scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
+                       key_pos0: int = 0) -> torch.Tensor:
     """q [B,Tq,Hq,128], k/v [B,Tk,Hkv,128] (bf16; arbitrary batch/time/head strides) -> out [B,Tq,Hq,128].
-    Causal with bottom-right alignment; ``window`` keys visible (self included) once Tk > window."""
+    Causal with bottom-right alignment; ``window`` keys visible (self included) once Tk > window.
+    ``key_pos0``: position of k[:, 0] in its sequence (cache + new tokens, halo + shard): the kernel tiles the keys at
+    absolute multiples of 64, so the output is bit-identical to the one-shot prefill of the whole sequence."""
     if not q.is_cuda:
         raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
     assert q.dtype == k.dtype == v.dtype == torch.bfloat16, "SWA kernel computes in bf16"
@@ -54,17 +57,17 @@ def swa_attention_bthd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window
                                       ws.data_ptr(), ws.numel(), torch.cuda.current_stream(q.device).cuda_stream)
         _lib.check(code, "ivl_swa_decode_fwd")
         return out
-    code = lib.ivl_swa_fwd(q.data_ptr(), _strides3(q), k.data_ptr(), _strides3(k), v.data_ptr(), _strides3(v),
-                           out.data_ptr(), _strides3(out), B, Tq, Tk, Hq, Hkv, D, int(window or 0),
-                           float(scale or 0.0), torch.cuda.current_stream(q.device).cuda_stream)
-    _lib.check(code, "ivl_swa_fwd")
+    code = lib.ivl_swa_fwd_pos(q.data_ptr(), _strides3(q), k.data_ptr(), _strides3(k), v.data_ptr(), _strides3(v),
+                               out.data_ptr(), _strides3(out), B, Tq, Tk, Hq, Hkv, D, int(window or 0),
+                               float(scale or 0.0), int(key_pos0), torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(code, "ivl_swa_fwd_pos")
     return out
 
 
 def swa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window: Optional[int] = None,
-                  scale: Optional[float] = None) -> torch.Tensor:
+                  scale: Optional[float] = None, key_pos0: int = 0) -> torch.Tensor:
     """HF head-first layout: q [B,Hq,Tq,D], k/v [B,Hkv,Tk,D] -> [B,Tq,Hq,D]."""
-    return swa_attention_bthd(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), window, scale)
+    return swa_attention_bthd(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), window, scale, key_pos0=key_pos0)
 
 
 def sliding_window_attention_forward(module, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
@@ -81,5 +84,7 @@ def sliding_window_attention_forward(module, query: torch.Tensor, key: torch.Ten
         raise NotImplementedError("attention dropout is not supported (inference / dropout=0 training only)")
     if scaling is None:
         scaling = query.shape[-1] ** -0.5
-    out = swa_attention(query, key, value, window=sliding_window, scale=scaling)
+    # key_position_offset (extension keyword): position of key[:, :, 0] in the sequence, see swa_attention_bthd
+    out = swa_attention(query, key, value, window=sliding_window, scale=scaling,
+                        key_pos0=int(kwargs.get("key_position_offset", 0) or 0))
     return out, None

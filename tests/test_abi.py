@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.ivl_abi_version() == 2
+    assert lib.ivl_abi_version() == 3
     assert lib.ivl_strerror(0) == b"ok"
     assert b"shape" in lib.ivl_strerror(-1)
     assert lib.ivl_strerror(-12345) == b"unknown error"
