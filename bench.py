@@ -334,15 +334,23 @@ def run_ours(args):
                      "pipelined_ms_per_step": round(ms_step, 3),
                      "ideal_wavefront_efficiency": round((N_GDN_LAYERS + N_SWA_LAYERS) / (N_GDN_LAYERS + N_SWA_LAYERS + world - 1), 4)}
         if not args.no_parity:
-            par = hp.ivl_dist.sharded_parity_check(T=min(T, 32768) if T % (64 * world) == 0 else 64 * world * 8, num_layers=8)
-            par_t = torch.zeros(4, device=dev)
+            Tp = min(T, 32768) if T % (64 * world) == 0 else 64 * world * 8
+            op = hp.ivl_dist.operator_parity_check(T=Tp)
+            par = hp.ivl_dist.sharded_parity_check(T=Tp, num_layers=8)
+            keys = ("out", "state", "kv", "conv", "oneshot_out", "oneshot_out_chunked_on_one_gpu", "oneshot_state")
+            par_t = torch.zeros(len(keys) + 2, device=dev)
             if par:
-                par_t = torch.tensor([par["out"], par["state"], par["kv"], 1.0 if par["ints_equal"] else 0.0], device=dev)
+                par_t = torch.tensor([par[k] for k in keys] + [1.0 if par["ints_equal"] else 0.0,
+                                                                 1.0 if par["bit_identical"] else 0.0], device=dev)
             dist.all_reduce(par_t, op=dist.ReduceOp.MAX)
             pl = par_t.tolist()
-            dist_info["parity_err"] = {"out": pl[0], "state": pl[1], "kv": pl[2], "ints_equal": bool(pl[3]),
-                                       "what": "dist.sharded_prefill (HybridDecoder, 8 layers, 3B mixer dims, T=%d) over NCCL vs the "
-                                               "same decoder on one GPU; RMS error ratio, gate 1e-3" % min(T, 32768)}
+            dist_info["parity_err"] = {
+                "operators": op,
+                "decoder": dict({k: pl[i] for i, k in enumerate(keys)}, ints_equal=bool(pl[-2]), bit_identical=bool(pl[-1])),
+                "what": "operators: the two hot-path operators with the NCCL neighbour hand-off vs the one-shot call on the "
+                        "whole sequence (T=%d), bit for bit.  decoder: dist.sharded_prefill (HybridDecoder, 8 layers, 3B "
+                        "mixer dims) vs the same token ranges run one after the other on one GPU (out/state/kv/conv: RMS "
+                        "error ratio, must be 0) and vs one call over the whole sequence (oneshot_*: gate 1e-3, BASELINE.md 3c)" % Tp}
 
     # ---- per-kernel timing for the roofline (device events on the launching stream) --------------
     roof = None

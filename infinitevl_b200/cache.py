@@ -177,6 +177,7 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
         self._state = torch.zeros(2 + self.batch_size * self.num_kv_heads, dtype=torch.int32, device=self.device)
         self._size = 0
         self._cum = 0
+        self._pend_size = self._pend_cum = None
         self._dirty = False
         self._ws = None
 
@@ -188,19 +189,23 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
         s = self._start()
         return ring[:, s:s + n].permute(0, 2, 1, 3)          # [B, Hkv, n, D] view
 
-    size = property(lambda self: self._size)
-    cumulative_length = property(lambda self: self._cum)
+    # Writes to `size` / `cumulative_length` from outside (the demo's clone protocol, the sharded hand-off) are held
+    # as PENDING values until the next call re-anchors the ring: until then the `_buf_*` / `keys` views keep pointing
+    # at the rows the outside writer has filled (rows [0, n) of the window as it was anchored when it wrote), exactly
+    # as the reference's fixed `_buf_keys[:, :, :n]` does.
+    size = property(lambda self: self._size if self._pend_size is None else self._pend_size)
+    cumulative_length = property(lambda self: self._cum if self._pend_cum is None else self._pend_cum)
 
     @size.setter
     def size(self, v):
-        self._size, self._dirty = int(v), True
+        self._pend_size, self._dirty = int(v), True
 
     @cumulative_length.setter
     def cumulative_length(self, v):
-        self._cum, self._dirty = int(v), True
+        self._pend_cum, self._dirty = int(v), True
 
-    keys = property(lambda self: self._window(self._ring_k, self._size))
-    values = property(lambda self: self._window(self._ring_v, self._size))
+    keys = property(lambda self: self._window(self._ring_k, self.size))
+    values = property(lambda self: self._window(self._ring_v, self.size))
     _buf_keys = property(lambda self: self._window(self._ring_k, self.capacity))
     _buf_values = property(lambda self: self._window(self._ring_v, self.capacity))
 
@@ -215,13 +220,14 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
     def _resync(self) -> None:
         """After size / cumulative_length (and the window contents, through the views) were written from outside:
         rewrite both ring copies of the window and the device counter."""
-        n = self._size
-        k = self._window(self._ring_k, n).clone()
+        n, cum = self.size, self.cumulative_length          # the values written from outside (or the current ones)
+        k = self._window(self._ring_k, n).clone()           # rows [0, n) of the window as anchored BEFORE the writes
         v = self._window(self._ring_v, n).clone()
+        self._pend_size = self._pend_cum = None
         self._state.zero_()
-        self._state[0] = self._cum - n
+        self._state[0] = cum - n
         self._dirty = False
-        self._cum -= n
+        self._cum = cum - n
         self._size = 0
         if n > 0:
             self._append(k.transpose(1, 2), v.transpose(1, 2))
@@ -312,6 +318,8 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
     def crop(self, max_length: int) -> None:
         if self.get_seq_length() >= self.sliding_window:
             raise ValueError("Cropping is forbidden after filling SWA window (to avoid state loss)")
+        if self._dirty:
+            self._resync()
         new_size = max(0, self._size - abs(max_length)) if max_length < 0 else min(self._size, max_length)
         k = self._window(self._ring_k, self._size)[:, :, self._size - new_size:].clone()
         v = self._window(self._ring_v, self._size)[:, :, self._size - new_size:].clone()
@@ -321,6 +329,7 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
 
     def reset(self) -> None:
         self._size = self._cum = 0
+        self._pend_size = self._pend_cum = None
         self._dirty = False
         self._state.zero_()
 
@@ -330,6 +339,7 @@ class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
         `keys` on the host again."""
         self._cum = int(self._state[0].item())
         self._size = min(self.capacity, self._cum)
+        self._pend_size = self._pend_cum = None
         self._dirty = False
 
     # -- snapshots (SURVEY.md 8 f-3: branch a stream for a question, resume a stream from disk) ---------------------------
@@ -514,6 +524,7 @@ class StaticCachePrealloc(_HFCache):
             if getattr(s_, "is_ring", False):
                 d._ring_k.copy_(s_._ring_k); d._ring_v.copy_(s_._ring_v); d._state.copy_(s_._state)
                 d._size, d._cum, d._dirty = s_._size, s_._cum, s_._dirty
+                d._pend_size, d._pend_cum = s_._pend_size, s_._pend_cum
             elif getattr(s_, "is_sliding", False):
                 d._buf_keys.copy_(s_._buf_keys); d._buf_values.copy_(s_._buf_values)
                 d.size, d.cumulative_length = s_.size, s_.cumulative_length

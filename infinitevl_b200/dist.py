@@ -218,15 +218,87 @@ def gdn_layer_sharded(ho: OperatorHandOff, prep: Callable[[], None], scan: Calla
 
 
 # ------------------------------------------------------------------------------------------------
-# parity of the sharded run against the one-GPU run (error ratio <= 1e-3)
+# parity of the sharded run against the one-GPU run
 # ------------------------------------------------------------------------------------------------
+def _err(ref: torch.Tensor, y: torch.Tensor) -> float:
+    ref, y = ref.float(), y.float()
+    return float(((ref - y).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-30)).item())
+
+
+def operator_parity_check(T: int = 32768, seed: int = 0, group=None) -> dict:
+    """The hot path itself (the two operators, no projections): every rank builds the SAME full-length inputs, runs
+    its token range with the neighbour hand-off of `OperatorHandOff` / `gdn_layer_sharded` over the process group, and
+    compares its outputs with the matching slice of the one-shot operator call on the whole sequence, which it also
+    runs.  The kernels are deterministic, the state travels in fp32 and the SWA key tiles are anchored at absolute
+    positions, so the sharded run must reproduce the one-shot run BIT FOR BIT.  Returns the same dict on every rank:
+    {"gdn_o_equal", "gdn_state_equal", "swa_equal"} (logical AND over the ranks) and the worst error ratios."""
+    from . import ops, swa
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    s, e = shard_range(T, world, rank)
+    Tl = e - s
+    H, K, V, HQ, HKV, D, W = 16, 128, 256, 16, 2, 128, 8192
+    gen = torch.Generator().manual_seed(seed)
+    q = torch.randn(1, T, H, K, generator=gen).bfloat16().to(dev)
+    k = torch.randn(1, T, H, K, generator=gen).bfloat16().to(dev)
+    v = torch.randn(1, T, H, V, generator=gen).bfloat16().to(dev)
+    g = (-torch.rand(1, T, H, generator=gen) * 0.1).float().to(dev)
+    beta = torch.rand(1, T, H, generator=gen).bfloat16().to(dev)
+    h0 = (torch.randn(1, H, K, V, generator=gen) * 0.1).float().to(dev)
+    ref_o, ref_s = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
+                                              use_qk_l2norm_in_kernel=True)
+    ho = OperatorHandOff(rank, world, group)
+    state_in, state_out = torch.empty_like(h0), torch.empty_like(h0)
+    pend = ho.post_recv([state_in])
+    if pend is not None:
+        pend.wait()
+    o, _ = ops.chunk_gated_delta_rule(q[:, s:e].contiguous(), k[:, s:e].contiguous(), v[:, s:e].contiguous(),
+                                      g[:, s:e].contiguous(), beta[:, s:e].contiguous(),
+                                      initial_state=h0 if rank == 0 else state_in, output_final_state=True,
+                                      use_qk_l2norm_in_kernel=True, state_out=state_out)
+    ho.post_send([state_out])
+    ho.drain()
+    flags = [float(torch.equal(o, ref_o[:, s:e])), float(torch.equal(state_out, ref_s)) if rank == world - 1 else 1.0]
+    errs = [_err(ref_o[:, s:e], o), _err(ref_s, state_out) if rank == world - 1 else 0.0]
+    # SWA: halo of the last W-1 keys/values from the previous rank(s) in front of the local ones
+    sq = torch.randn(1, T, HQ, D, generator=gen).bfloat16().to(dev)
+    sk = torch.randn(1, T, HKV, D, generator=gen).bfloat16().to(dev)
+    sv = torch.randn(1, T, HKV, D, generator=gen).bfloat16().to(dev)
+    ref_a = swa.swa_attention_bthd(sq, sk, sv, window=W)
+    Hh = W - 1
+    n_in, n_out = min(Hh, s), min(Hh, e)
+    kb = torch.zeros(1, Hh + Tl, HKV, D, dtype=torch.bfloat16, device=dev)
+    vb = torch.zeros_like(kb)
+    kb[:, Hh:].copy_(sk[:, s:e])
+    vb[:, Hh:].copy_(sv[:, s:e])
+    pend = ho.post_recv([kb[:, Hh - n_in:Hh], vb[:, Hh - n_in:Hh]]) if n_in else None
+    if pend is not None:
+        pend.wait()
+    ho.post_send([kb[:, Hh + Tl - n_out:], vb[:, Hh + Tl - n_out:]])
+    a = swa.swa_attention_bthd(sq[:, s:e], kb[:, Hh - n_in:], vb[:, Hh - n_in:], window=W, key_pos0=s - n_in)
+    ho.drain()
+    flags.append(float(torch.equal(a, ref_a[:, s:e])))
+    errs.append(_err(ref_a[:, s:e], a))
+    ft = torch.tensor(flags, device=dev)
+    et = torch.tensor(errs, device=dev)
+    dist.all_reduce(ft, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(et, op=dist.ReduceOp.MAX, group=group)
+    f, er = ft.tolist(), et.tolist()
+    return {"gdn_o_equal": bool(f[0]), "gdn_state_equal": bool(f[1]), "swa_equal": bool(f[2]),
+            "gdn_o_err": er[0], "gdn_state_err": er[1], "swa_err": er[2], "T": T, "world": world}
+
+
 def sharded_parity_check(T: int = 32768, num_layers: int = 8, seed: int = 0, group=None, config=None) -> dict:
     """Every rank builds the same HybridDecoder (3B mixer dims, `num_layers` layers in the model's 1 SWA : 3 GDN
-    pattern, mixers only) and the same inputs; the ranks run `sharded_prefill` over NCCL, the last rank also runs
-    the whole sequence alone, and the rank-concatenated output and the last rank's cache are compared with that
-    run.  The DeltaNet state is handed over (and cached) in fp32, as `sharded_prefill` callers should.
-    Returns {"out": err, "state": max err over GDN layers, "conv": ..., "kv": max err over SWA layers} on the
-    last rank, {} elsewhere."""
+    pattern, mixers only) and the same inputs; the ranks run `sharded_prefill` over NCCL.  The last rank also runs
+    (a) the same token ranges ONE AFTER THE OTHER through one cache on its own GPU -- the identical computation
+    without the network: the sharded run must match it bit for bit (keys "out", "state", "conv", "kv": error ratios,
+    gate 0) -- and (b) the whole sequence in one call ("oneshot_*").  The hot-path operators are bit-identical
+    between (a) and (b) (`operator_parity_check`); the only thing that may differ is cuBLAS, should it pick a
+    different kernel for the projections at a different number of rows.  Measured on B200 (profiles/r02_summary.md):
+    0.0 everywhere at P = 2 -- the sharded prefill reproduces the one-call prefill bit for bit.  The DeltaNet state
+    is handed over in fp32.
+    Returns the dict on the last rank, {} elsewhere."""
     from .modeling import HybridDecoder, HybridTextConfig
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -247,22 +319,50 @@ def sharded_parity_check(T: int = 32768, num_layers: int = 8, seed: int = 0, gro
     dist.all_gather(parts, out.contiguous(), group=group)
     res = {}
     if rank == world - 1:
-        def err(ref, y):
-            ref, y = ref.float(), y.float()
-            return float(((ref - y).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-30)).item())
-        rcache = dec.allocate_inference_cache(1, state_dtype=torch.float32)
-        ref = dec(x, position_ids=pos, past_key_values=rcache)
-        res = {"out": err(ref, torch.cat(parts, 1)), "state": 0.0, "conv": 0.0, "kv": 0.0, "ints_equal": True,
-               "T": T, "layers": num_layers, "world": world}
-        for a, b in zip(cache.layers, rcache.layers):
+        got = torch.cat(parts, 1)
+        # (a) the same ranges, one after the other, on this GPU
+        ccache = dec.allocate_inference_cache(1, state_dtype=torch.float32)
+        outs = []
+        for r in range(world):
+            rs, re_ = shard_range(T, world, r)
+            o_r, ccache = _local_range(dec, x[:, rs:re_], pos[:, :, rs:re_], rs, re_, ccache)
+            outs.append(o_r)
+        chunked = torch.cat(outs, 1)
+        res = {"out": _err(chunked, got), "state": 0.0, "conv": 0.0, "kv": 0.0, "ints_equal": True,
+               "bit_identical": bool(torch.equal(chunked, got)), "T": T, "layers": num_layers, "world": world}
+        for a, b in zip(cache.layers, ccache.layers):
             if a.is_sliding:
                 res["ints_equal"] &= (a.size == b.size and a.cumulative_length == b.cumulative_length)
-                res["kv"] = max(res["kv"], err(b.keys, a.keys), err(b.values, a.values))
+                res["kv"] = max(res["kv"], _err(b.keys, a.keys), _err(b.values, a.values))
             else:
                 res["ints_equal"] &= a.seq_len == b.seq_len
-                res["state"] = max(res["state"], err(b.recurrent_state, a.recurrent_state))
-                res["conv"] = max(res["conv"], err(b.conv_state_v, a.conv_state_v))
-        del rcache, ref
+                res["state"] = max(res["state"], _err(b.recurrent_state, a.recurrent_state))
+                res["conv"] = max(res["conv"], _err(b.conv_state_v, a.conv_state_v))
+        # (b) one call over the whole sequence
+        rcache = dec.allocate_inference_cache(1, state_dtype=torch.float32)
+        ref = dec(x, position_ids=pos, past_key_values=rcache)
+        res["oneshot_out"] = _err(ref, got)
+        res["oneshot_out_chunked_on_one_gpu"] = _err(ref, chunked)
+        res["oneshot_state"] = max(_err(b.recurrent_state, a.recurrent_state)
+                                   for a, b in zip(cache.layers, rcache.layers) if not a.is_sliding)
+        del rcache, ref, ccache, chunked, got
     del dec, x, cache, out, parts
     torch.cuda.empty_cache()
     return res
+
+
+def _local_range(decoder, x_local, pos_local, start, end, cache):
+    """One token range of a prefill through `cache` on this device (no hand-off): what a rank of `sharded_prefill`
+    computes between its receive and its send."""
+    from .modeling import mrope_select
+    cache_position = torch.arange(start, end, device=x_local.device)
+    cos, sin = decoder.rotary_emb(x_local, pos_local)
+    cos, sin = mrope_select(cos, sin, decoder.config.rope_scaling["mrope_section"])
+    h = x_local
+    for layer in decoder.layers:
+        if decoder.mixers_only:
+            h = h + layer.self_attn(hidden_states=layer.input_layernorm(h), past_key_values=cache,
+                                    cache_position=cache_position, position_embeddings=(cos, sin))[0]
+        else:
+            h = layer(h, past_key_values=cache, cache_position=cache_position, position_embeddings=(cos, sin))[0]
+    return decoder.norm(h), cache

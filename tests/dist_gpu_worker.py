@@ -8,7 +8,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from infinitevl_b200.dist import sharded_parity_check  # noqa: E402
+from infinitevl_b200.dist import operator_parity_check, sharded_parity_check  # noqa: E402
 
 
 def main():
@@ -20,6 +20,9 @@ def main():
         res = sharded_parity_check(T=T, num_layers=8)
         if res:
             print("DIST_PARITY " + json.dumps(res), flush=True)
+        op = operator_parity_check(T=T)
+        if dist.get_rank() == 0:
+            print("OP_PARITY " + json.dumps(op), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

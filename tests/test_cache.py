@@ -174,6 +174,16 @@ def test_ring_layer_equals_reference_layer_on_the_reference_trace():
     kk = torch.full((1, 1, 2, 4), 99.0)
     a, b = rng.update(kk, kk), dst.update(kk, kk)
     assert torch.equal(a[0], b[0]) and torch.equal(rng.keys, dst.keys) and int(dst._state[0]) == int(rng._state[0])
+    # the other order (dist.recv_cache_layer: rows first, integers afterwards), into a layer with its own history
+    dst2 = mk(True)
+    dst2.update(torch.ones(1, 1, 5, 4), torch.ones(1, 1, 5, 4))
+    L = rng.size
+    dst2._buf_keys[:, :, :L, :].copy_(rng._buf_keys[:, :, :L, :])
+    dst2._buf_values[:, :, :L, :].copy_(rng._buf_values[:, :, :L, :])
+    dst2.size, dst2.cumulative_length = rng.size, rng.cumulative_length
+    assert torch.equal(dst2.keys, rng.keys) and torch.equal(dst2.values, rng.values)
+    a, b = rng.update(kk, kk), dst2.update(kk, kk)
+    assert torch.equal(a[0], b[0]) and torch.equal(rng.keys, dst2.keys) and int(dst2._state[0]) == int(rng._state[0])
     # snapshot / restore
     again = mk(True)
     again.load_state_dict(rng.state_dict())
