@@ -143,7 +143,7 @@ class HotPath:
         # (no reuse hazards between the transfers of neighbouring layers)
         from infinitevl_b200 import dist as ivl_dist
         self.ivl_dist = ivl_dist
-        self.ho = ivl_dist.OperatorHandOff(rank, world) if world > 1 else None
+        self.ho = ivl_dist.OperatorHandOff(rank, world, dry=os.environ.get("IVL_BENCH_NOCOMM", "0") == "1") if world > 1 else None
         if world > 1:
             self.state_ins = [torch.empty_like(self.h0) for _ in range(N_GDN_LAYERS)]
             self.hts = [torch.empty_like(self.h0) for _ in range(N_GDN_LAYERS)]
@@ -170,6 +170,25 @@ class HotPath:
             self.has_swa = True
         except ImportError:
             self.has_swa = False
+        # neighbour hand-off through peer memory (dist.PeerLink: copy engines + stream-ordered flags, no NCCL kernels);
+        # IVL_SHARD_TRANSPORT=nccl keeps the isend / irecv path
+        self.link = None
+        self.transport = "nccl"
+        if world > 1 and os.environ.get("IVL_SHARD_TRANSPORT", "p2p") == "p2p" and os.environ.get("IVL_BENCH_NOCOMM", "0") != "1":
+            try:
+                Hh = WINDOW - 1
+                n_in = min(Hh, rank * T_local)
+                boxes = {f"S{g}": self.state_ins[g] for g in range(N_GDN_LAYERS)}
+                if self.has_swa:
+                    for i in range(N_SWA_LAYERS):
+                        boxes[f"K{i}"] = self.kbufs[i][:, Hh - n_in:Hh] if n_in else None
+                        boxes[f"V{i}"] = self.vbufs[i][:, Hh - n_in:Hh] if n_in else None
+                link = ivl_dist.PeerLink(rank, world, None, device)
+                link.open(boxes)
+                self.link, self.transport = link, "p2p"
+                self.ho.dry = True
+            except Exception as e:  # noqa: BLE001  (no IPC / no peer access on this box: NCCL carries the hand-off)
+                print(f"[bench] peer-memory hand-off unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
 
     # -- single kernels (for the roofline timing) ---------------------------------------------
     def gdn_prep(self):
@@ -191,6 +210,13 @@ class HotPath:
         self._lib_mod.check(self.lib.ivl_gdn_chunk_fwd(
             self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.g.data_ptr(), self.beta.data_ptr(),
             h0.data_ptr(), 0, self.o.data_ptr(), self.ht.data_ptr(), 0, 1, self.T, H, K, V, 0.0, 1,
+            self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_fwd")
+
+    def gdn_fwd_into(self, h0, ht):
+        st = torch.cuda.current_stream().cuda_stream
+        self._lib_mod.check(self.lib.ivl_gdn_chunk_fwd(
+            self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.g.data_ptr(), self.beta.data_ptr(),
+            h0.data_ptr(), 0, self.o.data_ptr(), ht.data_ptr(), 0, 1, self.T, H, K, V, 0.0, 1,
             self.ws.data_ptr(), self.ws.numel(), st), "ivl_gdn_chunk_fwd")
 
     def gdn_scan_into(self, h0, ht):
@@ -219,7 +245,14 @@ class HotPath:
         n = 0
         L = N_GDN_LAYERS + N_SWA_LAYERS
         nxt = self._post_recv(0)
+        trace = getattr(self, "layer_trace", None)   # developer probe: one event per layer (IVL_BENCH_LAYER_TRACE=1)
+        if trace is not None:
+            trace.append([])
         for layer in range(L):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=os.environ.get("IVL_BENCH_LAYER_TRACE") != "3")
+                ev.record()
+                trace[-1].append(ev)
             cur, nxt = nxt, self._post_recv(layer + 1)
             if layer % 4 == 0:
                 if self.has_swa:
@@ -230,11 +263,24 @@ class HotPath:
                 n += 2
                 continue
             g = layer - layer // 4 - 1
+            if self.link is not None:
+                lk, name = self.link, f"S{g}"
+                lk.wait(name)
+                lk.before_overwrite(name)
+                self.gdn_fwd_into(self.h0 if self.rank == 0 else self.state_ins[g], self.hts[g])
+                lk.release(name)
+                lk.send(name, self.hts[g])
+                n += 2
+                continue
+            overlap = os.environ.get("IVL_SHARD_GDN", "overlap") == "overlap"
             self.ivl_dist.gdn_layer_sharded(self.ho, self.gdn_prep, lambda h0, g=g: self.gdn_scan_into(h0, self.hts[g]),
-                                            self.h0, self.state_ins[g], self.hts[g], cur)
+                                            self.h0, self.state_ins[g], self.hts[g], cur,
+                                            fwd=(lambda h0, g=g: self.gdn_fwd_into(h0, self.hts[g])) if overlap else None)
             n += 2
         if self.ho is not None:
             self.ho.drain()
+        if self.link is not None:
+            self.link.drain()
         self.launches_per_step = n
         return n
 
@@ -244,6 +290,22 @@ class HotPath:
             kb, vb = self.kbufs[i], self.vbufs[i]
             n_in = min(Hh, self.rank * self.T)
             n_out = min(Hh, (self.rank + 1) * self.T)
+            if self.link is not None:
+                lk = self.link
+                send = lambda: (lk.send(f"K{i}", kb[:, Hh + self.T - n_out:]), lk.send(f"V{i}", vb[:, Hh + self.T - n_out:]))
+                if n_out <= self.T:
+                    send()
+                if n_in:
+                    lk.wait(f"K{i}")
+                    lk.wait(f"V{i}")
+                if n_out > self.T:
+                    send()
+                self.swa.swa_attention_bthd(self.sq, kb[:, Hh - n_in:], vb[:, Hh - n_in:], window=WINDOW, out=self.so,
+                                            key_pos0=self.rank * self.T - n_in)
+                if n_in:
+                    lk.release(f"K{i}")
+                    lk.release(f"V{i}")
+                return 1
             # halo hand-off: the last W-1 keys/values up to the end of this rank's range go to the next rank (the tail
             # of the layer's K/V buffer: contiguous, no staging copy).  Only when the local range is shorter than the
             # window does the outgoing halo contain received rows, and the send has to follow the receive.
@@ -296,16 +358,35 @@ def run_ours(args):
     for _ in range(args.warmup):
         hp.step()
     barrier()
+    if os.environ.get("IVL_BENCH_LAYER_TRACE", "0") == "1":
+        hp.layer_trace = []
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(4):
+            hp.step()
+        torch.cuda.synchronize()
+        rows = [[round(t0.elapsed_time(e), 2) for e in st] for st in hp.layer_trace]
+        print(f"[layer-trace rank {rank}] start of every layer (ms since the loop start), steps 0..3:\n" +
+              "\n".join(" ".join(f"{x:7.2f}" for x in r) for r in rows), file=sys.stderr, flush=True)
+        hp.layer_trace = None
+        barrier()
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
-    if rank == 0:
+    if rank == 0 and os.environ.get("IVL_BENCH_NO_SAMPLER", "0") != "1":
         sampler.start()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if os.environ.get("IVL_BENCH_LAYER_TRACE", "0") in ("2", "3"):
+        hp.layer_trace = []
     barrier()
     a.record()
     for _ in range(args.steps):
         hp.step()
     b.record()
     barrier()
+    if getattr(hp, "layer_trace", None) and os.environ.get("IVL_BENCH_LAYER_TRACE") == "2":
+        rows = [[round(a.elapsed_time(e), 2) for e in st] for st in hp.layer_trace]
+        print(f"[layer-trace rank {rank}] timed loop, start of every layer (ms):\n" +
+              "\n".join(" ".join(f"{x:7.2f}" for x in r) for r in rows) + f"\n end {a.elapsed_time(b):.2f}", file=sys.stderr, flush=True)
+        hp.layer_trace = None
     ms_total = torch.tensor([a.elapsed_time(b)], device=dev)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
@@ -329,13 +410,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             lat.append(t.item())
         lat.sort()
-        dist_info = {"single_prompt_ms": round(lat[len(lat) // 2], 3),
+        dist_info = {"transport": hp.transport, "single_prompt_ms": round(lat[len(lat) // 2], 3),
                      "single_prompt_tokens_per_s": round(T / (lat[len(lat) // 2] * 1e-3), 1),
                      "pipelined_ms_per_step": round(ms_step, 3),
                      "ideal_wavefront_efficiency": round((N_GDN_LAYERS + N_SWA_LAYERS) / (N_GDN_LAYERS + N_SWA_LAYERS + world - 1), 4)}
         if not args.no_parity:
             Tp = min(T, 32768) if T % (64 * world) == 0 else 64 * world * 8
-            op = hp.ivl_dist.operator_parity_check(T=Tp)
+            op = hp.ivl_dist.operator_parity_check(T=Tp, transport=hp.transport)
             par = hp.ivl_dist.sharded_parity_check(T=Tp, num_layers=8)
             keys = ("out", "state", "kv", "conv", "oneshot_out", "oneshot_out_chunked_on_one_gpu", "oneshot_state")
             par_t = torch.zeros(len(keys) + 2, device=dev)
@@ -360,12 +441,13 @@ def run_ours(args):
         scan = time_events(lambda: hp.gdn_scan(hp.h0), 10)
         fwd = time_events(lambda: hp.gdn_fwd(hp.h0), 10)
         t_prep, t_scan, t_fwd = sum(prep) / len(prep), sum(scan) / len(scan), sum(fwd) / len(fwd)
-        t_layer = t_fwd if world == 1 else t_prep + t_scan   # what step() launches per GDN layer
+        shard_overlap = os.environ.get("IVL_SHARD_GDN", "overlap") == "overlap"
+        t_layer = t_fwd if (world == 1 or shard_overlap) else t_prep + t_scan   # what step() launches per GDN layer
         alg_bytes = GDN_BYTES_PER_TOKEN * T_local + GDN_STATE_BYTES
         achieved = alg_bytes / (t_layer * 1e-3) / 1e9
         roof = {"bound": "hbm",
                 "kernel": "gdn_chunk = gdn_prep_kernel + gdn_scan_t3_kernel (one GDN layer; "
-                          + ("overlapped on two streams, timed as one operator call" if world == 1 else "back to back") + ")",
+                          + ("overlapped on two streams, timed as one operator call" if (world == 1 or shard_overlap) else "back to back") + ")",
                 "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": GDN_DRAM_TRAFFIC_NCU if (T_local == 131072 and world == 1) else None,
                 "traffic_note": "ncu --replay-mode range over one overlapped operator call (kernel replay would serialise "
@@ -408,7 +490,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "seq_len": T, "batch": 1,
-                       "parallelism": f"sequence-chunk x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"sequence-chunk x{world}, neighbour hand-off over " + ("peer memory (CUDA IPC + copy engines + stream flags)" if hp.transport == "p2p" else "NCCL send/recv")) if world > 1 else "single GPU",
                        "l2": "inputs (>3 GB per layer) exceed the 126 MB L2; no flush needed"},
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "decode": decode,
             "gpu_reference": gpu_ref, "config2_32k": config2, "config3_stream": config3, "dist": dist_info,

@@ -61,6 +61,28 @@ IVL_API const char* ivl_last_cuda_error(void);
 IVL_API int ivl_stream_init(void* stream);
 IVL_API int ivl_stream_release(void* stream);
 
+/* Make `stream` wait until the 32-bit word at device address `addr` (4-byte aligned, device memory of the current
+ * device) is >= `value` (cuStreamWaitValue32, wrap-around compare; no kernel, no SM).  The consumer half of the
+ * peer-memory neighbour hand-off of the sequence-sharded prefill (infinitevl_b200/dist.py PeerLink): the previous
+ * rank copies the DeltaNet state / SWA halo straight into this rank's buffers over NVLink and then writes the flag.
+ * Replaces nothing in the reference (it never shards a sequence). */
+IVL_API int ivl_stream_wait_value32(void* stream, const void* addr, uint32_t value);
+
+/* The producer half: copy `bytes` (multiple of 16; both pointers 16-byte aligned) from `src` (this device) to `dst`
+ * -- memory of ANOTHER GPU of the node, mapped into this process (CUDA IPC) -- with ordinary stores over NVLink, then
+ * write `value` to `*flag` (also peer memory) with a system-scope release, in one launch on `stream`.  bytes == 0
+ * writes the flag only.  `counter`: one zero-initialised 32-bit word in THIS device's memory per concurrently
+ * running put (the kernel leaves it at zero). */
+IVL_API int ivl_peer_put(void* dst, const void* src, size_t bytes, uint32_t* flag, uint32_t value, uint32_t* counter,
+                         void* stream);
+/* Map a device allocation exported by another process of the node (the 64-byte cudaIpcMemHandle_t of its BASE
+ * allocation) for the CURRENT device, peer access enabled -- the `dst` / `flag` addresses of ivl_peer_put.  One open
+ * per handle and process; ivl_ipc_close unmaps. */
+/* Export side: the handle of the cudaMalloc allocation that contains `ptr` and ptr's byte offset inside it. */
+IVL_API int ivl_ipc_export(const void* ptr, void* handle64_out, uint64_t* offset_out);
+IVL_API int ivl_ipc_open(const void* handle64, void** base_ptr);
+IVL_API int ivl_ipc_close(void* base_ptr);
+
 /* ------------------------------------------------------------------------------------
  * Gated DeltaNet, chunked prefill (T > 64 in the model, any T >= 1 here).
  * Replaces chunk_gated_delta_rule(q,k,v,g,beta,scale,initial_state,output_final_state,

@@ -39,6 +39,11 @@ SIGNATURES = {
     "ivl_gdn_recurrent_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
                               + [c_float, c_int, c_void_p]),
     "ivl_swa_fwd": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, c_void_p]),
+    "ivl_ipc_export": (c_int, [c_void_p, c_void_p, ctypes.POINTER(ctypes.c_uint64)]),
+    "ivl_ipc_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "ivl_ipc_close": (c_int, [c_void_p]),
+    "ivl_peer_put": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, ctypes.c_uint32, c_void_p, c_void_p]),
+    "ivl_stream_wait_value32": (c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
     "ivl_swa_fwd_pos": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, ctypes.c_int64, c_void_p]),
     "ivl_swa_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ivl_swa_decode_fwd": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),

@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libivl_b200.so")
 STAMP = os.path.join(LIB_DIR, "libivl_b200.stamp")
 
-SOURCES = ["ivl_abi.cu", "gdn_prep.cu", "gdn_scan.cu", "gdn_scan_t.cu", "gdn_bwd.cu", "gdn_recurrent.cu", "gdn_decode.cu", "gdn_fused.cu", "swa_fwd.cu",
+SOURCES = ["ivl_abi.cu", "gdn_prep.cu", "gdn_scan.cu", "gdn_scan_t.cu", "gdn_bwd.cu", "gdn_recurrent.cu", "gdn_decode.cu", "gdn_fused.cu", "peer_put.cu", "swa_fwd.cu",
            "swa_misc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--use_fast_math",

@@ -1,5 +1,6 @@
 // extern "C" entry points of libivl_b200.so (declared in include/ivl_b200.h).
 // Argument validation + launch only; all math lives in the kernel files.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -35,6 +36,8 @@ cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, co
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
                            int window, float scale, const int* ring_state, int ring_R, long long key_pos0,
                            cudaStream_t stream);
+cudaError_t launch_peer_put(void* dst, const void* src, size_t bytes, uint32_t* flag, uint32_t value, uint32_t* counter,
+                            cudaStream_t stream);
 size_t swa_ring_decode_workspace_bytes(int B, int Hq, int window);
 cudaError_t launch_swa_ring_decode(const void* q, const void* knew, long long kn_sb, long long kn_sh, const void* vnew,
                                    long long vn_sb, long long vn_sh, void* ring_k, void* ring_v, int* state,
@@ -211,6 +214,74 @@ int ivl_stream_release(void* stream) {
   }
   g_fj_sets.erase(it);
   cudaGetLastError();
+  return IVL_OK;
+}
+
+int ivl_stream_wait_value32(void* stream, const void* addr, uint32_t value) {
+  if (!addr || (reinterpret_cast<uintptr_t>(addr) & 3)) return IVL_ERR_NULL;
+  typedef CUresult (*WaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  static std::atomic<WaitFn> fn{nullptr};
+  WaitFn f = fn.load(std::memory_order_acquire);
+  if (!f) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cuda_failed(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint") ||
+        q != cudaDriverEntryPointSuccess || !p)
+      return IVL_ERR_LAUNCH;
+    f = reinterpret_cast<WaitFn>(p);
+    fn.store(f, std::memory_order_release);
+  }
+  const CUresult r = f(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuStreamWaitValue32: CUresult %d", (int)r);
+    return IVL_ERR_LAUNCH;
+  }
+  return IVL_OK;
+}
+
+int ivl_peer_put(void* dst, const void* src, size_t bytes, uint32_t* flag, uint32_t value, uint32_t* counter,
+                 void* stream) {
+  if (!flag || !counter || (bytes && (!dst || !src))) return IVL_ERR_NULL;
+  if ((bytes & 15) || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) ||
+      (reinterpret_cast<uintptr_t>(flag) & 3) || (reinterpret_cast<uintptr_t>(counter) & 3))
+    return IVL_ERR_BAD_SHAPE;
+  IVL_CUDA(ivl::launch_peer_put(dst, src, bytes, flag, value, counter, static_cast<cudaStream_t>(stream)));
+  return IVL_OK;
+}
+
+int ivl_ipc_export(const void* ptr, void* handle64_out, uint64_t* offset_out) {
+  if (!ptr || !handle64_out || !offset_out) return IVL_ERR_NULL;
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cuda_failed(cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint") ||
+      q != cudaDriverEntryPointSuccess || !p)
+    return IVL_ERR_LAUNCH;
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  const CUresult r = reinterpret_cast<RangeFn>(p)(&base, &size, reinterpret_cast<CUdeviceptr>(ptr));
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuMemGetAddressRange: CUresult %d", (int)r);
+    return IVL_ERR_LAUNCH;
+  }
+  cudaIpcMemHandle_t h;
+  IVL_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle64_out, &h, sizeof(h));
+  *offset_out = (uint64_t)(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return IVL_OK;
+}
+
+int ivl_ipc_open(const void* handle64, void** base_ptr) {
+  if (!handle64 || !base_ptr) return IVL_ERR_NULL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  IVL_CUDA(cudaIpcOpenMemHandle(base_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return IVL_OK;
+}
+
+int ivl_ipc_close(void* base_ptr) {
+  if (!base_ptr) return IVL_ERR_NULL;
+  IVL_CUDA(cudaIpcCloseMemHandle(base_ptr));
   return IVL_OK;
 }
 

@@ -171,9 +171,10 @@ class OperatorHandOff:
                 [W-1 + T_local] K/V buffer whose tail holds the local K/V (no concatenation), attend.
     Receives are posted one layer ahead (`post_recv`), so a transfer never waits for the host."""
 
-    def __init__(self, rank: int, world: int, group=None):
+    def __init__(self, rank: int, world: int, group=None, dry: bool = False):
         self.rank, self.world, self.group = rank, world, group
         self._sends: List[Pending] = []
+        self.dry = dry   # developer knob: skip every transfer (per-rank compute time of the sharded step)
 
     @property
     def first(self) -> bool:
@@ -184,12 +185,12 @@ class OperatorHandOff:
         return self.rank == self.world - 1
 
     def post_recv(self, tensors: Sequence[torch.Tensor]) -> Optional[Pending]:
-        if self.first:
+        if self.first or self.dry:
             return None
         return Pending([dist.irecv(t, src=self.rank - 1, group=self.group) for t in tensors], keep=tuple(tensors))
 
     def post_send(self, tensors: Sequence[torch.Tensor]) -> None:
-        if self.last:
+        if self.last or self.dry:
             return
         self._sends.append(Pending([dist.isend(t, dst=self.rank + 1, group=self.group) for t in tensors],
                                    keep=tuple(tensors)))
@@ -202,18 +203,175 @@ class OperatorHandOff:
         self._sends = []
 
 
+class PeerLink:
+    """Neighbour hand-off r -> r + 1 through PEER MEMORY instead of NCCL: the receive buffers of rank r + 1 (the
+    DeltaNet state slots, the halo rows at the front of its K/V buffers) are opened on rank r through CUDA IPC, the
+    sender stores its tensors straight into them over NVLink and then publishes a flag, in one small launch
+    (`ivl_peer_put`: no rendezvous, a few CTAs for a few microseconds); the receiver's compute stream waits on that flag with a stream memory operation
+    (`ivl_stream_wait_value32`).  Back-pressure is a second flag the other way round ("consumed"), so a buffer is
+    never overwritten before the kernel that read it has finished.  Everything is stream-ordered: the host never
+    blocks, and neither side spends an SM on the transfer -- NCCL's send / recv kernels cost the two-GPU step 12 %
+    (75.0 ms against 65.8 ms of per-rank compute, profiles/r02_summary.md).
+
+    Usage (same call order on every rank):
+        link = PeerLink(rank, world, group, device)
+        link.open({"S0": state_in_0, ..., "K0": kbuf0[:, :halo], ...})   # the tensors the PREVIOUS rank writes
+        link.wait("S0"); <kernels reading state_in_0>; link.release("S0")  # receiver
+        link.before_overwrite("S0"); <kernel writing src>; link.send("S0", src)   # sender
+    """
+
+    def __init__(self, rank: int, world: int, group=None, device=None):
+        from . import _lib
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.first, self.last = rank == 0, rank == world - 1
+        self._lib, self._libmod = _lib.load(), _lib
+        # high priority: a put is a few CTAs that must slip in between the thousands of queued CTAs of the next layer's
+        # kernels -- at equal priority the block scheduler drains those first and the neighbour waits for ~0.5 ms
+        self.side = torch.cuda.Stream(self.device, priority=-1)   # sends
+        self.ack = torch.cuda.Stream(self.device, priority=-1)    # "consumed" flags going back (never behind a waiting send)
+        self.names: List[str] = []
+        import os
+        # Fork / join events between the compute stream and the two side streams are created WITH timing: measured on
+        # 2 x B200 the pipelined step takes 73-74 ms with timing-disabled events and 66.5-68 ms with these (the
+        # per-rank compute is 65.8 ms); profiles/r02_summary.md.  IVL_P2P_TIMING_EVENTS=0 restores the plain ones.
+        self._timing = os.environ.get("IVL_P2P_TIMING_EVENTS", "1") == "1"
+
+    def open(self, recv: dict) -> None:
+        """Collective.  `recv[name]`: the local tensor rank - 1 will write (every rank passes the same names; rank 0's
+        tensors are never written and may be None)."""
+        self.names = list(recv.keys())
+        n = len(self.names)
+        self.idx = {k: i for i, k in enumerate(self.names)}
+        self.recv = dict(recv)
+        # flags[0:n]: "data of epoch e is in" (written by rank - 1); flags[n:2n]: "epoch e consumed" (written by rank + 1)
+        self.flags = torch.zeros(2 * n, dtype=torch.int32, device=self.device)
+        self.counters = torch.zeros(2 * n, dtype=torch.int32, device=self.device)   # block counters of ivl_peer_put
+        torch.cuda.synchronize(self.device)
+
+        def export(t: torch.Tensor):
+            # (IPC handle of the BASE allocation the caching allocator carved this tensor from, byte offset, bytes)
+            assert t.is_contiguous(), "PeerLink buffers must be contiguous"
+            import ctypes
+            handle = ctypes.create_string_buffer(64)
+            off = ctypes.c_uint64()
+            self._libmod.check(self._lib.ivl_ipc_export(t.data_ptr(), handle, ctypes.byref(off)), "ivl_ipc_export")
+            return handle.raw, int(off.value), t.numel() * t.element_size()
+
+        mine = {"flags": export(self.flags),
+                "recv": {k: (export(t) if (t is not None and not self.first) else None) for k, t in recv.items()}}
+        every = [None] * self.world
+        dist.all_gather_object(every, mine, group=self.group)
+        self._bases = {}
+
+        def map_(ex) -> int:
+            handle, off, _ = ex
+            if handle not in self._bases:
+                import ctypes
+                p = ctypes.c_void_p()
+                self._libmod.check(self._lib.ivl_ipc_open(handle, ctypes.byref(p)), "ivl_ipc_open")
+                self._bases[handle] = int(p.value)
+            return self._bases[handle] + off
+
+        self.peer_ptr, self.peer_bytes, self.next_flags, self.prev_flags = {}, {}, None, None
+        err = None
+        try:
+            if not self.last:
+                nxt = every[self.rank + 1]
+                self.next_flags = map_(nxt["flags"])
+                for k, ex in nxt["recv"].items():
+                    if ex is not None:
+                        self.peer_ptr[k], self.peer_bytes[k] = map_(ex), ex[2]
+            if not self.first:
+                self.prev_flags = map_(every[self.rank - 1]["flags"])
+        except Exception as e:  # noqa: BLE001
+            err = e
+        # all or nothing: a rank that cannot map its neighbours must not leave them waiting on flags it never writes
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() < 1.0:
+            raise RuntimeError(f"PeerLink: peer mapping failed on at least one rank ({err!r} here)")
+        self.epoch_in = {k: 0 for k in self.names}
+        self.epoch_out = {k: 0 for k in self.names}
+        self.sent = {}
+        dist.barrier(group=self.group)
+
+    def _wait_value(self, stream: torch.cuda.Stream, index: int, value: int) -> None:
+        self._libmod.check(self._lib.ivl_stream_wait_value32(stream.cuda_stream, self.flags.data_ptr() + 4 * index,
+                                                           value & 0xFFFFFFFF), "ivl_stream_wait_value32")
+
+    def wait(self, name: str) -> None:
+        """The current stream waits until the previous rank's next transfer into `recv[name]` has landed."""
+        if self.first:
+            return
+        self.epoch_in[name] += 1
+        self._wait_value(torch.cuda.current_stream(self.device), self.idx[name], self.epoch_in[name])
+
+    def release(self, name: str) -> None:
+        """Everything enqueued on the current stream so far has finished reading `recv[name]`: tell the sender."""
+        if self.first:
+            return
+        ev = torch.cuda.Event(enable_timing=self._timing)
+        ev.record(torch.cuda.current_stream(self.device))
+        n, i, e = len(self.names), self.idx[name], self.epoch_in[name]
+        self.ack.wait_event(ev)
+        self._put(None, None, self.prev_flags, n + i, e, self.ack)
+
+    def _put(self, dst_ptr, src, flags_ptr: int, index: int, value: int, stream=None) -> None:
+        nbytes = 0 if src is None else src.numel() * src.element_size()
+        self._libmod.check(self._lib.ivl_peer_put(
+            dst_ptr, src.data_ptr() if src is not None else None, nbytes, flags_ptr + 4 * index, value & 0xFFFFFFFF,
+            self.counters.data_ptr() + 4 * index, (stream or self.side).cuda_stream), "ivl_peer_put")
+
+    def send(self, name: str, src: torch.Tensor) -> None:
+        """Copy `src` (as of everything enqueued on the current stream so far) into the next rank's `recv[name]`."""
+        if self.last:
+            return
+        self.epoch_out[name] += 1
+        n, i, e = len(self.names), self.idx[name], self.epoch_out[name]
+        ev = torch.cuda.Event(enable_timing=self._timing)
+        ev.record(torch.cuda.current_stream(self.device))
+        assert src.is_contiguous() and src.numel() * src.element_size() == self.peer_bytes[name]
+        self.side.wait_event(ev)
+        if e > 1:
+            self._wait_value(self.side, n + i, e - 1)      # the receiver has consumed the previous epoch
+        self._put(self.peer_ptr[name], src, self.next_flags, i, e)
+        done = torch.cuda.Event()
+        done.record(self.side)
+        self.sent[name] = done
+
+    def before_overwrite(self, name: str) -> None:
+        """The current stream waits until the last send of `name` has read its source."""
+        ev = self.sent.pop(name, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def drain(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        torch.cuda.current_stream(self.device).wait_stream(self.ack)
+
+
 def gdn_layer_sharded(ho: OperatorHandOff, prep: Callable[[], None], scan: Callable[[torch.Tensor], None],
                       h0_local: torch.Tensor, state_in: torch.Tensor, state_out: torch.Tensor,
-                      pending: Optional[Pending]) -> None:
+                      pending: Optional[Pending], fwd: Optional[Callable[[torch.Tensor], None]] = None) -> None:
     """One GDN layer of a sharded prefill at operator level: `prep()` launches the chunk pre-pass,
     `scan(h0)` the recurrence writing the final state into `state_out`.  `pending` is the posted receive
-    of `state_in` (None on rank 0, which starts from `h0_local`)."""
-    prep()
+    of `state_in` (None on rank 0, which starts from `h0_local`).
+    `fwd(h0)` (optional): the whole chunk operator, which overlaps its pre-pass with its scan on two streams.  With
+    the receive posted a layer ahead the state is normally there before the layer starts, so waiting for it first
+    and then running the overlapped operator beats "pre-pass, wait, scan" (measured, profiles/r02_summary.md)."""
     h0 = h0_local
-    if pending is not None:
-        pending.wait()
-        h0 = state_in
-    scan(h0)
+    if fwd is not None:
+        if pending is not None:
+            pending.wait()
+            h0 = state_in
+        fwd(h0)
+    else:
+        prep()
+        if pending is not None:
+            pending.wait()
+            h0 = state_in
+        scan(h0)
     ho.post_send([state_out])
 
 
@@ -225,12 +383,13 @@ def _err(ref: torch.Tensor, y: torch.Tensor) -> float:
     return float(((ref - y).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-30)).item())
 
 
-def operator_parity_check(T: int = 32768, seed: int = 0, group=None) -> dict:
+def operator_parity_check(T: int = 32768, seed: int = 0, group=None, transport: str = "nccl") -> dict:
     """The hot path itself (the two operators, no projections): every rank builds the SAME full-length inputs, runs
     its token range with the neighbour hand-off of `OperatorHandOff` / `gdn_layer_sharded` over the process group, and
     compares its outputs with the matching slice of the one-shot operator call on the whole sequence, which it also
     runs.  The kernels are deterministic, the state travels in fp32 and the SWA key tiles are anchored at absolute
-    positions, so the sharded run must reproduce the one-shot run BIT FOR BIT.  Returns the same dict on every rank:
+    positions, so the sharded run must reproduce the one-shot run BIT FOR BIT.  transport: "nccl" (isend / irecv) or
+    "p2p" (`PeerLink`: copy-engine writes into the neighbour's buffers + stream-ordered flags).  Same dict on every rank:
     {"gdn_o_equal", "gdn_state_equal", "swa_equal"} (logical AND over the ranks) and the worst error ratios."""
     from . import ops, swa
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -247,15 +406,29 @@ def operator_parity_check(T: int = 32768, seed: int = 0, group=None) -> dict:
     h0 = (torch.randn(1, H, K, V, generator=gen) * 0.1).float().to(dev)
     ref_o, ref_s = ops.chunk_gated_delta_rule(q, k, v, g, beta, initial_state=h0, output_final_state=True,
                                               use_qk_l2norm_in_kernel=True)
-    ho = OperatorHandOff(rank, world, group)
+    p2p = transport == "p2p"
+    ho = OperatorHandOff(rank, world, group, dry=p2p)
     state_in, state_out = torch.empty_like(h0), torch.empty_like(h0)
+    Hh = W - 1
+    n_in, n_out = min(Hh, s), min(Hh, e)
+    kb = torch.zeros(1, Hh + Tl, HKV, D, dtype=torch.bfloat16, device=dev)
+    vb = torch.zeros_like(kb)
+    link = None
+    if p2p:
+        link = PeerLink(rank, world, group, dev)
+        link.open({"S": state_in, "K": kb[:, Hh - n_in:Hh] if n_in else None, "V": vb[:, Hh - n_in:Hh] if n_in else None})
     pend = ho.post_recv([state_in])
     if pend is not None:
         pend.wait()
+    if link is not None:
+        link.wait("S")
     o, _ = ops.chunk_gated_delta_rule(q[:, s:e].contiguous(), k[:, s:e].contiguous(), v[:, s:e].contiguous(),
                                       g[:, s:e].contiguous(), beta[:, s:e].contiguous(),
                                       initial_state=h0 if rank == 0 else state_in, output_final_state=True,
                                       use_qk_l2norm_in_kernel=True, state_out=state_out)
+    if link is not None:
+        link.release("S")
+        link.send("S", state_out)
     ho.post_send([state_out])
     ho.drain()
     flags = [float(torch.equal(o, ref_o[:, s:e])), float(torch.equal(state_out, ref_s)) if rank == world - 1 else 1.0]
@@ -265,18 +438,33 @@ def operator_parity_check(T: int = 32768, seed: int = 0, group=None) -> dict:
     sk = torch.randn(1, T, HKV, D, generator=gen).bfloat16().to(dev)
     sv = torch.randn(1, T, HKV, D, generator=gen).bfloat16().to(dev)
     ref_a = swa.swa_attention_bthd(sq, sk, sv, window=W)
-    Hh = W - 1
-    n_in, n_out = min(Hh, s), min(Hh, e)
-    kb = torch.zeros(1, Hh + Tl, HKV, D, dtype=torch.bfloat16, device=dev)
-    vb = torch.zeros_like(kb)
     kb[:, Hh:].copy_(sk[:, s:e])
     vb[:, Hh:].copy_(sv[:, s:e])
+
+    def send_halo():
+        if link is not None:
+            link.send("K", kb[:, Hh + Tl - n_out:])
+            link.send("V", vb[:, Hh + Tl - n_out:])
+        else:
+            ho.post_send([kb[:, Hh + Tl - n_out:], vb[:, Hh + Tl - n_out:]])
+
     pend = ho.post_recv([kb[:, Hh - n_in:Hh], vb[:, Hh - n_in:Hh]]) if n_in else None
+    if n_out <= Tl:
+        send_halo()          # only local rows leave: no need to wait for the incoming halo
     if pend is not None:
         pend.wait()
-    ho.post_send([kb[:, Hh + Tl - n_out:], vb[:, Hh + Tl - n_out:]])
+    if link is not None and n_in:
+        link.wait("K")
+        link.wait("V")
+    if n_out > Tl:
+        send_halo()
     a = swa.swa_attention_bthd(sq[:, s:e], kb[:, Hh - n_in:], vb[:, Hh - n_in:], window=W, key_pos0=s - n_in)
+    if link is not None and n_in:
+        link.release("K")
+        link.release("V")
     ho.drain()
+    if link is not None:
+        link.drain()
     flags.append(float(torch.equal(a, ref_a[:, s:e])))
     errs.append(_err(ref_a[:, s:e], a))
     ft = torch.tensor(flags, device=dev)
@@ -285,7 +473,7 @@ def operator_parity_check(T: int = 32768, seed: int = 0, group=None) -> dict:
     dist.all_reduce(et, op=dist.ReduceOp.MAX, group=group)
     f, er = ft.tolist(), et.tolist()
     return {"gdn_o_equal": bool(f[0]), "gdn_state_equal": bool(f[1]), "swa_equal": bool(f[2]),
-            "gdn_o_err": er[0], "gdn_state_err": er[1], "swa_err": er[2], "T": T, "world": world}
+            "gdn_o_err": er[0], "gdn_state_err": er[1], "swa_err": er[2], "T": T, "world": world, "transport": transport}
 
 
 def sharded_parity_check(T: int = 32768, num_layers: int = 8, seed: int = 0, group=None, config=None) -> dict:

@@ -20,9 +20,10 @@ def main():
         res = sharded_parity_check(T=T, num_layers=8)
         if res:
             print("DIST_PARITY " + json.dumps(res), flush=True)
-        op = operator_parity_check(T=T)
-        if dist.get_rank() == 0:
-            print("OP_PARITY " + json.dumps(op), flush=True)
+        for transport in ("nccl", "p2p"):
+            op = operator_parity_check(T=T, transport=transport)
+            if dist.get_rank() == 0:
+                print("OP_PARITY " + json.dumps(op), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

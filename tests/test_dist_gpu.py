@@ -45,6 +45,6 @@ def test_sharded_prefill_matches_single_gpu(world):
         assert r["out"] == 0.0 and r["state"] == 0.0 and r["kv"] == 0.0 and r["conv"] == 0.0, r
         assert r["oneshot_out"] <= TOL and r["oneshot_state"] <= TOL, r
     ops = [json.loads(l.split(" ", 1)[1]) for l in p.stdout.splitlines() if l.startswith("OP_PARITY ")]
-    assert len(ops) == 2, p.stdout[-2000:]
+    assert len(ops) == 4 and {r["transport"] for r in ops} == {"nccl", "p2p"}, p.stdout[-2000:]
     for r in ops:
         assert r["gdn_o_equal"] and r["gdn_state_equal"] and r["swa_equal"], r

@@ -1,0 +1,8 @@
+for ns in 1 0; do
+IVL_BENCH_NO_SAMPLER=$ns IVL_SHARD_TRANSPORT=p2p timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2> gpurun_out/bench_r02o.err | grep '^{' > gpurun_out/bench_r02o_$ns.json
+python - <<P
+import json
+d=json.load(open('gpurun_out/bench_r02o_$ns.json'))
+print('nosampler=$ns', d['ms_per_step'], d['value'], {k:v for k,v in d['dist'].items() if k!='parity_err'}, d['clocks'])
+P
+done

@@ -1,0 +1,8 @@
+for m in p2p nccl; do for tr in 0 2; do
+IVL_BENCH_LAYER_TRACE=$tr IVL_SHARD_TRANSPORT=$m timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline --no-parity 2> gpurun_out/bench_r02p.err | grep '^{' > gpurun_out/bench_r02p.json
+python - <<P
+import json
+d=json.load(open('gpurun_out/bench_r02p.json'))
+print('$m trace=$tr', d['ms_per_step'], d['dist']['single_prompt_ms'], d['clocks']['sm_mhz'])
+P
+done; done
