@@ -111,6 +111,22 @@ IVL_API int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const
                       int H, int K, int V, float scale, int l2norm_qk, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Prefill-side fusion (replaces the two ShortConvolution calls on q and k and the gate
+ * math in front of the operator, std:1263-1294): the chunk operator on the RAW projection outputs.
+ *   xq, xk  bf16 [B,T,H*128]  q_proj / k_proj outputs BEFORE the short conv (conv + SiLU + L2 norm happen in the pre-pass)
+ *   v       bf16 [B,T,H,256]  values AFTER their short conv (the scan reads them with TMA)
+ *   a, b    bf16 [B,T,H]      a_proj / b_proj outputs: g = -exp(A_log) softplus(a + dt_bias), beta = sigmoid(b)
+ *   conv_wq/wk bf16 [H*128,4]; conv_q_in/k_in bf16 [B,H*128,4] carried tails or NULL; conv_q_out/k_out: tails after
+ *   the call or NULL (both or neither; must not alias the inputs); A_log, dt_bias fp32 [H].
+ * Rounding points are those of the unfused chain (ivl_short_conv_fwd, ivl_gdn_gate_fwd, ivl_gdn_chunk_fwd with
+ * l2norm_qk = 1), so the results are bit-identical to it.  Dense batches only. */
+IVL_API int ivl_gdn_chunk_fwd_fused(const void* xq, const void* xk, const void* v, const void* a, const void* b,
+                                    const void* conv_wq, const void* conv_wk, const void* conv_q_in,
+                                    const void* conv_k_in, void* conv_q_out, void* conv_k_out, const float* A_log,
+                                    const float* dt_bias, const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype,
+                                    int B, int T, int H, int K, int V, float scale, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* Packed variable-length batch: the reference's `cu_seqlens` form (fla/ops/gated_delta_rule/chunk.py:211-214,
  * 355-369: B = 1, sequences concatenated on the token axis, one initial / final state per sequence).  One launch
  * pair for the whole batch.  The caller cuts every sequence into chunks of 64 tokens (the last one may be

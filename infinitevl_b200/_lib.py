@@ -27,6 +27,7 @@ SIGNATURES = {
     "ivl_gdn_chunk_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ivl_gdn_chunk_fwd": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5
                           + [c_float, c_int, c_void_p, c_size_t, c_void_p]),
+    "ivl_gdn_chunk_fwd_fused": (c_int, [c_void_p] * 14 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 5 + [c_float, c_void_p, c_size_t, c_void_p]),
     "ivl_gdn_chunk_fwd_varlen": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_void_p, c_int] + [c_int] * 4
                                  + [c_float, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t,
                                     c_void_p]),

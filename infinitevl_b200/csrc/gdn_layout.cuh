@@ -78,6 +78,23 @@ struct GdnVarlen {
   int num_seqs;                // N
 };
 
+// Prefill-side fusion: when `wq` is set, gdn_prep_kernel reads the RAW q / k projection
+// outputs and applies the depthwise causal conv (kernel 4) + SiLU itself, and derives g / beta from the raw a / b
+// projections -- the three launches in front of the chunk operator (ivl_short_conv_fwd x2 on q and k, ivl_gdn_gate_fwd)
+// and their 2.2 GB of HBM round trip per 128K-token layer disappear.  All pointers are device pointers.
+struct GdnPrepFused {
+  const void* wq = nullptr;        // bf16 [H*128][4] conv weights of q (null: not fused)
+  const void* wk = nullptr;        // bf16 [H*128][4]
+  const void* cq_in = nullptr;     // bf16 [B][H*128][4] carried conv tails (newest input in column 3) or null
+  const void* ck_in = nullptr;
+  void* cq_out = nullptr;          // bf16 [B][H*128][4] tails after this call, or null
+  void* ck_out = nullptr;
+  const void* a = nullptr;         // bf16 [B][T][H] raw a_proj / b_proj outputs (replace g / beta)
+  const void* b = nullptr;
+  const float* A_log = nullptr;    // fp32 [H]
+  const float* dt_bias = nullptr;  // fp32 [H]
+};
+
 struct GdnWorkspace {
   uint8_t* blob;       // [B][H][ring][BLOB_BYTES]
   uint8_t* ublob;      // [B][H][ring][NS][UBLOB_BYTES]

@@ -81,6 +81,59 @@ __device__ __forceinline__ void load_row_quarter(const __nv_bfloat16* src, bool 
     raw[p] = valid ? __ldg(reinterpret_cast<const uint4*>(src) + p) : make_uint4(0, 0, 0, 0);
 }
 
+// Fused prologue: depthwise causal conv (kernel 4) + SiLU of 32 channels of one token row, rounded to bf16 exactly
+// as ivl_short_conv_fwd does (gdn_fused.cu: same fp32 expression, same rounding point), from the RAW projection
+// rows t-3 .. t.  x: the row of token t (this thread's 32 channels); row_stride: elements between token rows; t: index
+// of the token in its sequence (rows before 0 come from the carried tail `cache` [D][4], newest in column 3, or are
+// zero); w: conv weights of this thread's first channel ([ch][4]).
+__device__ __forceinline__ void conv_row_quarter(const __nv_bfloat16* x, long long row_stride, int t, bool valid,
+                                                 const __nv_bfloat16* w, const __nv_bfloat16* cache, uint4* raw) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (!valid) { raw[p] = make_uint4(0, 0, 0, 0); continue; }
+    float acc[8];
+    float wt[8][4];
+    {
+      const uint4* wp = reinterpret_cast<const uint4*>(w + p * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(wp + i);
+        const uint32_t* ww = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          wt[(i * 8 + 2 * e) / 4][(i * 8 + 2 * e) % 4] = bf16_lo(ww[e]);
+          wt[(i * 8 + 2 * e + 1) / 4][(i * 8 + 2 * e + 1) % 4] = bf16_hi(ww[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {          // tap j multiplies the input of token t - 3 + j
+      const int tt = t - 3 + j;
+      float xin[8];
+      if (tt >= 0) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (long long)(j - 3) * row_stride) + p);
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { xin[2 * e] = bf16_lo(xw[e]); xin[2 * e + 1] = bf16_hi(xw[e]); }
+      } else if (cache != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xin[e] = __bfloat162float(cache[(p * 8 + e) * 4 + 4 + tt]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xin[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = (j == 0) ? wt[e][0] * xin[e] : fmaf(wt[e][j], xin[e], acc[e]);
+    }
+    uint32_t* out = reinterpret_cast<uint32_t*>(&raw[p]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a0 = acc[2 * e], a1 = acc[2 * e + 1];
+      out[e] = pack_bf16(a0 / (1.0f + __expf(-a0)), a1 / (1.0f + __expf(-a1)));
+    }
+  }
+}
+
 template <class PieceOffset>
 __device__ __forceinline__ void norm_row_quarter(const uint4* raw, bool l2norm, float weight,
                                                  __nv_bfloat16* smem_row, uint8_t* img, PieceOffset img_piece) {
@@ -164,12 +217,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 // coupling matrix R_c = Wg_c Kt_{c-1}^T (negated, 8 KiB image behind Au); the first chunk of a sequence has
 // gamma_{-1} = 1 and R = 0.  It recomputes Kt_{c-1} from the previous chunk's k rows and g (bit-identical to the
 // image the previous chunk's CTA writes, which the state update uses).
-template <int MODE>
+template <int MODE, bool FUSED = false>
 __global__ void __launch_bounds__(PREP_THREADS, 3)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
                 const __nv_bfloat16* __restrict__ beta, GdnWorkspace ws, GdnVarlen vl, int T, int H, float scale,
-                int l2norm, int prefetch_ahead, int scan_ctas_per_head) {
+                int l2norm, int prefetch_ahead, int scan_ctas_per_head, GdnPrepFused fz) {
   constexpr bool TR = MODE != 0, LAG = MODE == 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
@@ -215,8 +268,39 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   {
     const int row = tid >> 2, qt = tid & 3;  // 4 threads per row, 32 elements each
     const size_t off = ((tok0 + row) * H + h) * GDN_K + qt * 32;
-    load_row_quarter(q + off, row < valid, rawq);
-    load_row_quarter(k + off, row < valid, rawk);
+    if (FUSED) {
+      // q, k are the RAW projection outputs: conv + SiLU here (dense batches only: t0 + row is the position in the sequence)
+      const size_t ch = (size_t)h * GDN_K + qt * 32;
+      const size_t D = (size_t)H * GDN_K;
+      const __nv_bfloat16* cq = fz.cq_in ? static_cast<const __nv_bfloat16*>(fz.cq_in) + ((size_t)b * D + ch) * 4 : nullptr;
+      const __nv_bfloat16* ck = fz.ck_in ? static_cast<const __nv_bfloat16*>(fz.ck_in) + ((size_t)b * D + ch) * 4 : nullptr;
+      conv_row_quarter(q + off, (long long)H * GDN_K, t0 + row, row < valid,
+                       static_cast<const __nv_bfloat16*>(fz.wq) + ch * 4, cq, rawq);
+      conv_row_quarter(k + off, (long long)H * GDN_K, t0 + row, row < valid,
+                       static_cast<const __nv_bfloat16*>(fz.wk) + ch * 4, ck, rawk);
+    } else {
+      load_row_quarter(q + off, row < valid, rawq);
+      load_row_quarter(k + off, row < valid, rawk);
+    }
+  }
+  if (FUSED && c == NT - 1 && fz.cq_out != nullptr) {
+    // carried conv tails after this call: the last four raw inputs of [tail_in | x] per channel (gdn_fused.cu)
+    const int chl = tid & 127;
+    const size_t D = (size_t)H * GDN_K, ch = (size_t)h * GDN_K + chl;
+    const __nv_bfloat16* x = tid < 128 ? q : k;
+    const __nv_bfloat16* cin = static_cast<const __nv_bfloat16*>(tid < 128 ? fz.cq_in : fz.ck_in);
+    __nv_bfloat16* cout = static_cast<__nv_bfloat16*>(tid < 128 ? fz.cq_out : fz.ck_out) + ((size_t)b * D + ch) * 4;
+    float tl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tt = T - 4 + j;
+      tl[j] = tt >= 0 ? __bfloat162float(x[(((size_t)b * T + tt) * H + h) * GDN_K + chl])
+                      : (cin ? __bfloat162float(cin[((size_t)b * D + ch) * 4 + 4 + tt]) : 0.f);
+    }
+    uint2 o2;
+    o2.x = pack_bf16(tl[0], tl[1]);
+    o2.y = pack_bf16(tl[2], tl[3]);
+    *reinterpret_cast<uint2*>(cout) = o2;
   }
   {
     // Warm L2 for the CTA that will run on this SM slot one wave later: its q/k/v/g/beta lines then hit
@@ -232,7 +316,7 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q + poff));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(k + poff));
         if (!TR) asm volatile("prefetch.global.L2 [%0];" ::"l"(v + ((ptok + row) * H + ph) * GDN_V + qt * 64));
-        if (qt == 0) {
+        if (qt == 0 && !FUSED) {
           asm volatile("prefetch.global.L2 [%0];" ::"l"(g + (ptok + row) * H + ph));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(beta + (ptok + row) * H + ph));
         }
@@ -252,8 +336,21 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   }
   for (int i = tid; i < 64 * L_LD; i += PREP_THREADS) sL[i] = 0.f;
   if (warp == 0) {
-    float g0 = (lane < valid) ? g[(tok0 + lane) * H + h] : 0.f;
-    float g1 = (lane + 32 < valid) ? g[(tok0 + lane + 32) * H + h] : 0.f;
+    float g0, g1;
+    if (FUSED) {
+      // g = -exp(A_log) softplus(a + dt_bias), beta = sigmoid(b) rounded to bf16: the expressions of gdn_gate_kernel
+      const __nv_bfloat16* ar = static_cast<const __nv_bfloat16*>(fz.a);
+      const float dtb = fz.dt_bias[h], na = -expf(fz.A_log[h]);
+      auto gate = [&](int i) {
+        const float z = __bfloat162float(ar[(tok0 + i) * H + h]) + dtb;
+        return na * (z > 20.f ? z : log1pf(expf(z)));
+      };
+      g0 = (lane < valid) ? gate(lane) : 0.f;
+      g1 = (lane + 32 < valid) ? gate(lane + 32) : 0.f;
+    } else {
+      g0 = (lane < valid) ? g[(tok0 + lane) * H + h] : 0.f;
+      g1 = (lane + 32 < valid) ? g[(tok0 + lane + 32) * H + h] : 0.f;
+    }
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       float a0 = __shfl_up_sync(0xffffffffu, g0, d), a1 = __shfl_up_sync(0xffffffffu, g1, d);
@@ -262,8 +359,18 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     g1 += __shfl_sync(0xffffffffu, g0, 31);
     s.G[lane] = g0;
     s.G[lane + 32] = g1;
-    s.beta[lane] = (lane < valid) ? __bfloat162float(beta[(tok0 + lane) * H + h]) : 0.f;
-    s.beta[lane + 32] = (lane + 32 < valid) ? __bfloat162float(beta[(tok0 + lane + 32) * H + h]) : 0.f;
+    if (FUSED) {
+      const __nv_bfloat16* br = static_cast<const __nv_bfloat16*>(fz.b);
+      auto sig = [&](int i) {
+        const float bb = __bfloat162float(br[(tok0 + i) * H + h]);
+        return __bfloat162float(__float2bfloat16(1.0f / (1.0f + expf(-bb))));
+      };
+      s.beta[lane] = (lane < valid) ? sig(lane) : 0.f;
+      s.beta[lane + 32] = (lane + 32 < valid) ? sig(lane + 32) : 0.f;
+    } else {
+      s.beta[lane] = (lane < valid) ? __bfloat162float(beta[(tok0 + lane) * H + h]) : 0.f;
+      s.beta[lane + 32] = (lane + 32 < valid) ? __bfloat162float(beta[(tok0 + lane + 32) * H + h]) : 0.f;
+    }
   }
   if (LAG && warp == 2) {
     // in-chunk cumsum of the previous chunk's g (a full chunk: only the last chunk of a sequence can be short)
@@ -686,6 +793,8 @@ cudaError_t configure_gdn_prep() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gdn_prep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gdn_prep_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
+    if (e != cudaSuccess) return e;
     configured[dev].store(true, std::memory_order_release);
   }
   return cudaSuccess;
@@ -696,7 +805,8 @@ cudaError_t configure_gdn_prep() {
 // vl.chunk_tok0 != nullptr: packed variable-length batch (B must be 1) of num_chunks chunks
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                             const GdnWorkspace& ws, const GdnVarlen& vl, int num_chunks, int B, int T, int H,
-                            float scale, int l2norm, int scan_ctas_per_head, int transposed, cudaStream_t stream) {
+                            float scale, int l2norm, int scan_ctas_per_head, int transposed, cudaStream_t stream,
+                            const GdnPrepFused* fused) {
   const int smem = (int)sizeof(PrepSmem);
   if (cudaError_t e = configure_gdn_prep()) return e;
   static int resident = 0;
@@ -707,11 +817,14 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
     resident = 3 * sms;
   }
   dim3 grid((unsigned)num_chunks * (unsigned)H, 1, B);
-  auto kern = transposed == 2 ? gdn_prep_kernel<2> : (transposed == 1 ? gdn_prep_kernel<1> : gdn_prep_kernel<0>);
+  const bool fz = fused != nullptr && fused->wq != nullptr;
+  if (fz && (transposed != 1 || vl.chunk_tok0 != nullptr)) return cudaErrorInvalidValue;   // transposed scan, dense only
+  auto kern = fz ? gdn_prep_kernel<1, true>
+                 : (transposed == 2 ? gdn_prep_kernel<2> : (transposed == 1 ? gdn_prep_kernel<1> : gdn_prep_kernel<0>));
   kern<<<grid, PREP_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
       static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, vl, T, H, scale, l2norm,
-      resident, scan_ctas_per_head);
+      resident, scan_ctas_per_head, fz ? *fused : GdnPrepFused{});
   return cudaGetLastError();
 }
 

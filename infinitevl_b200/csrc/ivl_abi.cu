@@ -17,7 +17,8 @@
 namespace ivl {
 cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const float* g, const void* beta,
                             const GdnWorkspace& ws, const GdnVarlen& vl, int num_chunks, int B, int T, int H,
-                            float scale, int l2norm, int scan_ctas_per_head, int transposed, cudaStream_t stream);
+                            float scale, int l2norm, int scan_ctas_per_head, int transposed, cudaStream_t stream,
+                            const GdnPrepFused* fused = nullptr);
 cudaError_t configure_gdn_prep();
 cudaError_t launch_gdn_scan_t(const void* v, const GdnWorkspace& ws, const GdnVarlen& vl, int ntrow, int nseq, int B,
                               const void* h0, int h0_dtype, void* o, void* ht, int ht_dtype, int T, int H, int lag,
@@ -344,8 +345,10 @@ namespace {
 int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float* g, const void* beta, const void* h0,
                        int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H, float scale, int l2norm_qk,
                        const ivl::GdnVarlen& vl, int num_chunks, int nseq, void* workspace, size_t workspace_bytes,
-                       void* stream) {
-  if (!q || !k || !v || !g || !beta || !o || !workspace) return IVL_ERR_NULL;
+                       void* stream, const ivl::GdnPrepFused* fused = nullptr) {
+  if (!q || !k || !v || !o || !workspace) return IVL_ERR_NULL;
+  if (!fused && (!g || !beta)) return IVL_ERR_NULL;
+  if (fused && tscan_mode() != 3 && tscan_mode() != 1) return IVL_ERR_BAD_SHAPE;   // images of prep mode 1 only
   if ((h0 && bad_dtype(h0_dtype)) || (ht && bad_dtype(ht_dtype))) return IVL_ERR_DTYPE;
   const int T_ws = num_chunks * ivl::GDN_C;   // the workspace is sized by chunks
   if (workspace_bytes < ivl::gdn_workspace_bytes(B, T_ws, H) || (reinterpret_cast<uintptr_t>(workspace) & 1023))
@@ -385,7 +388,7 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   if (first || !fits || env_int("IVL_GDN_PIPE", overlap_default) == 0) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, prep_mode(trm), st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, prep_mode(trm), st, fused));
     if (tr)
       IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm, st));
     else
@@ -403,7 +406,7 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   if (other_busy) {
     ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, /*ring=*/0);
     IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
-    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, prep_mode(trm), st));
+    IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, 0, prep_mode(trm), st, fused));
     if (tr)
       IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm, st));
     else
@@ -430,7 +433,7 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
     IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, bv, st));
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv,
-                                prep_mode(trm), fj->aux));
+                                prep_mode(trm), fj->aux, fused));
   IVL_CUDA(cudaEventRecord(fj->join, fj->aux));
   IVL_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
   if (cap == cudaStreamCaptureStatusNone) {
@@ -447,6 +450,21 @@ int ivl_gdn_chunk_fwd(const void* q, const void* k, const void* v, const float* 
   if (int e = check_gdn_shape(B, T, H, K, V)) return e;
   return gdn_chunk_fwd_impl(q, k, v, g, beta, h0, h0_dtype, o, ht, ht_dtype, B, T, H, scale, l2norm_qk, ivl::GdnVarlen{},
                             ivl::gdn_num_chunks(T), B, workspace, workspace_bytes, stream);
+}
+
+int ivl_gdn_chunk_fwd_fused(const void* xq, const void* xk, const void* v, const void* a, const void* b,
+                            const void* conv_wq, const void* conv_wk, const void* conv_q_in, const void* conv_k_in,
+                            void* conv_q_out, void* conv_k_out, const float* A_log, const float* dt_bias, const void* h0,
+                            int h0_dtype, void* o, void* ht, int ht_dtype, int B, int T, int H, int K, int V, float scale,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_gdn_shape(B, T, H, K, V)) return e;
+  if (!xq || !xk || !a || !b || !conv_wq || !conv_wk || !A_log || !dt_bias) return IVL_ERR_NULL;
+  if ((conv_q_out == nullptr) != (conv_k_out == nullptr)) return IVL_ERR_NULL;
+  ivl::GdnPrepFused fz;
+  fz.wq = conv_wq; fz.wk = conv_wk; fz.cq_in = conv_q_in; fz.ck_in = conv_k_in; fz.cq_out = conv_q_out;
+  fz.ck_out = conv_k_out; fz.a = a; fz.b = b; fz.A_log = A_log; fz.dt_bias = dt_bias;
+  return gdn_chunk_fwd_impl(xq, xk, v, nullptr, nullptr, h0, h0_dtype, o, ht, ht_dtype, B, T, H, scale, /*l2norm=*/1,
+                            ivl::GdnVarlen{}, ivl::gdn_num_chunks(T), B, workspace, workspace_bytes, stream, &fz);
 }
 
 int ivl_gdn_chunk_fwd_varlen(const void* q, const void* k, const void* v, const float* g, const void* beta,

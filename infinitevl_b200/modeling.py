@@ -244,6 +244,22 @@ class GatedDeltaNet(nn.Module):
         if q_len == 1 and self._fused_decode_ok(prev_q, prev_k, prev_v, recurrent_state):
             return self._decode_step(hidden_states, past_key_values, cache_position, prev_q, prev_k, prev_v,
                                      recurrent_state), None
+        if mode == "chunk" and self._fused_prefill_ok(hidden_states):
+            # prefill-side fusion: q / k conv + SiLU, gate math and L2 norm run inside the operator's
+            # pre-pass (ivl_gdn_chunk_fwd_fused); bit-identical to the kernel-by-kernel chain below
+            v, new_v = self.v_conv1d(self.v_proj(hidden_states), cache=prev_v, output_final_state=use_cache)
+            o, next_state, convs = ops.chunk_gated_delta_rule_fused(
+                self.q_proj(hidden_states), self.k_proj(hidden_states), v.view(B, q_len, self.num_heads, self.head_v_dim),
+                self.a_proj(hidden_states), self.b_proj(hidden_states), self.q_conv1d.weight, self.k_conv1d.weight,
+                self.A_log, self.dt_bias, conv_state_q=prev_q, conv_state_k=prev_k, output_conv_state=use_cache,
+                initial_state=recurrent_state, output_final_state=use_cache)
+            if use_cache:
+                past_key_values.update(layer_idx=self.layer_idx, key_states=None, value_states=None,
+                                       conv_state=(convs[0], convs[1], new_v), recurrent_state=next_state,
+                                       cache_kwargs={"op": "set", "delta_len": q_len, "cache_position": cache_position})
+            gate = self.g_proj(hidden_states).view(B, q_len, self.num_heads, self.head_v_dim)
+            o = self.o_norm(o, gate)
+            return self.o_proj(o.reshape(B, q_len, self.num_heads * self.head_v_dim)), None
         q, new_q = self.q_conv1d(self.q_proj(hidden_states), cache=prev_q, output_final_state=use_cache)
         k, new_k = self.k_conv1d(self.k_proj(hidden_states), cache=prev_k, output_final_state=use_cache)
         v, new_v = self.v_conv1d(self.v_proj(hidden_states), cache=prev_v, output_final_state=use_cache)
@@ -263,6 +279,23 @@ class GatedDeltaNet(nn.Module):
         o = self.o_proj(o.reshape(B, q_len, self.num_heads * self.head_v_dim))
         return o, None
 
+
+    FUSED_PREFILL_MAX_T = 4096
+
+    def _fused_prefill_ok(self, hidden_states) -> bool:
+        # IVL_GDN_FUSED_PREFILL: 1 = always, 0 = never, unset = for calls of at most FUSED_PREFILL_MAX_T tokens.  Measured
+        # (profiles/r02_summary.md): the conv + gate work moves into the pre-pass; at 128K tokens that makes the pre-pass
+        # the longer side of the overlapped operator (whole mixer 10.29 vs 9.93 ms), for streamed frames it removes three
+        # launches per layer.
+        knob = os.environ.get("IVL_GDN_FUSED_PREFILL", "")
+        if knob == "0" or os.environ.get("IVL_GDN_TSCAN", "3") not in ("1", "3"):
+            return False
+        if knob != "1" and hidden_states.shape[1] > self.FUSED_PREFILL_MAX_T:
+            return False
+        ws = (self.q_proj.weight, self.q_conv1d.weight, self.k_conv1d.weight)
+        return (hidden_states.is_cuda and self.num_key_value_heads == self.num_heads and self.head_k_dim == 128
+                and self.head_v_dim == 256 and getattr(self, "conv_size", 4) == 4
+                and all(w.dtype == torch.bfloat16 for w in ws))
 
     # -- single-token decode: the whole mixer core in one launch (ivl_gdn_decode_step) -------------------------
     def _fused_decode_ok(self, prev_q, prev_k, prev_v, state) -> bool:

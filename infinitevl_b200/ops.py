@@ -195,6 +195,51 @@ def _run_chunk_varlen(q, k, v, g, beta, scale, h0, ht, o, l2norm, bounds):
     _lib.check(code, "ivl_gdn_chunk_fwd_varlen")
 
 
+def chunk_gated_delta_rule_fused(xq: torch.Tensor, xk: torch.Tensor, v: torch.Tensor, a: torch.Tensor, b: torch.Tensor,
+                                 conv_weight_q: torch.Tensor, conv_weight_k: torch.Tensor, A_log: torch.Tensor,
+                                 dt_bias: torch.Tensor, conv_state_q: Optional[torch.Tensor] = None,
+                                 conv_state_k: Optional[torch.Tensor] = None, output_conv_state: bool = False,
+                                 scale: Optional[float] = None, initial_state: Optional[torch.Tensor] = None,
+                                 output_final_state: bool = False, state_out: Optional[torch.Tensor] = None):
+    """Prefill-side fusion (`ivl_gdn_chunk_fwd_fused`): the chunk operator on the RAW q / k projection
+    outputs -- the depthwise causal conv + SiLU of q and k, the gate math and the L2 norm all run inside the operator's
+    pre-pass.  Replaces std:1263-1266 (q / k ShortConvolution), std:1293-1294 (g, beta) and std:1298-1308 in one call.
+        xq, xk [B,T,H*128] bf16 (before the conv); v [B,T,H,256] bf16 (after ITS conv); a, b [B,T,H] bf16;
+        conv_weight_* [H*128, 4] (or [H*128, 1, 4]) bf16; A_log, dt_bias [H]; conv_state_* [B, H*128, 4] or None.
+    Returns (o, final_state | None, (conv_state_q, conv_state_k) | None); bit-identical to the unfused chain."""
+    if not xq.is_cuda:
+        raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
+    B, T, D = xq.shape
+    H = a.shape[-1]
+    K = D // H
+    V = v.shape[-1]
+    if xk.shape != xq.shape or v.shape[:3] != (B, T, H) or a.shape != (B, T, H) or b.shape != (B, T, H) or K != 128:
+        raise ValueError("chunk_gated_delta_rule_fused: inconsistent operand shapes")
+    bf = lambda t: t.to(torch.bfloat16).contiguous()
+    xq, xk, v, a, b = bf(xq), bf(xk), bf(v), bf(a), bf(b)
+    wq, wk = bf(conv_weight_q.reshape(D, -1)), bf(conv_weight_k.reshape(D, -1))
+    if wq.shape[1] != 4 or wk.shape != wq.shape:
+        raise ValueError("chunk_gated_delta_rule_fused: conv kernel size must be 4")
+    A32, dt32 = A_log.detach().float().contiguous(), dt_bias.detach().float().contiguous()
+    cq = bf(conv_state_q) if conv_state_q is not None else None
+    ck = bf(conv_state_k) if conv_state_k is not None else None
+    cq_out = torch.empty(B, D, 4, dtype=torch.bfloat16, device=xq.device) if output_conv_state else None
+    ck_out = torch.empty_like(cq_out) if output_conv_state else None
+    o = torch.empty(B, T, H, V, dtype=torch.bfloat16, device=xq.device)
+    h0 = initial_state.contiguous() if initial_state is not None else None
+    ht = None
+    if output_final_state:
+        ht = state_out if state_out is not None else torch.empty(B, H, K, V, dtype=torch.float32, device=xq.device)
+    ws = gdn_workspace(B, T, H, xq.device)
+    code = _lib.load().ivl_gdn_chunk_fwd_fused(
+        xq.data_ptr(), xk.data_ptr(), v.data_ptr(), a.data_ptr(), b.data_ptr(), wq.data_ptr(), wk.data_ptr(),
+        _ptr(cq), _ptr(ck), _ptr(cq_out), _ptr(ck_out), A32.data_ptr(), dt32.data_ptr(),
+        _ptr(h0), _dtype_code(h0) if h0 is not None else 0, o.data_ptr(), _ptr(ht), _dtype_code(ht) if ht is not None else 0,
+        B, T, H, K, V, float(scale or K ** -0.5), ws.data_ptr(), ws.numel(), _stream_ptr(xq.device))
+    _lib.check(code, "ivl_gdn_chunk_fwd_fused")
+    return o, ht, ((cq_out, ck_out) if output_conv_state else None)
+
+
 def chunk_gated_delta_rule(
     q: torch.Tensor,
     k: torch.Tensor,

@@ -130,6 +130,31 @@ def test_gated_deltanet_mixer_and_streaming(M):
     assert err_ratio(rconv[2], lin.conv_state_v.float().cpu()) < 1e-2
 
 
+@pytest.mark.parametrize("B", [1, 2])
+def test_fused_prefill_is_bit_identical_to_the_kernel_chain(M, monkeypatch, B):
+    """Prefill-side fusion: for q_len > 64 the mixer hands the RAW q / k projections and a / b to
+    ivl_gdn_chunk_fwd_fused, whose pre-pass does the depthwise conv + SiLU, the gate math and the L2 norm.  Same
+    expressions, same rounding points as ivl_short_conv_fwd + ivl_gdn_gate_fwd + ivl_gdn_chunk_fwd: outputs, the
+    recurrent state and the carried conv tails must be equal bit for bit -- without a cache, with a fresh cache, and
+    continuing from a cache (tails and state carried in), with a ragged last chunk and a 3-token left context."""
+    cfg = M.HybridTextConfig(num_hidden_layers=4)
+    mod = _init(M.GatedDeltaNet(cfg, 1), 41).bfloat16().cuda()
+    x = torch.randn(B, 1000, 2048, generator=gen(42)).bfloat16().cuda()
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("IVL_GDN_FUSED_PREFILL", fused)   # "1" forces the fused path at any length
+        outs = [mod(x[:, :333])[0]]
+        cache = M.StaticCachePrealloc(config=cfg, batch_size=B, device="cuda", dtype=torch.bfloat16)
+        for a, b in ((0, 67), (67, 600), (600, 1000)):
+            outs.append(mod(x[:, a:b], past_key_values=cache, cache_position=torch.arange(a, b, device="cuda"))[0])
+        lin = cache.layers[1]
+        assert lin.seq_len == 1000
+        res[fused] = outs + [lin.recurrent_state.clone(), lin.conv_state_q.clone(), lin.conv_state_k.clone(),
+                             lin.conv_state_v.clone()]
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("B,cache_dtype", [(1, torch.bfloat16), (3, torch.bfloat16)])
 def test_fused_decode_step_is_bit_identical_to_the_kernel_chain(M, monkeypatch, B, cache_dtype):
     """q_len == 1 with a started cache runs the whole mixer core in one launch (ivl_gdn_decode_step: conv steps,
