@@ -225,6 +225,17 @@ IVL_API int ivl_swa_fwd_pos(const void* q, const int64_t* q_strides, const void*
                             int Tq, int Tk, int Hq, int Hkv, int D, int window, float scale, int64_t key_pos0,
                             void* stream);
 
+/* Packed variable-length batch (the reference reaches flash_attn_varlen_func through the HF
+ * glue when the collator packs sequences, src/llamafactory/.../dt/workflow.py:83-92): q, k, v, o [1,T,H,128], the
+ * token axis holds several sequences back to back, every sequence attends to itself only (causal, window as above
+ * per sequence).  The host cuts every sequence into query tiles of <= 128 tokens that never straddle a boundary:
+ * tile_tok0[i] first token of tile i, tile_seq_lo/hi[i] the [lo, hi) token range of its sequence (device int32).
+ * Key tiles are anchored at the start of each sequence: bit-identical to running the sequences one by one. */
+IVL_API int ivl_swa_fwd_varlen(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides,
+                               const void* v, const int64_t* v_strides, void* o, const int64_t* o_strides, int T,
+                               int Hq, int Hkv, int D, int window, float scale, const int32_t* tile_tok0,
+                               const int32_t* tile_seq_lo, const int32_t* tile_seq_hi, int num_tiles, void* stream);
+
 /* Decode step of the same attention: ONE new query token per sequence (Tq == 1) against the
  * cached window, split over the key axis (HBM-bound).  q, o bf16 [B,1,Hq,128] contiguous; k, v as
  * above.  workspace: ivl_swa_decode_workspace_bytes(B, Tk, Hq) bytes of fp32 scratch. */
@@ -272,6 +283,12 @@ IVL_API int ivl_swa_ring_fwd(const void* q, const int64_t* q_strides, const void
  * cache_in is left context (pip-fla semantics); cache_out must not alias cache_in.  D % 8 == 0. */
 IVL_API int ivl_short_conv_fwd(const void* x, const void* w, const void* cache_in, void* y, void* cache_out,
                                int B, int T, int D, int activation_silu, void* stream);
+
+/* Packed variable-length batch (cu_seqlens; fla/modules/convolution.py:224-251): x, y bf16 [1,T,D], no carried
+ * tail; left_ctx uint8 [T] = min(3, number of tokens of the token's own sequence before it), so the window never
+ * reaches into an earlier sequence. */
+IVL_API int ivl_short_conv_fwd_varlen(const void* x, const void* w, void* y, const uint8_t* left_ctx, int T, int D,
+                                      int activation_silu, void* stream);
 
 /* g = -exp(A_log[h]) * softplus(a + dt_bias[h]) (fp32), beta = sigmoid(b) (bf16) -- std:1293-1294.
  * a, b bf16 [n_tokens, H] (outputs of a_proj / b_proj); A_log, dt_bias fp32 [H]. */

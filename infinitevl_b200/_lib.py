@@ -45,6 +45,7 @@ SIGNATURES = {
     "ivl_ipc_close": (c_int, [c_void_p]),
     "ivl_peer_put": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, ctypes.c_uint32, c_void_p, c_void_p]),
     "ivl_stream_wait_value32": (c_int, [c_void_p, c_void_p, ctypes.c_uint32]),
+    "ivl_swa_fwd_varlen": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ivl_swa_fwd_pos": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_float, ctypes.c_int64, c_void_p]),
     "ivl_swa_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ivl_swa_decode_fwd": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "ivl_swa_ring_decode": (c_int, [c_void_p] * 9 + [c_int] * 6 + [c_float, c_void_p, c_size_t, c_void_p]),
     "ivl_swa_ring_fwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_void_p]),
     "ivl_short_conv_fwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    "ivl_short_conv_fwd_varlen": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ivl_gdn_gate_fwd": (c_int, [c_void_p] * 6 + [ctypes.c_int64, c_int, c_void_p]),
     "ivl_rmsnorm_gated_fwd": (c_int, [c_void_p] * 4 + [ctypes.c_int64, c_int, c_float, c_void_p]),
     "ivl_mrope_apply": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),

@@ -8,6 +8,8 @@
 //   rmsnorm_gated   : y = x rsqrt(mean x^2 + eps) w * gate sigmoid(gate) over 256-wide head vectors
 //                     (fla/modules/fused_norm_gate.py:26-95)
 // All are coalesced 16-byte-vector streaming kernels; fp32 math, bf16 I/O.
+#include <stdint.h>
+
 #include "sm100.cuh"
 
 namespace ivl {
@@ -34,7 +36,8 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x));
 __global__ void __launch_bounds__(CONV_THREADS)
 short_conv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                   const __nv_bfloat16* __restrict__ cache_in, __nv_bfloat16* __restrict__ y,
-                  __nv_bfloat16* __restrict__ cache_out, int T, int D, int act) {
+                  __nv_bfloat16* __restrict__ cache_out, int T, int D, int act,
+                  const uint8_t* __restrict__ left_ctx) {
   const int c0 = (blockIdx.x * CONV_THREADS + threadIdx.x) * 8;  // first of 8 channels
   if (c0 >= D) return;
   const int b = blockIdx.z;
@@ -73,11 +76,14 @@ short_conv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   for (int t = t0; t < t1; ++t) {
     load_row(t, cur);
     float out[8];
+    // packed sequences (cu_seqlens; fla/modules/convolution.py:224-251): left_ctx[t] = min(3, tokens of t's own
+    // sequence before t) -- inputs of an earlier sequence never enter the window
+    const int m = left_ctx ? (int)left_ctx[(size_t)b * T + t] : 3;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float a = wt[e][0] * h0[e];
-      a = fmaf(wt[e][1], h1[e], a);
-      a = fmaf(wt[e][2], h2[e], a);
+      float a = wt[e][0] * (m >= 3 ? h0[e] : 0.f);
+      a = fmaf(wt[e][1], m >= 2 ? h1[e] : 0.f, a);
+      a = fmaf(wt[e][2], m >= 1 ? h2[e] : 0.f, a);
       a = fmaf(wt[e][3], cur[e], a);
       out[e] = act ? silu(a) : a;
       h0[e] = h1[e]; h1[e] = h2[e]; h2[e] = cur[e];
@@ -140,12 +146,12 @@ rmsnorm_gated_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 }  // namespace
 
 cudaError_t launch_short_conv(const void* x, const void* w, const void* cache_in, void* y, void* cache_out, int B,
-                              int T, int D, int act, cudaStream_t stream) {
+                              int T, int D, int act, cudaStream_t stream, const uint8_t* left_ctx) {
   dim3 grid((D / 8 + CONV_THREADS - 1) / CONV_THREADS, (T + CONV_TT - 1) / CONV_TT, B);
   short_conv_kernel<<<grid, CONV_THREADS, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
       static_cast<const __nv_bfloat16*>(cache_in), static_cast<__nv_bfloat16*>(y),
-      static_cast<__nv_bfloat16*>(cache_out), T, D, act);
+      static_cast<__nv_bfloat16*>(cache_out), T, D, act, left_ctx);
   return cudaGetLastError();
 }
 

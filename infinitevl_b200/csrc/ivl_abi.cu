@@ -36,7 +36,8 @@ cudaError_t launch_gdn_recurrent(const void* q, const void* k, const void* v, co
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
                            int window, float scale, const int* ring_state, int ring_R, long long key_pos0,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const int* vt_tok0 = nullptr, const int* vt_lo = nullptr,
+                           const int* vt_hi = nullptr, int vt_tiles = 0);
 cudaError_t launch_peer_put(void* dst, const void* src, size_t bytes, uint32_t* flag, uint32_t value, uint32_t* counter,
                             cudaStream_t stream);
 size_t swa_ring_decode_workspace_bytes(int B, int Hq, int window);
@@ -52,7 +53,7 @@ cudaError_t launch_gdn_bwd(const float* qn, const float* kn, const void* v, cons
                            float* dg, float* dbeta, float* dh0, float* workspace, int B, int T, int H, float scale,
                            cudaStream_t stream);
 cudaError_t launch_short_conv(const void* x, const void* w, const void* cache_in, void* y, void* cache_out, int B,
-                              int T, int D, int act, cudaStream_t stream);
+                              int T, int D, int act, cudaStream_t stream, const uint8_t* left_ctx = nullptr);
 cudaError_t launch_gdn_gate(const void* a, const void* b, const float* A_log, const float* dt_bias, float* g,
                             void* beta, long long n, int H, cudaStream_t stream);
 cudaError_t launch_rmsnorm_gated(const void* x, const void* gate, const void* w, void* y, long long rows, float eps,
@@ -567,6 +568,30 @@ int ivl_swa_fwd_pos(const void* q, const int64_t* q_strides, const void* k, cons
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 
+int ivl_swa_fwd_varlen(const void* q, const int64_t* q_strides, const void* k, const int64_t* k_strides, const void* v,
+                       const int64_t* v_strides, void* o, const int64_t* o_strides, int T, int Hq, int Hkv, int D,
+                       int window, float scale, const int32_t* tile_tok0, const int32_t* tile_seq_lo,
+                       const int32_t* tile_seq_hi, int num_tiles, void* stream) {
+  if (T <= 0 || Hq <= 0 || Hkv <= 0 || Hq % Hkv != 0 || D != 128 || num_tiles <= 0 || num_tiles > 65535)
+    return IVL_ERR_BAD_SHAPE;
+  if (!q || !k || !v || !o || !q_strides || !k_strides || !v_strides || !o_strides || !tile_tok0 || !tile_seq_lo ||
+      !tile_seq_hi)
+    return IVL_ERR_NULL;
+  long long qs[3], ks[3], vs[3], os[3];
+  for (int i = 0; i < 3; ++i) {
+    qs[i] = q_strides[i]; ks[i] = k_strides[i]; vs[i] = v_strides[i]; os[i] = o_strides[i];
+    if ((qs[i] | ks[i] | vs[i] | os[i]) & 7) return IVL_ERR_BAD_SHAPE;
+  }
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+       reinterpret_cast<uintptr_t>(o)) & 15)
+    return IVL_ERR_BAD_SHAPE;
+  const float sc = scale > 0.f ? scale : 1.0f / sqrtf((float)D);
+  IVL_ARCH();
+  cudaError_t e = ivl::launch_swa_fwd(q, qs, k, ks, v, vs, o, os, 1, T, T, Hq, Hkv, window, sc, nullptr, 0, 0,
+                                      static_cast<cudaStream_t>(stream), tile_tok0, tile_seq_lo, tile_seq_hi, num_tiles);
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
 // ---- ring-buffer window cache -------------------------------------------------------------------------------
 size_t ivl_swa_ring_workspace_bytes(int B, int Hq, int window) {
   if (B <= 0 || Hq <= 0 || window <= 0) return 0;
@@ -668,6 +693,16 @@ int ivl_short_conv_fwd(const void* x, const void* w, const void* cache_in, void*
   IVL_ARCH();
   cudaError_t e = ivl::launch_short_conv(x, w, cache_in, y, cache_out, B, T, D, activation_silu,
                                          static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
+}
+
+int ivl_short_conv_fwd_varlen(const void* x, const void* w, void* y, const uint8_t* left_ctx, int T, int D,
+                              int activation_silu, void* stream) {
+  if (T <= 0 || D <= 0 || (D & 7) || (T + 31) / 32 > 65535) return IVL_ERR_BAD_SHAPE;
+  if (!x || !w || !y || !left_ctx) return IVL_ERR_NULL;
+  IVL_ARCH();
+  cudaError_t e = ivl::launch_short_conv(x, w, nullptr, y, nullptr, 1, T, D, activation_silu,
+                                         static_cast<cudaStream_t>(stream), left_ctx);
   return e == cudaSuccess ? IVL_OK : IVL_ERR_LAUNCH;
 }
 

@@ -73,6 +73,12 @@ struct SwaArgs {
   // tokens, or as halo + local shard: chunked, streamed and sequence-sharded prefills are bit-identical to the
   // one-shot prefill.  The partial first tile starts before key 0 (TMA zero-fills, the mask hides it).
   int kalign;
+  // packed variable-length batch (cu_seqlens of the training collator): B = 1, Tq == Tk, the
+  // token axis holds several sequences back to back.  One query tile never straddles two sequences; per tile the
+  // tables give its first token and the [lo, hi) token range of its sequence.  Null: dense batch.
+  const int* vt_tok0;
+  const int* vt_lo;
+  const int* vt_hi;
 };
 
 // 2^x for a pair of values on the FMA pipe instead of the XU pipe (two MUFU.EX2): Cody-Waite range reduction
@@ -107,7 +113,8 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, mt = blockIdx.y, b = blockIdx.z;
   const int hk = h / a.group;
-  const int i0 = mt * BM;
+  const bool packed = a.vt_tok0 != nullptr;
+  const int i0 = packed ? __ldg(a.vt_tok0 + mt) : mt * BM;
   int koff = 0, kal = a.kalign;
   if (a.ring_state != nullptr) {
     const int cum = *reinterpret_cast<const volatile int*>(a.ring_state);
@@ -116,11 +123,18 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     kal = (cum - a.Tk) & (BN - 1);
     a.window = a.Tk > a.ring_W ? a.ring_W : 0;             // the window rule of the HF glue, evaluated on the device
   }
-  const int shift = a.Tk - a.Tq;                           // bottom-right alignment
+  // [jmin, jmax): the keys this tile's queries may see at all; org: index of an aligned tile boundary (position 0 of the
+  // sequence modulo the key tile); i_end: end of the query rows that exist
+  const int jmin = packed ? __ldg(a.vt_lo + mt) : 0;
+  const int jmax = packed ? __ldg(a.vt_hi + mt) : a.Tk;
+  const int i_end = packed ? jmax : a.Tq;
+  const int org = packed ? jmin : -kal;
+  if (packed) a.window = (a.window > 0 && jmax - jmin > a.window) ? a.window : 0;   // per sequence, like the dense rule
+  const int shift = packed ? 0 : a.Tk - a.Tq;              // bottom-right alignment
   const int p_first = i0 + shift;
-  const int p_last = min(i0 + BM - 1, a.Tq - 1) + shift;
-  const int lo_key = a.window > 0 ? max(0, p_first - a.window + 1) : 0;
-  const int t_lo = (lo_key + kal) / BN, t_hi = (min(p_last, a.Tk - 1) + kal) / BN;   // tiles of the ALIGNED key axis
+  const int p_last = min(i0 + BM - 1, i_end - 1) + shift;
+  const int lo_key = a.window > 0 ? max(jmin, p_first - a.window + 1) : jmin;
+  const int t_lo = (lo_key - org) / BN, t_hi = (min(p_last, jmax - 1) - org) / BN;   // tiles of the ALIGNED key axis
   const int n_tiles = t_hi - t_lo + 1;
 
   if (tid == 0) {
@@ -148,7 +162,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto load_k = [&](int t) {
       const int s = t & 1;
       if (t >= 2) mbar_wait(&bars.emptyK[s], ((t >> 1) - 1) & 1);
-      const int j0 = (t_lo + t) * BN - kal;   // may be negative for the first tile: zero-filled, masked
+      const int j0 = org + (t_lo + t) * BN;   // may be negative for the first tile: zero-filled, masked
       uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullK[s], KT_BYTES_);
       tma_load_4d_ws(kd, &tmK, 0, hk, koff + j0, b, &bars.fullK[s]);
@@ -157,7 +171,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto load_v = [&](int t) {
       const int s = t & 1;
       if (t >= 2) mbar_wait(&bars.emptyV[s], ((t >> 1) - 1) & 1);
-      const int j0 = (t_lo + t) * BN - kal;
+      const int j0 = org + (t_lo + t) * BN;
       uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullV[s], KT_BYTES_);
       tma_load_4d_ws(vd, &tmV, 0, hk, koff + j0, b, &bars.fullV[s]);
@@ -225,7 +239,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint32_t r[32], r2[32];          // raw scores of keys 0..31 / 32..63 of the tile
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t & 1;
-      const int j0 = (t_lo + t) * BN - kal;
+      const int j0 = org + (t_lo + t) * BN;
       mbar_wait(&bars.s[s], (t >> 1) & 1);
       tc_fence_after();
       tmem_ld32(tlane + TM_S + s * BN, r);
@@ -236,13 +250,13 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&bars.sfree[s]);
       // masks only on boundary tiles (CTA-uniform test)
       const bool need_mask = (j0 + BN - 1 > p_first) || (a.window > 0 && j0 < p_last - a.window + 1) ||
-                             (j0 + BN > a.Tk) || (j0 < 0);
+                             (j0 + BN > jmax) || (j0 < jmin);
       if (need_mask) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int ja = j0 + i, jb = j0 + 32 + i;
-          const bool va = (ja >= 0) && (ja <= pos) && (ja < a.Tk) && (a.window <= 0 || pos - ja < a.window);
-          const bool vb = (jb >= 0) && (jb <= pos) && (jb < a.Tk) && (a.window <= 0 || pos - jb < a.window);
+          const bool va = (ja >= jmin) && (ja <= pos) && (ja < jmax) && (a.window <= 0 || pos - ja < a.window);
+          const bool vb = (jb >= jmin) && (jb <= pos) && (jb < jmax) && (a.window <= 0 || pos - jb < a.window);
           r[i] = va ? r[i] : 0xff800000u;   // -inf
           r2[i] = vb ? r2[i] : 0xff800000u;
         }
@@ -312,7 +326,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int c = 0; c < HD; c += 32) {
       tmem_ld32(tlane + TM_O + c, r);
       tmem_ld_wait();
-      if (i < a.Tq) {
+      if (i < i_end) {
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           uint4 w;
@@ -372,7 +386,8 @@ bool make_map(CUtensorMap* m, const void* ptr, int B, int T, int Hn, long long s
 cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, const long long* ks, const void* v,
                            const long long* vs, void* o, const long long* os, int B, int Tq, int Tk, int Hq, int Hkv,
                            int window, float scale, const int* ring_state, int ring_R, long long key_pos0,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const int* vt_tok0 = nullptr, const int* vt_lo = nullptr,
+                           const int* vt_hi = nullptr, int vt_tiles = 0) {
   // IVL_SWA_POLY (developer knob): pairs out of 8 whose exponentials run on the FMA pipe
   int poly = SWA_POLY_DEFAULT;
   if (const char* e = getenv("IVL_SWA_POLY")) poly = atoi(e);
@@ -399,11 +414,12 @@ cudaError_t launch_swa_fwd(const void* q, const long long* qs, const void* k, co
   a.o = static_cast<__nv_bfloat16*>(o);
   a.o_sb = os[0]; a.o_st = os[1]; a.o_sh = os[2];
   a.Tq = Tq; a.Tk = Tk; a.Hq = Hq; a.group = Hq / Hkv;
-  a.window = (window > 0 && Tk > window) ? window : 0;  // HF glue passes the window only when key_len > W
+  a.window = (window > 0 && (Tk > window || vt_tok0)) ? window : 0;  // HF glue passes the window only when key_len > W
+  a.vt_tok0 = vt_tok0; a.vt_lo = vt_lo; a.vt_hi = vt_hi;
   a.ring_state = ring_state; a.ring_R = ring_R; a.ring_W = window;
   a.kalign = (int)(key_pos0 & (BN - 1));
   a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(Hq, (Tq + BM - 1) / BM, B);
+  dim3 grid(Hq, vt_tok0 ? vt_tiles : (Tq + BM - 1) / BM, B);
   kern<<<grid, SWA_THREADS, SWA_SMEM, stream>>>(tq, tk, tv, a);
   return cudaGetLastError();
 }

@@ -55,6 +55,32 @@ def short_conv_silu(x: torch.Tensor, weight: torch.Tensor, cache: Optional[torch
     return y, out_state
 
 
+def left_context_table(cu_seqlens, T: int, device) -> torch.Tensor:
+    """uint8 [T]: min(3, tokens of the token's own sequence before it); tokens outside every sequence get 0."""
+    cu = torch.as_tensor(cu_seqlens, device=device).to(torch.int64)
+    t = torch.arange(T, device=device)
+    seq = torch.bucketize(t, cu, right=True) - 1
+    start = cu[seq.clamp(0, cu.numel() - 1)]
+    return (t - start).clamp(0, 3).to(torch.uint8).contiguous()
+
+
+def short_conv_silu_varlen(x: torch.Tensor, weight: torch.Tensor, cu_seqlens, activation: Optional[str] = "silu"):
+    """Packed batch x bf16 [1,T,D]: the conv window never crosses a sequence boundary (ivl_short_conv_fwd_varlen)."""
+    if not x.is_cuda:
+        raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
+    assert x.dtype == torch.bfloat16 and x.shape[0] == 1
+    _, T, D = x.shape
+    x = x.contiguous()
+    w = weight.reshape(D, -1).to(torch.bfloat16).contiguous()
+    assert w.shape[1] == 4, "the B200 short-conv kernel is specialised for kernel_size 4"
+    lctx = left_context_table(cu_seqlens, T, x.device)
+    y = torch.empty_like(x)
+    code = _lib.load().ivl_short_conv_fwd_varlen(x.data_ptr(), w.data_ptr(), y.data_ptr(), lctx.data_ptr(), T, D,
+                                                 1 if activation in ("silu", "swish") else 0, _stream(x))
+    _lib.check(code, "ivl_short_conv_fwd_varlen")
+    return y
+
+
 def gdn_gates(a: torch.Tensor, b: torch.Tensor, A_log: torch.Tensor, dt_bias: torch.Tensor):
     """a, b bf16 [..., H] -> (g fp32 [..., H], beta bf16 [..., H])  (std:1293-1294)."""
     H = a.shape[-1]
@@ -122,7 +148,10 @@ class ShortConvolution(nn.Module):
     def forward(self, x: torch.Tensor, cache: Optional[torch.Tensor] = None, output_final_state: bool = False,
                 cu_seqlens=None, **kwargs):
         if cu_seqlens is not None:
-            raise NotImplementedError("packed variable-length input is not supported by the B200 short conv yet")
+            # packed sequences (fla/modules/convolution.py:224-251): no carried tail, the window stops at sequence starts
+            if cache is not None or output_final_state:
+                raise ValueError("ShortConvolution: cu_seqlens excludes cache / output_final_state (as in the reference)")
+            return short_conv_silu_varlen(x, self.weight, cu_seqlens, self.activation), None
         return short_conv_silu(x, self.weight, cache, output_final_state, self.activation)
 
 
@@ -228,11 +257,10 @@ class GatedDeltaNet(nn.Module):
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 past_key_values=None, cache_position: Optional[torch.LongTensor] = None, **kwargs):
         # padding masks are ignored, exactly as the reference does (std:1223)
-        if kwargs.get("cu_seqlens") is not None:
-            # the reference forwards cu_seqlens to the convs and the kernels (std:1234,1267,1306); the B200 short
-            # conv does not cut its left context at sequence boundaries yet, so refuse instead of leaking state
-            raise NotImplementedError("packed sequences (cu_seqlens) are not supported by the B200 GatedDeltaNet "
-                                      "mixer; call ops.chunk_gated_delta_rule(cu_seqlens=...) directly")
+        cu_seqlens = kwargs.get("cu_seqlens")
+        if cu_seqlens is not None:
+            # packed sequences: the reference forwards cu_seqlens to the convs and the operator (std:1234,1267,1306)
+            return self._forward_packed(hidden_states, cu_seqlens, past_key_values)
         B, q_len, _ = hidden_states.shape
         mode = "fused_recurrent" if q_len <= 64 else self.mode
         prev_q = prev_k = prev_v = recurrent_state = None
@@ -279,6 +307,24 @@ class GatedDeltaNet(nn.Module):
         o = self.o_proj(o.reshape(B, q_len, self.num_heads * self.head_v_dim))
         return o, None
 
+
+    def _forward_packed(self, hidden_states, cu_seqlens, past_key_values):
+        """Packed variable-length batch [1, T, hidden]: every sequence is an independent scan (no cache)."""
+        if past_key_values is not None:
+            raise ValueError("cu_seqlens and a cache exclude each other (the reference's packed path is training-time)")
+        B, T, _ = hidden_states.shape
+        if B != 1:
+            raise ValueError("packed sequences come as one row [1, T, hidden] (fla/ops/gated_delta_rule/chunk.py:355-359)")
+        q, _ = self.q_conv1d(self.q_proj(hidden_states), cu_seqlens=cu_seqlens)
+        k, _ = self.k_conv1d(self.k_proj(hidden_states), cu_seqlens=cu_seqlens)
+        v, _ = self.v_conv1d(self.v_proj(hidden_states), cu_seqlens=cu_seqlens)
+        g, beta = gdn_gates(self.a_proj(hidden_states), self.b_proj(hidden_states), self.A_log, self.dt_bias)
+        o, _ = ops.chunk_gated_delta_rule(
+            q=q.view(1, T, self.num_heads, self.head_k_dim), k=k.view(1, T, self.num_key_value_heads, self.head_k_dim),
+            v=v.view(1, T, self.num_key_value_heads, self.head_v_dim), g=g, beta=beta, cu_seqlens=cu_seqlens,
+            use_qk_l2norm_in_kernel=True)
+        gate = self.g_proj(hidden_states).view(1, T, self.num_heads, self.head_v_dim)
+        return self.o_proj(self.o_norm(o, gate).reshape(1, T, self.num_heads * self.head_v_dim)), None
 
     FUSED_PREFILL_MAX_T = 4096
 
@@ -383,6 +429,12 @@ class InfiniteVLSelfAttention(nn.Module):
             cos, sin = mrope_select(cos, sin, self.rope_scaling["mrope_section"])
         mrope_apply_(q, cos, sin)
         mrope_apply_(k, cos, sin)
+        if kwargs.get("cu_seqlens") is not None:
+            # packed sequences (the HF glue's flash_attn_varlen path): self-attention per sequence, no cache
+            if past_key_values is not None:
+                raise ValueError("cu_seqlens and a cache exclude each other")
+            out = swa.swa_attention_varlen(q, k, v, kwargs["cu_seqlens"], window=self.sliding_window, scale=self.scaling)
+            return self.o_proj(out.reshape(B, q_len, self.num_heads * self.head_dim)), None
         key_states, value_states = k.transpose(1, 2), v.transpose(1, 2)  # [B,H,T,D] views, as the cache expects
         layer = past_key_values.layers[self.layer_idx] if past_key_values is not None else None
         if attention_mask is not None and attention_mask.dim() != 2:
@@ -497,12 +549,25 @@ def normalize_position_ids(position_ids, cache_position, batch_size):
     if position_ids.dim() == 3 and position_ids.shape[0] == 4:
         text_position_ids = position_ids[0]
         position_ids = position_ids[1:]
-        if text_position_ids.shape[-1] > 1 and bool((text_position_ids[:, 1:] <= text_position_ids[:, :-1]).any()):
-            raise NotImplementedError("packed sequences (text position ids restart inside the row) need "
-                                      "block-diagonal attention, which the B200 SWA kernel does not implement")
     if position_ids.dim() != 3 or position_ids.shape[0] != 3:
         raise ValueError(f"position_ids must be [B, T], [3, B, T] or [4, B, T], got {tuple(position_ids.shape)}")
     return position_ids, text_position_ids
+
+
+def packed_cu_seqlens(text_position_ids):
+    """A text position row that restarts inside the row marks packed sequences (the reference turns it into a
+    block-diagonal mask / flash_attn_varlen boundaries): returns cu_seqlens (int32 tensor on the same device) for a
+    [1, T] row with restarts, None for an ordinary row."""
+    if text_position_ids is None or text_position_ids.shape[-1] <= 1:
+        return None
+    restart = text_position_ids[:, 1:] <= text_position_ids[:, :-1]
+    if not bool(restart.any()):
+        return None
+    if text_position_ids.shape[0] != 1:
+        raise ValueError("packed sequences come as one row (batch size 1)")
+    T = text_position_ids.shape[-1]
+    cuts = (torch.nonzero(restart[0]).flatten() + 1).to(torch.int32)
+    return torch.cat([cuts.new_zeros(1), cuts, cuts.new_full((1,), T)])
 
 
 class HybridDecoder(nn.Module):
@@ -722,6 +787,14 @@ class InfiniteVLTextModel(nn.Module):
             past = past_key_values.get_seq_length() if past_key_values is not None else 0
             cache_position = torch.arange(past, past + T, device=inputs_embeds.device)
         position_ids, text_position_ids = normalize_position_ids(position_ids, cache_position.reshape(-1), B)
+        cu_seqlens = packed_cu_seqlens(text_position_ids)
+        extra = {}
+        if cu_seqlens is not None:
+            # packed training rows: every mixer treats the sequences separately (varlen operators); no cache
+            if past_key_values is not None and past_key_values.get_seq_length() > 0:
+                raise ValueError("packed sequences cannot continue a cache")
+            past_key_values, use_cache = None, False
+            extra["cu_seqlens"] = cu_seqlens
         # The reference builds its mask through create_causal_mask; on its FA2 path that is the 2-D padding mask when
         # something is padded and None otherwise (causality and the window live in the kernel).  Same here: an
         # all-ones mask is dropped, a real padding mask travels to the attention operator, which refuses it.
@@ -738,7 +811,7 @@ class InfiniteVLTextModel(nn.Module):
                 all_hidden += (h,)
             h = layer(h, attention_mask=attention_mask, position_ids=text_position_ids,
                       past_key_values=past_key_values, use_cache=use_cache, cache_position=cache_position,
-                      position_embeddings=(cos, sin))[0]
+                      position_embeddings=(cos, sin), **extra)[0]
         h = self.norm(h)
         if output_hidden_states:
             all_hidden += (h,)

@@ -64,6 +64,36 @@ def swa_attention_bthd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window
     return out
 
 
+def swa_attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens, window: Optional[int] = None,
+                         scale: Optional[float] = None) -> torch.Tensor:
+    """Packed batch: q [1,T,Hq,128], k/v [1,T,Hkv,128] holding len(cu_seqlens) - 1 sequences back to back
+    (cu_seqlens: boundaries, tensor or list); every sequence attends to itself only.  -> [1,T,Hq,128]; tokens outside
+    every sequence come out zero."""
+    if not q.is_cuda:
+        raise _lib.IvlError("infinitevl_b200 operators run on CUDA tensors only (no CPU fallback)")
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16 and q.shape[0] == 1 and k.shape[:2] == q.shape[:2] == v.shape[:2]
+    _, T, Hq, D = q.shape
+    Hkv = k.shape[2]
+    bounds = [int(x) for x in (cu_seqlens.tolist() if hasattr(cu_seqlens, "tolist") else cu_seqlens)]
+    tok0, lo, hi = [], [], []
+    for s0, s1 in zip(bounds[:-1], bounds[1:]):
+        for t in range(s0, s1, 128):
+            tok0.append(t); lo.append(s0); hi.append(s1)
+    out = torch.zeros(1, T, Hq, D, dtype=torch.bfloat16, device=q.device)
+    if not tok0:
+        return out
+    fix = lambda t: t if (t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3]) and t.data_ptr() % 16 == 0) \
+        else t.contiguous()
+    q, k, v = fix(q), fix(k), fix(v)
+    tab = torch.tensor([tok0, lo, hi], dtype=torch.int32).to(q.device)
+    code = _lib.load().ivl_swa_fwd_varlen(q.data_ptr(), _strides3(q), k.data_ptr(), _strides3(k), v.data_ptr(), _strides3(v),
+                                          out.data_ptr(), _strides3(out), T, Hq, Hkv, D, int(window or 0), float(scale or 0.0),
+                                          tab[0].data_ptr(), tab[1].data_ptr(), tab[2].data_ptr(), len(tok0),
+                                          torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(code, "ivl_swa_fwd_varlen")
+    return out
+
+
 def swa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window: Optional[int] = None,
                   scale: Optional[float] = None, key_pos0: int = 0) -> torch.Tensor:
     """HF head-first layout: q [B,Hq,Tq,D], k/v [B,Hkv,Tk,D] -> [B,Tq,Hq,D]."""
@@ -84,6 +114,10 @@ def sliding_window_attention_forward(module, query: torch.Tensor, key: torch.Ten
         raise NotImplementedError("attention dropout is not supported (inference / dropout=0 training only)")
     if scaling is None:
         scaling = query.shape[-1] ** -0.5
+    cu = kwargs.get("cu_seqlens", kwargs.get("cu_seq_lens_q"))
+    if cu is not None:   # packed sequences (the HF glue's flash_attn_varlen path): self-attention per sequence
+        return swa_attention_varlen(query.transpose(1, 2), key.transpose(1, 2), value.transpose(1, 2), cu,
+                                    window=sliding_window, scale=scaling), None
     # key_position_offset (extension keyword): position of key[:, :, 0] in the sequence, see swa_attention_bthd
     out = swa_attention(query, key, value, window=sliding_window, scale=scaling,
                         key_pos0=int(kwargs.get("key_position_offset", 0) or 0))

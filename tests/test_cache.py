@@ -103,7 +103,8 @@ def test_cache_container_and_demo_clone_protocol():
 
 def test_position_id_normalisation_matches_reference_rules():
     """InfiniteVLTextModel.forward (std:1512-1525): default positions from cache_position, 2-D ids broadcast to the
-    three M-RoPE rows, the 4-row packed form split into text row + M-RoPE rows; restarts are refused."""
+    three M-RoPE rows, the 4-row packed form split into text row + M-RoPE rows; a text row that restarts marks packed
+    sequences and turns into cu_seqlens (one row only)."""
     import pytest
     from infinitevl_b200.modeling import normalize_position_ids
     cp = torch.arange(5, 9)
@@ -117,8 +118,13 @@ def test_position_id_normalisation_matches_reference_rules():
     assert torch.equal(t, ids) and torch.equal(p, four[1:])
     packed = four.clone()
     packed[0, 0] = torch.tensor([0, 1, 0, 1])
-    with pytest.raises(NotImplementedError):
-        normalize_position_ids(packed, cp, 2)
+    from infinitevl_b200.modeling import packed_cu_seqlens
+    _, text = normalize_position_ids(packed, cp, 2)
+    with pytest.raises(ValueError):
+        packed_cu_seqlens(text)                     # two rows: packed sequences come as one row
+    one = torch.tensor([[0, 1, 2, 0, 1, 0, 1, 2, 3]])
+    assert packed_cu_seqlens(one).tolist() == [0, 3, 5, 9]
+    assert packed_cu_seqlens(torch.arange(7)[None]) is None
     with pytest.raises(ValueError):
         normalize_position_ids(torch.zeros(2, 2, 4, dtype=torch.long), cp, 2)
 

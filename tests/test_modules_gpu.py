@@ -130,6 +130,35 @@ def test_gated_deltanet_mixer_and_streaming(M):
     assert err_ratio(rconv[2], lin.conv_state_v.float().cpu()) < 1e-2
 
 
+def test_packed_sequences_through_both_mixers(M):
+    """cu_seqlens through the mixers (short conv whose window stops at sequence starts, the packed
+    chunk operator, the packed attention kernel): a packed row equals the sequences run one by one."""
+    cfg = M.HybridTextConfig(num_hidden_layers=4)
+    bounds = [0, 70, 71, 400, 1000]
+    cu = torch.tensor(bounds, dtype=torch.int32, device="cuda")
+    x = torch.randn(1, 1000, 2048, generator=gen(52)).bfloat16().cuda()
+    # short conv: bit-identical to per-sequence calls
+    w = (torch.randn(2048, 1, 4, generator=gen(53)) * 0.5).bfloat16().cuda()
+    y = M.short_conv_silu_varlen(x, w, cu)
+    for s0, s1 in zip(bounds[:-1], bounds[1:]):
+        assert torch.equal(y[:, s0:s1], M.short_conv_silu(x[:, s0:s1], w)[0])
+    gdn = _init(M.GatedDeltaNet(cfg, 1), 51).bfloat16().cuda()
+    out, _ = gdn(x, cu_seqlens=cu)
+    for s0, s1 in zip(bounds[:-1], bounds[1:]):
+        one, _ = gdn(x[:, s0:s1])
+        # (sequences of <= 64 tokens take the token recurrence when run alone, the chunk kernel when packed)
+        assert err_ratio(one.float(), out[:, s0:s1].float()) < (1.5e-2 if s1 - s0 <= 64 else 1e-6), (s0, s1)
+    attn = _init(M.InfiniteVLSelfAttention(cfg, 0), 54).bfloat16().cuda()
+    pos = torch.cat([torch.arange(s1 - s0) for s0, s1 in zip(bounds[:-1], bounds[1:])]).cuda()
+    cos, sin = attn.rotary_emb(x, pos[None, None].expand(3, 1, -1))     # [3, 1, T, 128]
+    out, _ = attn(x, position_embeddings=(cos, sin), cu_seqlens=cu)
+    for s0, s1 in zip(bounds[:-1], bounds[1:]):
+        if s1 - s0 < 2:
+            continue
+        one, _ = attn(x[:, s0:s1], position_embeddings=(cos[:, :, s0:s1], sin[:, :, s0:s1]))
+        assert err_ratio(one.float(), out[:, s0:s1].float()) < 1e-6, (s0, s1)
+
+
 @pytest.mark.parametrize("B", [1, 2])
 def test_fused_prefill_is_bit_identical_to_the_kernel_chain(M, monkeypatch, B):
     """Prefill-side fusion: for q_len > 64 the mixer hands the RAW q / k projections and a / b to

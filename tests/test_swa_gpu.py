@@ -156,3 +156,27 @@ def test_chunked_prefill_is_bit_identical_to_one_shot(swa, window):
     # without the anchor the same cut differs in the last bits (different tiles -> different roundings of P)
     out = swa.swa_attention_bthd(q[:, 5001:9003], k[:, max(0, 5001 - W1):9003], v[:, max(0, 5001 - W1):9003], window=window)
     assert err_ratio(full[:, 5001:9003].float(), out.float()) < 5e-3
+
+
+@pytest.mark.parametrize("window", [None, 300])
+def test_packed_sequences_match_per_sequence_calls(swa, window):
+    """a packed row of several sequences (cu_seqlens) through ivl_swa_fwd_varlen -- every sequence
+    attends to itself only.  Key tiles are anchored at each sequence's start, so the result is bit-identical to
+    running the sequences one by one; tokens outside every sequence come out zero; and it matches the oracle."""
+    bounds = [0, 5, 133, 133, 700, 1500, 1501]          # lengths 5, 128, 0, 567, 800, 1 (+ 35 unowned tokens)
+    T = 1536
+    q, k, v = _qkv(1, 16, 2, T, T, seed=123)
+    q, k, v = q.cuda().transpose(1, 2), k.cuda().transpose(1, 2), v.cuda().transpose(1, 2)
+    out = swa.swa_attention_varlen(q, k, v, torch.tensor(bounds), window=window)
+    assert out.shape == (1, T, 16, 128) and torch.isfinite(out).all()
+    assert bool((out[:, bounds[-1]:] == 0).all())
+    for s0, s1 in zip(bounds[:-1], bounds[1:]):
+        if s1 - s0 < 2:
+            continue     # a single query takes the split-KV decode kernel in the dense entry point
+        one = swa.swa_attention_bthd(q[:, s0:s1], k[:, s0:s1], v[:, s0:s1], window=window)
+        assert torch.equal(out[:, s0:s1], one), (s0, s1)
+        ref = swa_attention_ref(q[:, s0:s1].transpose(1, 2).cpu(), k[:, s0:s1].transpose(1, 2).cpu(),
+                                v[:, s0:s1].transpose(1, 2).cpu(), window=window)
+        assert err_ratio(ref, out[:, s0:s1].float().cpu()) < 5e-3
+    # a one-token sequence attends to itself: the output is its value row (per kv group)
+    assert torch.equal(out[0, 1500, :8], v[0, 1500, 0].expand(8, 128)) and torch.equal(out[0, 1500, 8:], v[0, 1500, 1].expand(8, 128))
