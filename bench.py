@@ -32,10 +32,10 @@ HQ, HKV, D, WINDOW = 16, 2, 128, 8192
 GDN_BYTES_PER_TOKEN = 24672          # q,k,v,g,beta read + o written, per token per layer
 GDN_STATE_BYTES = 2 * H * K * V * 4  # h0 read + hT written, per sequence per layer
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE overlapped ivl_gdn_chunk_fwd call at T = 131072 (prep + scan
-# running concurrently), from the committed ncu range-replay capture profiles/r02d_range_overlapped.csv
-# (transposed scan: 4 769 495 552 read + 3 204 179 200 written; the round-1 row-major scan with U slices measured
-# 10.98 GB, profiles/r01h_range_overlapped.csv); refreshed whenever the kernels change
-GDN_DRAM_TRAFFIC_NCU = 7973674752
+# running concurrently, 24-chunk L2 image ring), from the committed ncu range-replay capture
+# profiles/r02f_range_ring24.csv (2 452 369 664 read + 1 224 527 872 written; without the ring 7.97 GB,
+# profiles/r02d_range_overlapped.csv; round 1: 10.98 GB); refreshed whenever the kernels change
+GDN_DRAM_TRAFFIC_NCU = 3676897536
 
 
 def swa_flops(T, Tk_prefix=0):
@@ -451,8 +451,9 @@ def run_ours(args):
                 "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": GDN_DRAM_TRAFFIC_NCU if (T_local == 131072 and world == 1) else None,
                 "traffic_note": "ncu --replay-mode range over one overlapped operator call (kernel replay would serialise "
-                                "the two kernels): prep reads q, k, g, beta and writes 64 KiB of operand images per chunk and head, the "
-                                "scan reads them back plus v and writes o; see profiles/r02_summary.md",
+                                "the two kernels): prep reads q, k, g, beta and hands 64 KiB of operand images per chunk and head to "
+                                "the scan through a 24-chunk ring that stays in L2; the scan also reads v and writes o; see "
+                                "profiles/r02_summary.md",
                 "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg_bytes}
         kernels = {"gdn_layer_ms": round(t_layer, 4), "gdn_prep_alone_ms": round(t_prep, 4),
                    "gdn_scan_alone_ms": round(t_scan, 4)}

@@ -100,6 +100,7 @@ struct GdnWorkspace {
   uint8_t* ublob;      // [B][H][ring][NS][UBLOB_BYTES]
   uint32_t* ready;     // [B][H][NT]
   uint32_t* progress;  // [B][H][GDN_NS]
+  uint32_t* checkin;   // one word: scan CTAs that are resident (zeroed with the flags; gates prep's launch when a ring is used)
   int ring;            // chunk slots per head (<= NT)
 };
 
@@ -108,7 +109,7 @@ __host__ __device__ inline int gdn_num_chunks(int T) { return (T + GDN_C - 1) / 
 // flags + progress counters (one memset), rounded to 1 KiB; they sit at the FRONT of the workspace so that
 // their address does not depend on the ring length
 __host__ inline size_t gdn_sync_bytes(int B, int T, int H) {
-  size_t n = (size_t)B * H * (gdn_num_chunks(T) + GDN_NS) * sizeof(uint32_t);
+  size_t n = ((size_t)B * H * (gdn_num_chunks(T) + GDN_NS) + 1) * sizeof(uint32_t);
   return (n + 1023) / 1024 * 1024;
 }
 
@@ -126,6 +127,7 @@ __host__ inline GdnWorkspace gdn_carve(void* ws, int B, int T, int H, int ring) 
   GdnWorkspace w;
   w.ready = static_cast<uint32_t*>(ws);
   w.progress = w.ready + (size_t)B * H * NT;
+  w.checkin = w.progress + (size_t)B * H * GDN_NS;
   w.blob = static_cast<uint8_t*>(ws) + gdn_sync_bytes(B, T, H);
   w.ublob = w.blob + n * BLOB_BYTES;
   w.ring = ring;

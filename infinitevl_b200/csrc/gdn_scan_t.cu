@@ -118,6 +118,8 @@ gdn_scan_t_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, GdnV
   const size_t slot0 = ((size_t)b * H + h) * ws.ring;
   const int ring = ws.ring;
   const int col0 = vh * 128;
+  // resident: with an image ring the pre-pass is only launched once every scan CTA has checked in (ivl_abi.cu)
+  if (tid == 0) atomicAdd(ws.checkin, 1u);
   if (NT <= 0) {
     // empty sequence: the final state is the initial state
     if (ht != nullptr) {
@@ -459,6 +461,8 @@ gdn_scan_t2_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   const size_t slot0 = ((size_t)b * H + h) * ws.ring;
   const int ring = ws.ring;
   const int col0 = vh * 128;
+  // resident: with an image ring the pre-pass is only launched once every scan CTA has checked in (ivl_abi.cu)
+  if (tid == 0) atomicAdd(ws.checkin, 1u);
   if (NT <= 0) {
     if (ht != nullptr) {
       const size_t base = ((size_t)seq * H + h) * GDN_K * GDN_V;
@@ -906,6 +910,8 @@ gdn_scan_t3_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
   const size_t slot0 = ((size_t)b * H + h) * ws.ring;
   const int ring = ws.ring;
   const int col0 = vh * 128;
+  // resident: with an image ring the pre-pass is only launched once every scan CTA has checked in (ivl_abi.cu)
+  if (tid == 0) atomicAdd(ws.checkin, 1u);
   if (NT <= 0) {
     // empty sequence: the final state is the initial state
     if (ht != nullptr) {

@@ -101,6 +101,10 @@ inline int env_int(const char* name, int dflt) {
 //                 3 = transposed scan, pipelined form (default): the operands of form 1, but the state / v_new hand-offs
 //                     to the tensor pipe are pipelined over the contraction dimension and the output products leave
 //                     the serial chain (gdn_scan_t3_kernel)
+// Chunks per head of the L2 image ring of the overlapped operator (0 = off).  24 measured best at 128K tokens: DRAM
+// traffic of a call 7.97 -> 3.68 GB (1.14 x algorithmic), operator 2.15 -> 2.16 ms alone, the 36-layer step 134.2 ->
+// 131.2 ms (less HBM power under the 1000 W cap); 20 stalls prep (2.22 ms), 32 starts to spill (4.94 GB).
+constexpr int GDN_RING_DEFAULT = 24;
 inline int tscan_mode() { const int m = env_int("IVL_GDN_TSCAN", 3); return (m >= 0 && m <= 3) ? m : 3; }
 inline int prep_mode(int tscan) { return tscan == 3 ? 1 : tscan; }   // form 3 reads the images of form 1
 inline bool tscan() { return tscan_mode() != 0; }
@@ -414,15 +418,19 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
       IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, scan_bv(32), st));
     return IVL_OK;
   }
-  // The image ring (gdn_layout.cuh: prep reuses a short ring of chunk slots and waits for the scan's progress)
-  // stays disabled: it does keep the images in L2 (4.2 GB instead of 9.4 GB of DRAM traffic at 128K tokens with a
-  // 16-chunk ring, ncu range replay) but prep needs ~16 chunks in flight, so the kernels then wait on each other
-  // (5 ms instead of 2.4 ms), and a randomised soak (tools/soak_gdn.py) found a hang with back-to-back calls: prep
-  // CTAs become resident before the scan's (which need a whole SM each), and once every SM holds a prep CTA that
-  // waits for scan progress the scan can never start.  A ring needs the scan's residency established first.
-  // The device code paths are kept for the next prep design; ring == chunks per row makes them inert.
+  // Image ring (gdn_layout.cuh): prep reuses a short ring of chunk slots per head and waits for the scan's progress
+  // before it overwrites one, so the operand images are produced and consumed inside L2 and never travel to HBM
+  // (the round trip is 2 x 2.1 GB of the call's 7.97 GB of DRAM traffic at 128K tokens).  Round 1 found two problems:
+  // prep needs ~16-22 chunks in flight per head, so a ring shorter than that makes the two kernels wait on each other,
+  // and -- a real hang -- prep CTAs could become resident before the scan's (which need a whole SM each); once every
+  // SM held a prep CTA waiting for scan progress the scan could never start.  Residency is now established first:
+  // every scan CTA checks in (ws.checkin) and the prep launch waits for the full count with a stream memory operation
+  // on the helper stream.  After that the oldest unfinished prep CTA only ever waits for a scan that only waits for
+  // older chunks: no cycle.  Transposed scans, dense batches, not under stream capture (IVL_GDN_RING chunks; 0 = off).
   const int bv = bv_overlap;
-  const int ring = 0;
+  int ring = env_int("IVL_GDN_RING", GDN_RING_DEFAULT);
+  if (!tr || vl.chunk_tok0 != nullptr || cap != cudaStreamCaptureStatusNone || ring < 0 || ring >= num_chunks) ring = 0;
+  if (ring > 0 && ring < 4) ring = 4;
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, ring);
   IVL_CUDA(ivl::configure_gdn_prep());  // prep must be loaded before a scan that waits for it is running
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
@@ -432,6 +440,13 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
     IVL_CUDA(ivl::launch_gdn_scan_t(v, ws, vl, num_chunks, nseq, B, h0, h0_dtype, o, ht, ht_dtype, T, H, trm, st));
   else
     IVL_CUDA(ivl::launch_gdn_scan(ws, vl, num_chunks, nseq, h0, h0_dtype, o, ht, ht_dtype, T, H, bv, st));
+  if (ring > 0) {
+    const int scan_ctas = nseq * H * (ivl::GDN_V / bv);
+    // (ncu range replay refuses stream memory operations; a profiled run of a single call goes without the handshake --
+    // the hazard it removes needs a previous call still draining -- and both wait loops trap instead of hanging)
+    if (!tool_attached())
+      if (int e = ivl_stream_wait_value32(fj->aux, ws.checkin, (uint32_t)scan_ctas)) return e;
+  }
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv,
                                 prep_mode(trm), fj->aux, fused));

@@ -29,7 +29,7 @@ while time.time() < t_end:
         N = len(cu) - 1
     state_bf16 = rng.random() < 0.3
     pipe, bv = rng.choice(["0", "1", "1", "1"]), rng.choice(["32", "64", "64", "128"])
-    ring = rng.choice(["0", "0", "8", "16", "40"]) if (pipe == "1" and not packed) else "0"   # (knob is inert now)
+    ring = rng.choice(["0", "8", "16", "24", "24", "40"]) if (pipe == "1" and not packed) else "0"
     reps = rng.randint(1, 3)
     only = os.environ.get("SOAK_ONLY")
     if only is not None and trials not in [int(x) for x in only.split(",")]:
