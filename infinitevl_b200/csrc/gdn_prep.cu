@@ -14,9 +14,12 @@
 //   Wg = (T diag(beta exp G)) Kn,   U = (T diag(beta)) V      bf16 operands, fp32 accumulate
 //   P  = tril(Qn Kn^T * Gamma) * scale,  Qg = Qn exp(G) scale,  Kt = Kn exp(G_C - G)
 //
-// This kernel is throughput work (32K independent CTAs at 128K tokens); it uses the
-// warp-level mma.sync path.  The latency-critical scan uses tcgen05 (gdn_scan.cu).
+// This kernel is throughput work (32K independent CTAs at 128K tokens).  For the transposed scan's images (the product
+// path) the three large products run on tcgen05 with TMEM accumulators (template flag TC below); the 16 x 16 tiles of
+// the blocked inverse use split-bf16 warp-level MMAs; the row-major / lag image modes keep the warp-level path.
 #include <atomic>
+#include <stddef.h>
+#include <stdlib.h>
 
 #include "gdn_layout.cuh"
 #include "sm100.cuh"
@@ -25,6 +28,7 @@ namespace ivl {
 
 namespace {
 
+constexpr int PREP_TC_DEFAULT = 1;   // see launch_gdn_prep
 constexpr int PREP_THREADS = 256;  // 8 warps: warp w owns rows 16*(w>>1).. of the chunk and column half (w&1)
 constexpr int KH_LD = 136;  // bf16 elements per row: 272 B, rows shift by 16 B mod 128 -> conflict-free ldmatrix
 constexpr int V_LD = 136;   // V is staged in two halves of 128 value columns
@@ -134,9 +138,9 @@ __device__ __forceinline__ void conv_row_quarter(const __nv_bfloat16* x, long lo
   }
 }
 
-template <class PieceOffset>
+template <class SmemPiece, class PieceOffset>
 __device__ __forceinline__ void norm_row_quarter(const uint4* raw, bool l2norm, float weight,
-                                                 __nv_bfloat16* smem_row, uint8_t* img, PieceOffset img_piece) {
+                                                 SmemPiece smem_piece, uint8_t* img, PieceOffset img_piece) {
   float ss = 0.f;
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
@@ -161,7 +165,7 @@ __device__ __forceinline__ void norm_row_quarter(const uint4* raw, bool l2norm, 
       n[e] = pack_bf16(bf16_lo(w[e]) * rstd, bf16_hi(w[e]) * rstd);
       g[e] = pack_bf16(bf16_lo(n[e]) * weight, bf16_hi(n[e]) * weight);
     }
-    *reinterpret_cast<uint4*>(smem_row + p * 8) = nrm;
+    *smem_piece(p) = nrm;
     *reinterpret_cast<uint4*>(img + img_piece(p)) = wgt;
   }
 }
@@ -217,7 +221,14 @@ __device__ __forceinline__ unsigned long long gtime() {
 // coupling matrix R_c = Wg_c Kt_{c-1}^T (negated, 8 KiB image behind Au); the first chunk of a sequence has
 // gamma_{-1} = 1 and R = 0.  It recomputes Kt_{c-1} from the previous chunk's k rows and g (bit-identical to the
 // image the previous chunk's CTA writes, which the state update uses).
-template <int MODE, bool FUSED = false>
+// TC = true (MODE 1 only): the three large products of the chunk -- Kn Kn^T, Qn Kn^T (M64 N64 K128) and Wg = Aw Kn
+// (M64 N128 K64) -- run on the tcgen05 tensor cores: the normalised rows are written to shared memory as 128-byte
+// swizzled UMMA tiles (the SAME Kn tile is the K-major A / B operand of the first two products and the MN-major B operand
+// of the third), accumulators live in 64 columns of tensor memory -- an M = 64 accumulator fills lanes 0..15 of every
+// lane quadrant, a second one issued with lane offset 16 fills lanes 16..31 (tools/umma_probe.cu), so two products
+// share the columns and all 32 lanes of the epilogue warps have a row to read with tcgen05.ld.
+// The 16 x 16 tiles of the blocked inverse keep their split-bf16 warp-level MMAs (they need fp32 accuracy).
+template <int MODE, bool FUSED = false, bool TC = false>
 __global__ void __launch_bounds__(PREP_THREADS, 3)
 gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                 const __nv_bfloat16* __restrict__ v, const float* __restrict__ g,
@@ -225,11 +236,28 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
                 int l2norm, int prefetch_ahead, int scan_ctas_per_head, GdnPrepFused fz) {
   constexpr bool TR = MODE != 0, LAG = MODE == 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  PrepSmem& s = *reinterpret_cast<PrepSmem*>(smem_raw);
+  // (TC: the swizzled operand tiles need 1 KiB alignment; kh, qh and vb sit at multiples of 17 KiB inside the struct)
+  PrepSmem& s = *reinterpret_cast<PrepSmem*>(TC ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw);
+  static_assert(offsetof(PrepSmem, qh) % 1024 == 0 && offsetof(PrepSmem, vb) % 1024 == 0, "tile alignment");
+  __shared__ uint64_t tc_bar[2];
+  __shared__ uint32_t tc_tmem;
+  uint8_t* const tKh = reinterpret_cast<uint8_t*>(s.kh);   // TC: Kn tile, 2 panels [64 tok][128 B], 128B swizzle
+  uint8_t* const tQh = reinterpret_cast<uint8_t*>(s.qh);   // TC: Qn tile (then T, as in the other path)
+  uint8_t* const tAw = reinterpret_cast<uint8_t*>(s.vb);   // TC: Aw tile [64][128 B], 128B swizzle
   float* const sL = s.LA;                                                  // strictly lower triangular, fp32
   __nv_bfloat16* const sAw = reinterpret_cast<__nv_bfloat16*>(s.LA);       // after the solve
   __nv_bfloat16* const sAu = sAw + 64 * A_LD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (TC) {
+    if (tid == 0) {
+      mbar_init(&tc_bar[0], 1);
+      mbar_init(&tc_bar[1], 1);
+      fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<64>(&tc_tmem);
+    tc_fence_before();
+    // (the __syncthreads() at the end of stage 0 publishes the barriers and the TMEM address)
+  }
   // CTAs are dispatched in linear block order: head fastest, then chunk, so the grid walks the sequence
   // front to back over all heads and a concurrently running scan (gdn_scan.cu) can follow it.
   const int c = blockIdx.x / H, h = blockIdx.x % H, b = blockIdx.z, NT = gridDim.x / H;
@@ -427,9 +455,16 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     const int row = tid >> 2, qt = tid & 3;
     const float Gr = s.G[row], Gc = s.G[63];
     const int R = 64 + row;  // Qg occupies rows 64..127 of the stacked [-Wg ; Qg] operand
-    norm_row_quarter(rawq, l2norm != 0, __expf(Gr) * scale, &s.qh[row * KH_LD + qt * 32],
+    // where piece p (8 elements, 16 B) of this thread's quarter row goes in shared memory: padded rows for the
+    // ldmatrix path, the 128-byte-swizzled UMMA tile (panel = 64 key dims) for the tcgen05 path
+    auto piece = [&](uint8_t* tile, __nv_bfloat16* padded, int p) {
+      const int kd = qt * 32 + p * 8;
+      return TC ? reinterpret_cast<uint4*>(tile + (kd >> 6) * 8192 + swz128((uint32_t)(row * 128 + (kd & 63) * 2)))
+                : reinterpret_cast<uint4*>(padded + row * KH_LD + kd);
+    };
+    norm_row_quarter(rawq, l2norm != 0, __expf(Gr) * scale, [&](int p) { return piece(tQh, s.qh, p); },
                      blob + BLOB_OFF_A1, [&](int p) { return a1_off<MODE>(R, (qt * 4 + p) * 8); });
-    norm_row_quarter(rawk, l2norm != 0, __expf(Gc - Gr), &s.kh[row * KH_LD + qt * 32],
+    norm_row_quarter(rawk, l2norm != 0, __expf(Gc - Gr), [&](int p) { return piece(tKh, s.kh, p); },
                      blob + BLOB_OFF_KT, [&](int p) { return kt_off<MODE>(row, (qt * 4 + p) * 8); });
     if (tid == 0) *reinterpret_cast<float*>(blob + BLOB_OFF_TAIL) = __expf(Gc);
   }
@@ -475,8 +510,60 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
   const int r0 = strip * 16;                // this warp's 16-row strip
 
   // ---- stage 2: Kn Kn^T and Qn Kn^T (lower triangle only) -> L (fp32, smem), P image -------
+  if (TC) {
+    // the tiles were written through the generic proxy: make them visible to the tensor core (async proxy)
+    fence_async_smem();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tc_tmem;
+    if (warp == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(64, 64, 0, 0);
+      const uint64_t dK = umma_desc(smem_u32(tKh), 16, 1024, SWZ_128B);
+      const uint64_t dQ = umma_desc(smem_u32(tQh), 16, 1024, SWZ_128B);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // K = 128 key dims: 2 panels x 4 slabs of 16
+        const uint32_t off = (uint32_t)((j >> 2) * 512 + (j & 3) * 2);
+        // an M = 64 accumulator fills lanes 0..15 of every 32-lane quadrant; with lane offset 16 it fills lanes 16..31:
+        // the two products share the 64 columns, and every lane of the epilogue warps has a row to work on
+        umma_bf16_ws(tm, dK + off, dK + off, idesc, j > 0);                  // lanes 32q + 0..15 : Kn Kn^T
+        umma_bf16_ws(tm + (16u << 16), dQ + off, dK + off, idesc, j > 0);    // lanes 32q + 16..31: Qn Kn^T
+      }
+      umma_commit_ws(&tc_bar[0]);
+    }
+    mbar_wait(&tc_bar[0], 0);
+    tc_fence_after();
+    // warp w: lane quadrant w & 3, columns 32 (w >> 2) .. + 31; lane l: product l >> 4 (0: Kn Kn^T -> L, 1: Qn Kn^T -> P),
+    // row 16 q + (l & 15)
+    const int q4 = warp & 3, ch = warp >> 2, sub = lane >> 4;
+    const int i = q4 * 16 + (lane & 15);
+    const float Gi = s.G[i], bi = s.beta[i];
+    uint32_t r[32];
+    tmem_ld32(tm + ((uint32_t)(q4 * 32) << 16) + ch * 32, r);
+    tmem_ld_wait();
+    float val[32];
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj)
+      val[jj] = __uint_as_float(r[jj]) * __expf(fminf(Gi - s.G[ch * 32 + jj], 0.f));
+    if (sub == 0) {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+        if (ch * 32 + jj < i) sL[i * L_LD + ch * 32 + jj] = bi * val[jj];
+    } else {
+      uint8_t* pimg = blob + BLOB_OFF_P;
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j0 = ch * 32 + g8 * 8 + 2 * e;
+          w4[e] = pack_bf16(j0 <= i ? val[g8 * 8 + 2 * e] * scale : 0.f, j0 + 1 <= i ? val[g8 * 8 + 2 * e + 1] * scale : 0.f);
+        }
+        *reinterpret_cast<uint4*>(pimg + sq_off<MODE>(i, ch * 32 + g8 * 8)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+    tc_fence_before();
+  } else {
   // warp (strip, half) computes column tiles 4*half .. 4*half+3 (32 key columns)
-  {
     float ckk[4][4], cqk[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -618,7 +705,8 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     for (int it = 0; it < 16; ++it) {
       const int i = rbase + 4 * it;
       const float tv = Tm[i * L_LD + cc];
-      sAw[i * A_LD + cc] = __float2bfloat16(tv * bw);
+      if (TC) *reinterpret_cast<__nv_bfloat16*>(tAw + swz128((uint32_t)(i * 128 + cc * 2))) = __float2bfloat16(tv * bw);
+      else sAw[i * A_LD + cc] = __float2bfloat16(tv * bw);
       sAu[i * A_LD + cc] = __float2bfloat16(tv * bu);
     }
   }
@@ -646,8 +734,44 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     }
   }
   // ---- stage 4: Wg = Aw Kn (negated, into rows 0..63 of the A1 image), U = Au V ------------
+  if (TC) {
+    fence_async_smem();      // the Aw tile was written through the generic proxy
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tc_tmem;
+    if (warp == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(64, 64, 0, /*b_mn=*/1);
+      const uint64_t dA = umma_desc(smem_u32(tAw), 16, 1024, SWZ_128B);            // K-major: 16 tokens = 32 B per MMA
+      const uint64_t dB0 = umma_desc(smem_u32(tKh), 8192, 1024, SWZ_128B);         // MN-major panel: key dims 0..63
+      const uint64_t dB1 = umma_desc(smem_u32(tKh) + 8192, 8192, 1024, SWZ_128B);  // key dims 64..127
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {   // K = 64 tokens: 16 per MMA = 2 KiB of the MN-major tile
+        umma_bf16_ws(tm, dA + j * 2, dB0 + j * 128, idesc, j > 0);                 // lanes 32q + 0..15 : key dims 0..63
+        umma_bf16_ws(tm + (16u << 16), dA + j * 2, dB1 + j * 128, idesc, j > 0);   // lanes 32q + 16..31: key dims 64..127
+      }
+      umma_commit_ws(&tc_bar[1]);
+    }
+    mbar_wait(&tc_bar[1], 0);
+    tc_fence_after();
+    const int q4 = warp & 3, ch = warp >> 2;           // lane quadrant, 32-column group
+    const int i = q4 * 16 + (lane & 15);
+    const int kd0 = (lane >> 4) * 64 + ch * 32;        // first of this thread's 32 key dims
+    uint32_t r[32];
+    tmem_ld32(tm + ((uint32_t)(q4 * 32) << 16) + ch * 32, r);
+    tmem_ld_wait();
+    uint8_t* img = blob + BLOB_OFF_A1;
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      uint4 w4;
+      w4.x = pack_bf16(-__uint_as_float(r[g8 * 8 + 0]), -__uint_as_float(r[g8 * 8 + 1]));
+      w4.y = pack_bf16(-__uint_as_float(r[g8 * 8 + 2]), -__uint_as_float(r[g8 * 8 + 3]));
+      w4.z = pack_bf16(-__uint_as_float(r[g8 * 8 + 4]), -__uint_as_float(r[g8 * 8 + 5]));
+      w4.w = pack_bf16(-__uint_as_float(r[g8 * 8 + 6]), -__uint_as_float(r[g8 * 8 + 7]));
+      *reinterpret_cast<uint4*>(img + a1_off<MODE>(i, kd0 + g8 * 8)) = w4;
+    }
+    tc_fence_before();
+  } else {
   // warp (strip, half): key dims 64*half..+63 of Wg; value columns 128*hv + 64*half..+63 of U in pass hv
-  {
     const int i0 = r0 + gq, i1 = i0 + 8;
     float acc[8][4];
 #pragma unroll
@@ -750,6 +874,10 @@ gdn_prep_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __rest
     }
   }
   PTR(7);
+  if (TC) {
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<64>(tc_tmem);
+  }
   // publish the chunk: every image store of this CTA happens-before the flag (bar.sync, then a gpu-scope
   // release by the publishing thread -- the split-K semaphore pattern).  The consumer pairs it with an acquire
   // and a proxy fence before its bulk copies (async proxy) read the images.
@@ -795,6 +923,12 @@ cudaError_t configure_gdn_prep() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gdn_prep_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PrepSmem));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gdn_prep_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(PrepSmem) + 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gdn_prep_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(PrepSmem) + 1024);
+    if (e != cudaSuccess) return e;
     configured[dev].store(true, std::memory_order_release);
   }
   return cudaSuccess;
@@ -819,9 +953,14 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
   dim3 grid((unsigned)num_chunks * (unsigned)H, 1, B);
   const bool fz = fused != nullptr && fused->wq != nullptr;
   if (fz && (transposed != 1 || vl.chunk_tok0 != nullptr)) return cudaErrorInvalidValue;   // transposed scan, dense only
-  auto kern = fz ? gdn_prep_kernel<1, true>
-                 : (transposed == 2 ? gdn_prep_kernel<2> : (transposed == 1 ? gdn_prep_kernel<1> : gdn_prep_kernel<0>));
-  kern<<<grid, PREP_THREADS, smem, stream>>>(
+  // IVL_GDN_PREP_TC (developer knob): 1 = the large products on tcgen05 (default for the transposed scan's images),
+  // 0 = warp-level mma.sync everywhere
+  static const int tc_default = [] { const char* e = getenv("IVL_GDN_PREP_TC"); return (e && *e) ? atoi(e) : PREP_TC_DEFAULT; }();
+  const bool tc = transposed == 1 && tc_default != 0;
+  auto kern = fz ? (tc ? gdn_prep_kernel<1, true, true> : gdn_prep_kernel<1, true>)
+                 : (tc ? gdn_prep_kernel<1, false, true>
+                       : (transposed == 2 ? gdn_prep_kernel<2> : (transposed == 1 ? gdn_prep_kernel<1> : gdn_prep_kernel<0>)));
+  kern<<<grid, PREP_THREADS, tc ? smem + 1024 : smem, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),
       static_cast<const __nv_bfloat16*>(v), g, static_cast<const __nv_bfloat16*>(beta), ws, vl, T, H, scale, l2norm,
       resident, scan_ctas_per_head, fz ? *fused : GdnPrepFused{});

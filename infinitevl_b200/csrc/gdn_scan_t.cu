@@ -972,7 +972,7 @@ gdn_scan_t3_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       const int sa = c % C::NA, sk = c % C::NK;
       const size_t cs = (size_t)((cb + c) % ring);  // image slot of chunk c
       const int tok0 = varlen ? __ldg(vl.chunk_tok0 + cb + c) : c * GDN_C;
-      if (c >= C::NA) mbar_wait(&bars.emptyA[sa], (c / C::NA - 1) & 1);
+      if (c >= C::NA) mbar_wait_relaxed(&bars.emptyA[sa], (c / C::NA - 1) & 1);
       uint8_t* as = smem + C::OFF_A + sa * C::ASLOT;
       mbar_arrive_expect_tx_ws(&bars.fullA[sa], C::A_TX);
       bulk_g2s_ws(as + C::A_BW, blob + cs * BLOB_BYTES + BLOB_OFF_A1, A1_BYTES, &bars.fullA[sa]);
@@ -980,7 +980,7 @@ gdn_scan_t3_kernel(const __grid_constant__ CUtensorMap tmV, GdnWorkspace ws, Gdn
       tma_load_4d_ws(as + C::A_V, &tmV, col0, h, tok0, b, &bars.fullA[sa]);
       tma_load_4d_ws(as + C::A_V + C::V_PANEL, &tmV, col0 + 64, h, tok0, b, &bars.fullA[sa]);
       if (c >= C::NK) {
-        mbar_wait(&bars.emptyK[sk], (c / C::NK - 1) & 1);
+        mbar_wait_relaxed(&bars.emptyK[sk], (c / C::NK - 1) & 1);
         // every product that read the K slot of chunk c - NK has retired, and -- the O part of a chunk is issued
         // before its C part -- so has every product that read its A slot: the image slot may be overwritten
         if (lane == 0 && ring < NTROW)

@@ -68,6 +68,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// For warps that run AHEAD of the critical path (TMA producers waiting for a free slot): back off between polls, so the
+// waiting warp does not compete for issue slots -- and power -- with the warps everybody is waiting for.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#ifdef IVL_NO_RELAXED_WAIT
+  mbar_wait(bar, parity);
+#else
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+#endif
+}
 
 // ----------------------------------------------------------------------------
 // async-proxy copies and fences

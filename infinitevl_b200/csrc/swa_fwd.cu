@@ -161,7 +161,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // order of the copies = order in which their slots come free: K(t) [after S(t-2)], then V(t-1) [after PV(t-3)]
     auto load_k = [&](int t) {
       const int s = t & 1;
-      if (t >= 2) mbar_wait(&bars.emptyK[s], ((t >> 1) - 1) & 1);
+      if (t >= 2) mbar_wait_relaxed(&bars.emptyK[s], ((t >> 1) - 1) & 1);
       const int j0 = org + (t_lo + t) * BN;   // may be negative for the first tile: zero-filled, masked
       uint8_t* kd = smem + OFF_K + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullK[s], KT_BYTES_);
@@ -170,7 +170,7 @@ swa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     };
     auto load_v = [&](int t) {
       const int s = t & 1;
-      if (t >= 2) mbar_wait(&bars.emptyV[s], ((t >> 1) - 1) & 1);
+      if (t >= 2) mbar_wait_relaxed(&bars.emptyV[s], ((t >> 1) - 1) & 1);
       const int j0 = org + (t_lo + t) * BN;
       uint8_t* vd = smem + OFF_V + s * KT_BYTES_;
       mbar_arrive_expect_tx_ws(&bars.fullV[s], KT_BYTES_);
