@@ -55,6 +55,28 @@ def short_conv_silu(x: torch.Tensor, weight: torch.Tensor, cache: Optional[torch
     return y, out_state
 
 
+def _packed_linear(owner: nn.Module, attr: str, mods, x: torch.Tensor):
+    """y_i = mods[i](x) for several nn.Linear over the same input as ONE matmul: the weights (and biases) are stacked
+    row-wise once and cached on `owner` (keyed on storage, version counter and device of every parameter, so a
+    load_state_dict / .to() / in-place update rebuilds the stack).  Costs one extra copy of the weights."""
+    params = [p for m in mods for p in (m.weight, m.bias) if p is not None]
+    key = tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in params)
+    cached = getattr(owner, attr, None)
+    if cached is None or cached[0] != key:
+        if x.is_cuda and torch.cuda.is_current_stream_capturing():
+            # never build the stack inside a graph capture (it would live in the graph's private pool): this call goes
+            # through the separate projections, an eager warm-up step builds it
+            return tuple(m(x) for m in mods)
+        with torch.no_grad():
+            W = torch.cat([m.weight for m in mods], dim=0).contiguous()
+            bias = None
+            if any(m.bias is not None for m in mods):
+                bias = torch.cat([m.bias if m.bias is not None else m.weight.new_zeros(m.weight.shape[0]) for m in mods])
+        cached = (key, W, bias, [m.weight.shape[0] for m in mods])
+        object.__setattr__(owner, attr, cached)     # (not a registered buffer: it must stay out of the state dict)
+    return torch.nn.functional.linear(x, cached[1], cached[2]).split(cached[3], dim=-1)
+
+
 def left_context_table(cu_seqlens, T: int, device) -> torch.Tensor:
     """uint8 [T]: min(3, tokens of the token's own sequence before it); tokens outside every sequence get 0."""
     cu = torch.as_tensor(cu_seqlens, device=device).to(torch.int64)
@@ -359,8 +381,14 @@ class GatedDeltaNet(nn.Module):
     def _decode_step(self, hidden_states, past_key_values, cache_position, conv_q, conv_k, conv_v, state):
         B = hidden_states.shape[0]
         H = self.num_heads
-        xq, xk, xv = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
-        a, b, gate = self.a_proj(hidden_states), self.b_proj(hidden_states), self.g_proj(hidden_states)
+        if B == 1 and os.environ.get("IVL_DECODE_PACKED_PROJ", "1") != "0":
+            # one GEMV over the six input projections stacked row-wise instead of six (a decode step is launch-bound:
+            # 2.79 -> see profiles/r02_summary.md); a one-row output splits into contiguous pieces, no copies
+            mods = (self.q_proj, self.k_proj, self.v_proj, self.a_proj, self.b_proj, self.g_proj)
+            xq, xk, xv, a, b, gate = _packed_linear(self, "_packed_in_proj", mods, hidden_states)
+        else:
+            xq, xk, xv = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+            a, b, gate = self.a_proj(hidden_states), self.b_proj(hidden_states), self.g_proj(hidden_states)
         # fp32 copies of the two per-head gate parameters, refreshed whenever the parameters change (in-place
         # update, load_state_dict, .to()): keyed on storage, version counter and device
         key = (self.A_log.data_ptr(), self.A_log._version, self.dt_bias.data_ptr(), self.dt_bias._version, xq.device)
@@ -421,9 +449,13 @@ class InfiniteVLSelfAttention(nn.Module):
                 use_cache: bool = False, cache_position: Optional[torch.LongTensor] = None,
                 position_embeddings: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, **kwargs):
         B, q_len, _ = hidden_states.shape
-        q = self.q_proj(hidden_states).view(B, q_len, self.num_heads, self.head_dim)
-        k = self.k_proj(hidden_states).view(B, q_len, self.num_key_value_heads, self.head_dim)
-        v = self.v_proj(hidden_states).view(B, q_len, self.num_key_value_heads, self.head_dim)
+        if B == 1 and q_len == 1 and os.environ.get("IVL_DECODE_PACKED_PROJ", "1") != "0":
+            q, k, v = _packed_linear(self, "_packed_qkv", (self.q_proj, self.k_proj, self.v_proj), hidden_states)
+        else:
+            q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+        q = q.view(B, q_len, self.num_heads, self.head_dim)
+        k = k.view(B, q_len, self.num_key_value_heads, self.head_dim)
+        v = v.view(B, q_len, self.num_key_value_heads, self.head_dim)
         cos, sin = position_embeddings
         if cos.dim() == 4:  # [3,B,T,D] M-RoPE tables -> merged [B,T,D]
             cos, sin = mrope_select(cos, sin, self.rope_scaling["mrope_section"])

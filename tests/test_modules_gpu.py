@@ -193,6 +193,7 @@ def test_fused_decode_step_is_bit_identical_to_the_kernel_chain(M, monkeypatch, 
     mod = _init(M.GatedDeltaNet(cfg, 1), 31).bfloat16().cuda()
     x = torch.randn(B, 140, 2048, generator=gen(32)).bfloat16().cuda()
     res = {}
+    monkeypatch.setenv("IVL_DECODE_PACKED_PROJ", "0")     # same projection GEMMs in both paths: compare the mixer cores
     for fused in ("1", "0"):
         monkeypatch.setenv("IVL_GDN_FUSED_DECODE", fused)
         cache = M.StaticCachePrealloc(config=cfg, batch_size=B, device="cuda", dtype=cache_dtype)
@@ -208,6 +209,16 @@ def test_fused_decode_step_is_bit_identical_to_the_kernel_chain(M, monkeypatch, 
     # and the streamed result is the same function as the one-shot forward (different chunking: tolerance)
     full, _ = mod(x)
     assert err_ratio(full.float().cpu(), res["1"][0].float().cpu()) < 1.5e-2
+    if B == 1:
+        # decode steps with the six input projections stacked into one GEMV (the default for a single sequence)
+        monkeypatch.setenv("IVL_DECODE_PACKED_PROJ", "1")
+        monkeypatch.setenv("IVL_GDN_FUSED_DECODE", "1")
+        cache = M.StaticCachePrealloc(config=cfg, batch_size=B, device="cuda", dtype=cache_dtype)
+        outs = [mod(x[:, :100], past_key_values=cache, cache_position=torch.arange(0, 100, device="cuda"))[0]]
+        for t in range(100, 140):
+            outs.append(mod(x[:, t:t + 1], past_key_values=cache, cache_position=torch.arange(t, t + 1, device="cuda"))[0])
+        assert err_ratio(res["1"][0].float(), torch.cat(outs, 1).float()) < 5e-3
+        assert "_packed_in_proj" not in mod.state_dict() and hasattr(mod, "_packed_in_proj")
 
 
 def test_self_attention_mixer_with_cache(M):
