@@ -477,6 +477,9 @@ def run_ours(args):
             config2 = run_config2(dev, peaks)
         if not args.no_config3:
             config3 = run_config3(dev, peaks, n_frames=args.stream_frames)
+    backward = None
+    if world == 1 and not args.no_backward:
+        backward = run_backward(dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -491,10 +494,11 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "seq_len": T, "batch": 1,
-                       "parallelism": (f"sequence-chunk x{world}, neighbour hand-off over " + ("peer memory (CUDA IPC + copy engines + stream flags)" if hp.transport == "p2p" else "NCCL send/recv")) if world > 1 else "single GPU",
+                       "parallelism": (f"sequence-chunk x{world}, neighbour hand-off over " + ("peer memory (CUDA IPC mapping, ivl_peer_put stores over NVLink + stream-ordered flags)" if hp.transport == "p2p" else "NCCL send/recv")) if world > 1 else "single GPU",
                        "l2": "inputs (>3 GB per layer) exceed the 126 MB L2; no flush needed"},
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "decode": decode,
-            "gpu_reference": gpu_ref, "config2_32k": config2, "config3_stream": config3, "dist": dist_info,
+            "gpu_reference": gpu_ref, "config2_32k": config2, "config3_stream": config3, "backward": backward,
+            "dist": dist_info,
             "gpu_launches": hp.launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -549,6 +553,33 @@ def gpu_reference(hp, T, ours_ms_step, warmup=3, iters=3):
                 "swa_layer_ms": round(t_swa, 4), "ours_ms_per_step": round(ours_ms_step, 3),
                 "hot_path_ratio": round(ms / ours_ms_step, 3)})
     return res
+
+
+def run_backward(dev, T=4096):
+    """forward + backward of the chunk operator through ops.ChunkGatedDeltaRuleFunction (CUDA forward,
+    ivl_gdn_bwd: exact fp32 gradient with checkpoint recomputation).  Reported, not optimised: the backward is the
+    parity anchor of the training drop-in."""
+    try:
+        from inputs import gdn_inputs
+        from infinitevl_b200 import ops
+        q, k, v, g, beta, h0 = gdn_inputs(T=T, H=H, seed=11)
+        leaves = [x.to(dev).requires_grad_(True) for x in (q, k, v, g, beta)]
+
+        def fwd_bwd():
+            for x in leaves:
+                x.grad = None
+            o, _ = ops.chunk_gated_delta_rule(*leaves, use_qk_l2norm_in_kernel=True)
+            o.float().square().mean().backward()
+
+        def fwd():
+            with torch.no_grad():
+                ops.chunk_gated_delta_rule(*leaves, use_qk_l2norm_in_kernel=True)
+        tf = sorted(time_events(fwd, 3))[1]
+        tb = sorted(time_events(fwd_bwd, 3))[1]
+        return {"seq_len": T, "forward_ms": round(tf, 3), "forward_backward_ms": round(tb, 3),
+                "what": "one GDN layer (H16 K128 V256), chunk forward + exact fp32 recurrence backward (ivl_gdn_bwd)"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
 
 def run_config2(dev, peaks, T=32768):
@@ -992,6 +1023,7 @@ def main():
     ap.add_argument("--no-config2", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-backward", action="store_true")
     ap.add_argument("--stream-frames", type=int, default=2048)
     ap.add_argument("--sweep", default=None, nargs="?", const="4096,8192,16384,32768,65536,131072,262144,524288,1048576",
                     help="comma-separated sequence lengths: run the config-5 sweep instead of the bench line")
