@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 CS = os.path.join(ROOT, "infinitevl_b200", "csrc")
 out = "/tmp/libivl_trace.so"
-srcs = [os.path.join(CS, f) for f in ("ivl_abi.cu", "gdn_prep.cu", "gdn_scan.cu", "gdn_recurrent.cu", "gdn_decode.cu", "gdn_fused.cu", "swa_fwd.cu", "swa_misc.cu")]
+from infinitevl_b200 import build as B
+srcs = [os.path.join(CS, f) for f in B.SOURCES]
 subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC",
                 "--expt-relaxed-constexpr", "-DIVL_BUILDING_DLL", "-DIVL_TRACE", "-shared", "-I", os.path.join(ROOT, "include"), "-o", out] + srcs, check=True)
 lib = ctypes.CDLL(out)
@@ -24,6 +25,7 @@ o = torch.empty(1, T, 16, 256, dtype=torch.bfloat16, device="cuda"); ht = torch.
 P = ctypes.c_void_p
 lib.ivl_gdn_chunk_prep.argtypes = [P] * 5 + [ctypes.c_int] * 3 + [ctypes.c_float, ctypes.c_int, P, ctypes.c_size_t, P]
 lib.ivl_gdn_chunk_scan.argtypes = [P, P, ctypes.c_int, P, P, ctypes.c_int] + [ctypes.c_int] * 3 + [P, ctypes.c_size_t, P]
+os.environ.setdefault("IVL_GDN_TSCAN", "0")   # the row-major scan carries this tool's scan probe
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(3):
     assert lib.ivl_gdn_chunk_prep(q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr(), 1, T, 16, 0.0, 1, ws.data_ptr(), need, st) == 0
