@@ -955,8 +955,8 @@ cudaError_t launch_gdn_prep(const void* q, const void* k, const void* v, const f
   if (fz && (transposed != 1 || vl.chunk_tok0 != nullptr)) return cudaErrorInvalidValue;   // transposed scan, dense only
   // IVL_GDN_PREP_TC (developer knob): 1 = the large products on tcgen05 (default for the transposed scan's images),
   // 0 = warp-level mma.sync everywhere
-  static const int tc_default = [] { const char* e = getenv("IVL_GDN_PREP_TC"); return (e && *e) ? atoi(e) : PREP_TC_DEFAULT; }();
-  const bool tc = transposed == 1 && tc_default != 0;
+  const char* tc_env = getenv("IVL_GDN_PREP_TC");
+  const bool tc = transposed == 1 && ((tc_env && *tc_env) ? atoi(tc_env) : PREP_TC_DEFAULT) != 0;
   auto kern = fz ? (tc ? gdn_prep_kernel<1, true, true> : gdn_prep_kernel<1, true>)
                  : (tc ? gdn_prep_kernel<1, false, true>
                        : (transposed == 2 ? gdn_prep_kernel<2> : (transposed == 1 ? gdn_prep_kernel<1> : gdn_prep_kernel<0>)));

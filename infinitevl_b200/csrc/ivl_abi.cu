@@ -223,19 +223,36 @@ int ivl_stream_release(void* stream) {
   return IVL_OK;
 }
 
-int ivl_stream_wait_value32(void* stream, const void* addr, uint32_t value) {
-  if (!addr || (reinterpret_cast<uintptr_t>(addr) & 3)) return IVL_ERR_NULL;
-  typedef CUresult (*WaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-  static std::atomic<WaitFn> fn{nullptr};
-  WaitFn f = fn.load(std::memory_order_acquire);
-  if (!f) {
+namespace {
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+// cuStreamWaitValue32 through the runtime's driver entry point (no link-time dependency on libcuda); nullptr when the
+// driver does not offer it -- callers that would rely on it (the image ring) then do without
+WaitValue32Fn wait_value32_fn() {
+  static std::atomic<WaitValue32Fn> fn{nullptr};
+  static std::atomic<bool> tried{false};
+  WaitValue32Fn f = fn.load(std::memory_order_acquire);
+  if (!f && !tried.load(std::memory_order_acquire)) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cuda_failed(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint") ||
-        q != cudaDriverEntryPointSuccess || !p)
-      return IVL_ERR_LAUNCH;
-    f = reinterpret_cast<WaitFn>(p);
-    fn.store(f, std::memory_order_release);
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess && p) {
+      f = reinterpret_cast<WaitValue32Fn>(p);
+      fn.store(f, std::memory_order_release);
+    } else {
+      cudaGetLastError();
+    }
+    tried.store(true, std::memory_order_release);
+  }
+  return f;
+}
+}  // namespace
+
+int ivl_stream_wait_value32(void* stream, const void* addr, uint32_t value) {
+  if (!addr || (reinterpret_cast<uintptr_t>(addr) & 3)) return IVL_ERR_NULL;
+  WaitValue32Fn f = wait_value32_fn();
+  if (!f) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuStreamWaitValue32 is not available from this driver");
+    return IVL_ERR_LAUNCH;
   }
   const CUresult r = f(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
   if (r != CUDA_SUCCESS) {
@@ -431,6 +448,7 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
   int ring = env_int("IVL_GDN_RING", GDN_RING_DEFAULT);
   if (!tr || vl.chunk_tok0 != nullptr || cap != cudaStreamCaptureStatusNone || ring < 0 || ring >= num_chunks) ring = 0;
   if (ring > 0 && ring < 4) ring = 4;
+  if (ring > 0 && !tool_attached() && wait_value32_fn() == nullptr) ring = 0;   // no handshake, no ring
   ivl::GdnWorkspace ws = ivl::gdn_carve(workspace, B, T_ws, H, ring);
   IVL_CUDA(ivl::configure_gdn_prep());  // prep must be loaded before a scan that waits for it is running
   IVL_CUDA(cudaMemsetAsync(ws.ready, 0, ivl::gdn_sync_bytes(B, T_ws, H), st));
@@ -444,8 +462,10 @@ int gdn_chunk_fwd_impl(const void* q, const void* k, const void* v, const float*
     const int scan_ctas = nseq * H * (ivl::GDN_V / bv);
     // (ncu range replay refuses stream memory operations; a profiled run of a single call goes without the handshake --
     // the hazard it removes needs a previous call still draining -- and both wait loops trap instead of hanging)
-    if (!tool_attached())
-      if (int e = ivl_stream_wait_value32(fj->aux, ws.checkin, (uint32_t)scan_ctas)) return e;
+    // (a failing wait is reported but must not stop here: the scan is already waiting for prep's flags)
+    int wait_err = IVL_OK;
+    if (!tool_attached()) wait_err = ivl_stream_wait_value32(fj->aux, ws.checkin, (uint32_t)scan_ctas);
+    (void)wait_err;
   }
   // (should prep fail to launch, the scan traps after its time-out instead of hanging)
   IVL_CUDA(ivl::launch_gdn_prep(q, k, v, g, beta, ws, vl, num_chunks, B, T, H, sc, l2norm_qk, ivl::GDN_V / bv,

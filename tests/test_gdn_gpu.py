@@ -187,6 +187,23 @@ def test_transposed_and_row_major_scans_agree(ops, monkeypatch):
     assert torch.equal(outs["1"][0], outs["3"][0]) and torch.equal(outs["1"][1], outs["3"][1])
 
 
+def test_tcgen05_and_warp_level_prep_agree(ops, monkeypatch):
+    """The pre-pass computes its three large products on tcgen05 (default) or with warp-level MMAs (IVL_GDN_PREP_TC=0):
+    same bf16 operands, fp32 accumulation in a different order -- the operator's outputs agree far inside the oracle
+    tolerance, and each path matches the oracle by itself."""
+    q, k, v, g, beta, h0 = gdn_inputs(T=2500, H=4, seed=71)
+    ro, rs = gdn_chunk_ref(q, k, v, g, beta, initial_state=h0)
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("IVL_GDN_PREP_TC", tc)
+        o, s = ops.chunk_gated_delta_rule(*_cuda([q, k, v, g, beta]), initial_state=h0.cuda(), output_final_state=True,
+                                          use_qk_l2norm_in_kernel=True)
+        assert err_ratio(ro, o.float().cpu()) < TOL_O and err_ratio(rs, s.cpu()) < TOL_S
+        outs[tc] = (o, s)
+    assert err_ratio(outs["0"][0].float(), outs["1"][0].float()) < 2e-3
+    assert err_ratio(outs["0"][1], outs["1"][1]) < 2e-3
+
+
 def test_chunk_then_recurrent_streaming(ops):
     """Prefill 300 tokens with the chunk kernel, then decode 8 tokens one at a time in place."""
     q, k, v, g, beta, h0 = gdn_inputs(T=308, H=4, seed=51)
