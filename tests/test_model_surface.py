@@ -104,3 +104,32 @@ def test_text_model_argument_rules():
     with pytest.raises(NotImplementedError):   # no vision tower attached
         model(input_ids=torch.zeros(1, 4, dtype=torch.long), pixel_values=torch.zeros(4, 8),
               image_grid_thw=torch.tensor([[1, 2, 2]]))
+
+
+def test_left_context_table_and_stacked_projections():
+    """Host-side helpers of the packed-row conv and of the stacked decode projections (no GPU needed)."""
+    import torch
+    from infinitevl_b200 import modeling as M
+    # left context per token of a packed row: min(3, tokens of the own sequence before it); unowned tokens get 0
+    tab = M.left_context_table([0, 1, 3, 3, 9], 11, "cpu")
+    assert tab.dtype == torch.uint8
+    naive = []
+    for t in range(11):
+        start = max(s for s in [0, 1, 3, 3, 9] if s <= t)
+        naive.append(min(3, t - start))
+    assert tab.tolist() == naive
+    # several nn.Linear over one input as one matmul; the stack follows the parameters
+    torch.manual_seed(0)
+    owner = torch.nn.Module()
+    mods = (torch.nn.Linear(16, 8, bias=True), torch.nn.Linear(16, 4, bias=False), torch.nn.Linear(16, 12, bias=True))
+    x = torch.randn(1, 1, 16)
+    outs = M._packed_linear(owner, "_stack", mods, x)
+    for m, y in zip(mods, outs):
+        assert torch.allclose(m(x), y, atol=1e-6)
+    first = owner._stack[1]
+    assert M._packed_linear(owner, "_stack", mods, x)[0] is not None and owner._stack[1] is first   # cached
+    with torch.no_grad():
+        mods[1].weight.add_(1.0)                       # in-place update bumps the version counter: the stack is rebuilt
+    outs = M._packed_linear(owner, "_stack", mods, x)
+    assert owner._stack[1] is not first and torch.allclose(mods[1](x), outs[1], atol=1e-6)
+    assert "_stack" not in owner.state_dict()
