@@ -203,6 +203,9 @@ class OperatorHandOff:
         self._sends = []
 
 
+_IPC_BASES: dict = {}   # (device, IPC handle) -> base address of the mapping in this process
+
+
 class PeerLink:
     """Neighbour hand-off r -> r + 1 through PEER MEMORY instead of NCCL: the receive buffers of rank r + 1 (the
     DeltaNet state slots, the halo rows at the front of its K/V buffers) are opened on rank r through CUDA IPC, the
@@ -262,16 +265,17 @@ class PeerLink:
                 "recv": {k: (export(t) if (t is not None and not self.first) else None) for k, t in recv.items()}}
         every = [None] * self.world
         dist.all_gather_object(every, mine, group=self.group)
-        self._bases = {}
-
         def map_(ex) -> int:
+            # one mapping per exported allocation and process (CUDA refuses to open a handle twice): shared by every
+            # link of this process, e.g. the links a sweep opens one after the other over recycled allocator blocks
             handle, off, _ = ex
-            if handle not in self._bases:
+            key = (self.device.index, handle)
+            if key not in _IPC_BASES:
                 import ctypes
                 p = ctypes.c_void_p()
                 self._libmod.check(self._lib.ivl_ipc_open(handle, ctypes.byref(p)), "ivl_ipc_open")
-                self._bases[handle] = int(p.value)
-            return self._bases[handle] + off
+                _IPC_BASES[key] = int(p.value)
+            return _IPC_BASES[key] + off
 
         self.peer_ptr, self.peer_bytes, self.next_flags, self.prev_flags = {}, {}, None, None
         err = None
