@@ -6,7 +6,9 @@
  *   - runs asynchronously on the CUDA stream passed in (a cudaStream_t cast to void*),
  *   - never allocates device memory, never synchronises, never throws (ivl_gdn_chunk_fwd creates one helper
  *     stream and two events per caller stream the first time it overlaps its kernels -- or ivl_stream_init does,
- *     ahead of time -- and nothing afterwards; ivl_stream_release frees them),
+ *     ahead of time -- and nothing afterwards; ivl_stream_release frees them; outside of stream capture the
+ *     overlapped form also issues one stream memory operation, cuStreamWaitValue32, on that helper stream; the
+ *     ivl_ipc_* functions of the multi-GPU hand-off map / unmap peer memory and are set-up calls, not stream work),
  *   - returns IVL_ERR_ARCH on a device that is not sm_100 (the kernels exist for sm_100a only),
  *   - returns IVL_OK or a negative IVL_ERR_* code (ivl_strerror() names it),
  * so it is safe inside CUDA-graph capture (the reference demo captures the whole
@@ -47,7 +49,8 @@ extern "C" {
 #define IVL_DTYPE_F32 0
 #define IVL_DTYPE_BF16 1
 
-/* Library identification; also the cheapest "does the .so load" check. */
+/* Library identification (3: ivl_swa_fwd_pos / _varlen, fused and packed entry points, peer-memory hand-off); also the
+ * cheapest "does the .so load" check. */
 IVL_API int ivl_abi_version(void);
 IVL_API const char* ivl_strerror(int code);
 /* After IVL_ERR_LAUNCH: the CUDA runtime call that failed and its error text (per calling thread). */
