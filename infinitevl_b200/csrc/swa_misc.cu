@@ -310,7 +310,6 @@ swa_ring_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
       sm_w[(i / nsplit) * 64 + i % nsplit] = __ldcg(recs + (long long)i * DEC_REC + 1);
     }
     __syncthreads();
-    float Linv[2] = {0.f, 0.f};
     for (int pass = 0; pass < 2; ++pass) {
       const int gh = warp + 4 * pass;                        // warp w normalises heads w and w + 4
       if (gh < group) {
@@ -329,7 +328,6 @@ swa_ring_decode_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
       }
     }
     __syncthreads();
-    (void)Linv;
     for (int pass = 0; pass < 2; ++pass) {
       const int gh = warp + 4 * pass;                        // warp w sums heads w and w + 4: lane = 4 head dims
       if (gh < group) {

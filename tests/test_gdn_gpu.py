@@ -187,6 +187,27 @@ def test_transposed_and_row_major_scans_agree(ops, monkeypatch):
     assert torch.equal(outs["1"][0], outs["3"][0]) and torch.equal(outs["1"][1], outs["3"][1])
 
 
+@pytest.mark.parametrize("B,H", [(2, 16), (3, 4)])
+def test_batched_overlapped_operator_with_the_image_ring(ops, monkeypatch, B, H):
+    """Batches in the overlapped form (scan CTAs of every batch row check in before the pre-pass starts; one image
+    ring per (row, head)): bit-identical to the back-to-back form, and right against the oracle."""
+    q, k, v, g, beta, h0 = gdn_inputs(B=B, T=4100, H=H, seed=81)
+    dq, dk, dv, dg, db, dh = _cuda([q, k, v, g, beta, h0])
+    monkeypatch.setenv("IVL_GDN_PIPE", "0")
+    o0, s0 = ops.chunk_gated_delta_rule(dq, dk, dv, dg, db, initial_state=dh, output_final_state=True,
+                                        use_qk_l2norm_in_kernel=True)
+    ro, rs = gdn_chunk_ref(q[:1], k[:1], v[:1], g[:1], beta[:1], initial_state=h0[:1])
+    assert err_ratio(ro, o0[:1].float().cpu()) < TOL_O and err_ratio(rs, s0[:1].cpu()) < TOL_S
+    for ring in ("24", "8", "0"):
+        monkeypatch.setenv("IVL_GDN_PIPE", "1")
+        monkeypatch.setenv("IVL_GDN_RING", ring)
+        for _ in range(2):     # back to back, no synchronisation in between
+            o, s = ops.chunk_gated_delta_rule(dq, dk, dv, dg, db, initial_state=dh, output_final_state=True,
+                                              use_qk_l2norm_in_kernel=True)
+        torch.cuda.synchronize()
+        assert torch.equal(o, o0) and torch.equal(s, s0), ring
+
+
 def test_tcgen05_and_warp_level_prep_agree(ops, monkeypatch):
     """The pre-pass computes its three large products on tcgen05 (default) or with warp-level MMAs (IVL_GDN_PREP_TC=0):
     same bf16 operands, fp32 accumulation in a different order -- the operator's outputs agree far inside the oracle
