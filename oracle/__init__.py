@@ -27,7 +27,7 @@ package's own ``naive_recurrent_gated_delta_rule`` /
 ``naive_chunk_gated_delta_rule``.
 """
 from .gdn import (  # noqa: F401
-    l2norm_ref, short_conv_ref, gdn_gate_ref, gdn_recurrent_ref, gdn_chunk_ref,
+    l2norm_ref, short_conv_ref, gdn_gate_ref, gdn_recurrent_ref, gdn_chunk_ref, gdn_chunk_segmented_ref,
     rmsnorm_gated_ref, rmsnorm_ref, err_ratio,
 )
 from .swa import (  # noqa: F401

@@ -183,6 +183,78 @@ def gdn_chunk_ref(
     return o, S
 
 
+def gdn_chunk_segmented_ref(q, k, v, g, beta, segments: int = 4, scale: Optional[float] = None,
+                            initial_state: Optional[torch.Tensor] = None, use_qk_l2norm: bool = True,
+                            chunk_size: int = 64, dtype=torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The chunk form with PARALLELISM ALONG THE SEQUENCE (DESIGN.md section 6, item 1 -- the restructuring the serial
+    scan kernel needs to get past its per-chunk hand-off latencies; test infrastructure like the rest of oracle/).
+
+    Per chunk the state map is affine:  S_{c+1} = A_c S_c + B_c  with
+        A_c = gamma_c I - Kt_c^T Wg_c   (K x K)        B_c = Kt_c^T U_c   (K x V)
+    (from Vn = U - Wg S and S <- gamma S + Kt^T Vn of `gdn_chunk_ref`).  The sequence is cut into `segments` runs of
+    chunks; pass 1 composes, independently per segment, the segment map (T_p, R_p) -- the same recurrence run on the
+    augmented state [I | 0] -- pass 2 is the short serial fix-up  S_start[p+1] = T_p S_start[p] + R_p,  pass 3 runs the
+    ordinary scan of every segment from its true start state (independent again).  Must equal `gdn_chunk_ref`."""
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    C = chunk_size
+    if scale is None:
+        scale = K ** -0.5
+    qf, kf = q.to(dtype), k.to(dtype)
+    if use_qk_l2norm:
+        qf, kf = l2norm_ref(qf, dtype=dtype), l2norm_ref(kf, dtype=dtype)
+    vf, gf, bf = v.to(dtype), g.to(dtype), beta.to(dtype)
+    pad = (-T) % C
+    if pad:
+        qf, kf, vf = (F.pad(x, (0, 0, 0, 0, 0, pad)) for x in (qf, kf, vf))
+        gf, bf = F.pad(gf, (0, 0, 0, pad)), F.pad(bf, (0, 0, 0, pad))
+    NT = (T + pad) // C
+    qc, kc, vc = (x.permute(0, 2, 1, 3).reshape(B, H, NT, C, -1) for x in (qf, kf, vf))
+    gc = gf.permute(0, 2, 1).reshape(B, H, NT, C)
+    bc = bf.permute(0, 2, 1).reshape(B, H, NT, C)
+    G = gc.cumsum(-1)
+    Gam = (G[..., :, None] - G[..., None, :]).tril().exp().tril()
+    eye = torch.eye(C, dtype=dtype)
+    L = ((kc * bc[..., None]) @ kc.transpose(-1, -2) * Gam).tril(-1)
+    A = torch.linalg.solve_triangular(eye + L, eye.expand_as(L).contiguous(), upper=False, unitriangular=True)
+    Wg = A @ (kc * (bc * G.exp())[..., None])
+    U = A @ (vc * bc[..., None])
+    P = (qc @ kc.transpose(-1, -2) * Gam).tril()
+    Qg = qc * G.exp()[..., None]
+    Kt = kc * (G[..., -1:] - G).exp()[..., None]
+    gamma = G[..., -1].exp()
+    # the affine map of every chunk (parallel over chunks: prep-side work)
+    eyeK = torch.eye(K, dtype=dtype)
+    Ac = gamma[..., None, None] * eyeK - Kt.transpose(-1, -2) @ Wg          # [B, H, NT, K, K]
+    Bc = Kt.transpose(-1, -2) @ U                                           # [B, H, NT, K, V]
+    bounds = [round(i * NT / segments) for i in range(segments + 1)]
+    # pass 1: segment maps, independent per segment
+    Tp, Rp = [], []
+    for p in range(segments):
+        Tm = eyeK.expand(B, H, K, K).clone()
+        Rm = torch.zeros(B, H, K, V, dtype=dtype)
+        for c in range(bounds[p], bounds[p + 1]):
+            Tm = Ac[:, :, c] @ Tm
+            Rm = Ac[:, :, c] @ Rm + Bc[:, :, c]
+        Tp.append(Tm)
+        Rp.append(Rm)
+    # pass 2: start state of every segment (serial over the few segments)
+    S0 = torch.zeros(B, H, K, V, dtype=dtype) if initial_state is None else initial_state.to(dtype).clone()
+    starts = [S0]
+    for p in range(segments):
+        starts.append(Tp[p] @ starts[p] + Rp[p])
+    # pass 3: the ordinary scan per segment from its true start state (independent per segment)
+    o = torch.empty(B, H, NT, C, V, dtype=dtype)
+    for p in range(segments):
+        S = starts[p].clone()
+        for c in range(bounds[p], bounds[p + 1]):
+            Vn = U[:, :, c] - Wg[:, :, c] @ S
+            o[:, :, c] = (Qg[:, :, c] @ S + P[:, :, c] @ Vn) * scale
+            S = S * gamma[:, :, c][..., None, None] + Kt[:, :, c].transpose(-1, -2) @ Vn
+    o = o.reshape(B, H, NT * C, V)[:, :, :T].permute(0, 2, 1, 3).contiguous()
+    return o, starts[-1]
+
+
 def rmsnorm_gated_ref(x: torch.Tensor, gate: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5,
                       dtype=torch.float32) -> torch.Tensor:
     """y = x * rsqrt(mean(x^2) + eps) * w * gate * sigmoid(gate) over the last axis

@@ -209,3 +209,23 @@ def test_linear_cache_matches_reference(golden_dir):
     assert c.seq_len == int(z["seq_len"])
     with pytest.raises(RuntimeError):
         c.update(recurrent_state=torch.zeros(1, 2, 4, 9), op="set")
+
+
+@pytest.mark.parametrize("segments", [2, 4, 7])
+def test_segmented_scan_equals_the_serial_chunk_form(segments):
+    """per chunk the state map is affine (A_c = gamma_c I - Kt_c^T Wg_c, B_c = Kt_c^T U_c),
+    so the sequence can be cut into segments whose maps are composed independently, fixed up with one small product
+    per segment, and scanned independently from their true start states.  In fp64 the three-pass form reproduces the
+    serial chunk form (and hence the token recurrence) to rounding; in fp32 to ~1e-5 -- the algebra the next scan
+    kernel rests on."""
+    import torch
+    from inputs import gdn_inputs
+    from oracle import err_ratio, gdn_chunk_ref, gdn_chunk_segmented_ref, gdn_recurrent_ref
+    q, k, v, g, beta, h0 = gdn_inputs(T=1100, H=2, seed=61)
+    ro, rs = gdn_chunk_ref(q, k, v, g, beta, initial_state=h0, dtype=torch.float64)
+    o, s = gdn_chunk_segmented_ref(q, k, v, g, beta, segments=segments, initial_state=h0, dtype=torch.float64)
+    assert err_ratio(ro, o) < 1e-10 and err_ratio(rs, s) < 1e-10
+    o32, s32 = gdn_chunk_segmented_ref(q, k, v, g, beta, segments=segments, initial_state=h0)
+    assert err_ratio(ro.float(), o32) < 1e-4 and err_ratio(rs.float(), s32) < 1e-4
+    tok_o, tok_s = gdn_recurrent_ref(q, k, v, g, beta, initial_state=h0)
+    assert err_ratio(tok_o, o32) < 1e-4 and err_ratio(tok_s, s32) < 1e-4
