@@ -64,6 +64,65 @@ def swa_attention_bthd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window
     return out
 
 
+def swa_attention_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, dout: torch.Tensor,
+                           window: Optional[int] = None, scale: Optional[float] = None, block: int = 512):
+    """Gradient of `swa_attention_bthd` (attention half; the reference trains through flash-attn's
+    backward): recomputes the probabilities query block by query block from q, k, v and the saved output -- the
+    flash-attention backward identities, dS = P * (dP - rowsum(dO * O)) -- with plain matrix products over the
+    visible key range of the block, fp32.  q, out, dout [B,Tq,Hq,D]; k, v [B,Tk,Hkv,D] -> (dq, dk, dv) in fp32.
+    Works on any device (the formula is layout-only torch code); O(block * window) memory."""
+    B, Tq, Hq, D = q.shape
+    Tk, Hkv = k.shape[1], k.shape[2]
+    G = Hq // Hkv
+    scale = float(scale) if scale else D ** -0.5
+    W = int(window) if (window and Tk > int(window)) else None
+    shift = Tk - Tq
+    dq = torch.zeros(B, Tq, Hq, D, dtype=torch.float32, device=q.device)
+    dk = torch.zeros(B, Tk, Hkv, D, dtype=torch.float32, device=q.device)
+    dv = torch.zeros_like(dk)
+    grp = lambda t: t.float().reshape(t.shape[0], t.shape[1], Hkv, G, D).permute(0, 2, 3, 1, 4)   # [B,Hkv,G,n,D]
+    kv = lambda t: t.float().permute(0, 2, 1, 3)                                                      # [B,Hkv,m,D]
+    for i0 in range(0, Tq, block):
+        i1 = min(Tq, i0 + block)
+        pos = torch.arange(i0, i1, device=q.device) + shift
+        j_lo = max(0, i0 + shift - W + 1) if W else 0
+        j_hi = min(Tk, i1 + shift)
+        if j_hi <= j_lo:
+            continue
+        j = torch.arange(j_lo, j_hi, device=q.device)
+        vis = j[None, :] <= pos[:, None]
+        if W:
+            vis &= (pos[:, None] - j[None, :]) <= W - 1
+        qs, do, o = grp(q[:, i0:i1]), grp(dout[:, i0:i1]), grp(out[:, i0:i1])
+        ks, vs = kv(k[:, j_lo:j_hi]), kv(v[:, j_lo:j_hi])
+        S = torch.einsum("bhgnd,bhmd->bhgnm", qs, ks) * scale
+        P = torch.softmax(S.masked_fill(~vis, float("-inf")), dim=-1)
+        P = torch.nan_to_num(P)            # a query with no visible key (does not happen for causal self-attention)
+        dP = torch.einsum("bhgnd,bhmd->bhgnm", do, vs)
+        dS = P * (dP - (do * o).sum(-1, keepdim=True)) * scale
+        dq[:, i0:i1] = torch.einsum("bhgnm,bhmd->bhgnd", dS, ks).permute(0, 3, 1, 2, 4).reshape(B, i1 - i0, Hq, D)
+        dk[:, j_lo:j_hi] += torch.einsum("bhgnm,bhgnd->bhmd", dS, qs).permute(0, 2, 1, 3)
+        dv[:, j_lo:j_hi] += torch.einsum("bhgnm,bhgnd->bhmd", P, do).permute(0, 2, 1, 3)
+    return dq, dk, dv
+
+
+class SlidingWindowAttentionFunction(torch.autograd.Function):
+    """Differentiable form of the attention operator: CUDA forward (ivl_swa_fwd_pos), recomputing backward."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, window, scale, key_pos0):
+        out = swa_attention_bthd(q.detach(), k.detach(), v.detach(), window=window, scale=scale, key_pos0=key_pos0)
+        ctx.save_for_backward(q, k, v, out)
+        ctx.window, ctx.scale = window, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out = ctx.saved_tensors
+        dq, dk, dv = swa_attention_backward(q, k, v, out, dout, window=ctx.window, scale=ctx.scale)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None
+
+
 def swa_attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens, window: Optional[int] = None,
                          scale: Optional[float] = None) -> torch.Tensor:
     """Packed batch: q [1,T,Hq,128], k/v [1,T,Hkv,128] holding len(cu_seqlens) - 1 sequences back to back
@@ -96,8 +155,12 @@ def swa_attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_s
 
 def swa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, window: Optional[int] = None,
                   scale: Optional[float] = None, key_pos0: int = 0) -> torch.Tensor:
-    """HF head-first layout: q [B,Hq,Tq,D], k/v [B,Hkv,Tk,D] -> [B,Tq,Hq,D]."""
-    return swa_attention_bthd(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), window, scale, key_pos0=key_pos0)
+    """HF head-first layout: q [B,Hq,Tq,D], k/v [B,Hkv,Tk,D] -> [B,Tq,Hq,D].  Differentiable (training through the HF
+    attention interface): when a gradient is required the call goes through SlidingWindowAttentionFunction."""
+    qb, kb, vb = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        return SlidingWindowAttentionFunction.apply(qb, kb, vb, window, scale, key_pos0)
+    return swa_attention_bthd(qb, kb, vb, window, scale, key_pos0=key_pos0)
 
 
 def sliding_window_attention_forward(module, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,

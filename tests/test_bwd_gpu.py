@@ -152,3 +152,28 @@ def test_fla_layer_training_step(ops):
     yr, _, _ = gdn_mixer_ref(xr, params, proj_dtype=None)
     (yr * w.float().cpu()).sum().backward()
     assert err_ratio(xr.grad, x.grad.float().cpu()) < 3e-2
+
+
+@pytest.mark.parametrize("Tq,Tk,window", [(300, 300, None), (700, 700, 256), (130, 600, 200)])
+def test_attention_backward_against_autograd_through_the_oracle(Tq, Tk, window):
+    """SURVEY.md 8 f-1, attention half: `swa.swa_attention` is differentiable (CUDA forward, recomputing backward) --
+    what training through the HF attention interface needs.  Gradients against fp64 autograd through the oracle's
+    eager attention on the same bf16 inputs: <= 1e-2 (bf16 output / probabilities in the forward)."""
+    import torch
+    from infinitevl_b200 import swa
+    from oracle import err_ratio, swa_attention_ref
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = torch.Generator().manual_seed(Tq + 7 * Tk)
+    q = torch.randn(1, 16, Tq, 128, generator=g).bfloat16()
+    k = torch.randn(1, 2, Tk, 128, generator=g).bfloat16()
+    v = torch.randn(1, 2, Tk, 128, generator=g).bfloat16()
+    dout = torch.randn(1, Tq, 16, 128, generator=g).bfloat16()
+    rq, rk, rv = (x.double().requires_grad_(True) for x in (q, k, v))
+    swa_attention_ref(rq, rk, rv, window=window, dtype=torch.float64).backward(dout.double())
+    dq, dk, dv = (x.cuda().requires_grad_(True) for x in (q, k, v))
+    out = swa.swa_attention(dq, dk, dv, window=window)
+    out.backward(dout.cuda())
+    for ref, got in ((rq.grad, dq.grad), (rk.grad, dk.grad), (rv.grad, dv.grad)):
+        assert got is not None and got.dtype == torch.bfloat16
+        assert err_ratio(ref.float(), got.float().cpu()) < 1e-2

@@ -229,3 +229,24 @@ def test_segmented_scan_equals_the_serial_chunk_form(segments):
     assert err_ratio(ro.float(), o32) < 1e-4 and err_ratio(rs.float(), s32) < 1e-4
     tok_o, tok_s = gdn_recurrent_ref(q, k, v, g, beta, initial_state=h0)
     assert err_ratio(tok_o, o32) < 1e-4 and err_ratio(tok_s, s32) < 1e-4
+
+
+@pytest.mark.parametrize("Tq,Tk,window", [(70, 70, None), (150, 150, 40), (60, 200, 90), (33, 33, 8)])
+def test_attention_backward_formula_against_autograd(Tq, Tk, window):
+    """The recomputing backward of the attention operator (infinitevl_b200.swa.swa_attention_backward: layout-only torch
+    code, so it runs here on the CPU) against autograd through the oracle's eager attention, fp64."""
+    import torch
+    from infinitevl_b200.swa import swa_attention_backward
+    from oracle import swa_attention_ref
+    g = torch.Generator().manual_seed(Tq * 13 + Tk)
+    q = torch.randn(2, 4, Tq, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    k = torch.randn(2, 2, Tk, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    v = torch.randn(2, 2, Tk, 16, generator=g, dtype=torch.float64, requires_grad=True)
+    out = swa_attention_ref(q, k, v, window=window, dtype=torch.float64)          # [B, Tq, Hq, D]
+    dout = torch.randn(out.shape, generator=g, dtype=torch.float64)
+    out.backward(dout)
+    dq, dk, dv = swa_attention_backward(q.detach().transpose(1, 2).float(), k.detach().transpose(1, 2).float(),
+                                        v.detach().transpose(1, 2).float(), out.detach().float(), dout.float(),
+                                        window=window, block=32)
+    for ref, got in ((q.grad.transpose(1, 2), dq), (k.grad.transpose(1, 2), dk), (v.grad.transpose(1, 2), dv)):
+        assert err_ratio(ref.float(), got) < 1e-5
