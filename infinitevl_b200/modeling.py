@@ -705,6 +705,90 @@ class InfiniteVLConfig:
             return cls.from_dict(json.load(f))
 
 
+def _rope_index_vectorized(config, input_ids, image_grid_thw, video_grid_thw, second_per_grid_ts, attention_mask):
+    """get_rope_index without a Python loop over the vision blocks (the reference walks the blocks of
+    every row on the CPU, std:1664-1742 -- thousands of tiny tensor operations for a long stream): every step below is
+    a tensor operation over all blocks / all tokens of a row ON THE DEVICE of `input_ids`, with one shape-dependent
+    host synchronisation per row.  Same integer arithmetic as the reference (so the same bits); returns None for rows
+    that are not well formed (a vision-start token not followed by exactly t*h*w placeholders), which then take the
+    block-by-block path."""
+    dev = input_ids.device
+    merge = int(config.vision_config.spatial_merge_size)
+    tps = config.vision_config.tokens_per_second
+    IMG, VID, VS = config.image_token_id, config.video_token_id, config.vision_start_token_id
+    B, T = input_ids.shape
+    as_grid = lambda g: (torch.zeros(1, 3, dtype=torch.long, device=dev) if g is None or g.numel() == 0
+                         else g.to(dev, torch.long).reshape(-1, 3))
+    img_g, vid_g = as_grid(image_grid_thw), as_grid(video_grid_thw)
+    spg = None if second_per_grid_ts is None else second_per_grid_ts.to(dev).reshape(-1)
+    out = torch.ones(3, B, T, dtype=input_ids.dtype, device=dev)
+    deltas = torch.zeros(B, dtype=torch.long, device=dev)
+    n_img = n_vid = 0
+    for b in range(B):
+        keep = (attention_mask[b] == 1).to(dev) if attention_mask is not None else None
+        row = input_ids[b][keep] if keep is not None else input_ids[b]
+        L = row.numel()
+        if L < 2:
+            return None
+        is_start = (row[:-1] == VS) & ((row[1:] == IMG) | (row[1:] == VID))
+        s = torch.nonzero(is_start).squeeze(1)
+        nb = int(s.numel())
+        if nb == 0:
+            llm = torch.arange(L, device=dev).view(1, -1).expand(3, -1)
+        else:
+            kind = row[s + 1]
+            is_img = kind == IMG
+            img_rank = torch.cumsum(is_img.long(), 0) - 1
+            vid_rank = torch.cumsum((~is_img).long(), 0) - 1
+            ni, nv = int(is_img.sum()), nb - int(is_img.sum())
+            if n_img + ni > (0 if image_grid_thw is None else img_g.shape[0]) or \
+               n_vid + nv > (0 if video_grid_thw is None else vid_g.shape[0]):
+                return None
+            thw = torch.where(is_img[:, None], img_g[(n_img + img_rank).clamp(0, img_g.shape[0] - 1)],
+                              vid_g[(n_vid + vid_rank).clamp(0, vid_g.shape[0] - 1)])
+            if spg is not None and nv:
+                sec = torch.where(is_img, torch.zeros((), device=dev, dtype=spg.dtype),
+                                  spg[(n_vid + vid_rank).clamp(0, spg.numel() - 1)])
+            else:
+                sec = torch.where(is_img, 0.0, 1.0).to(dev)
+            sec_i = sec.to(torch.long)                          # the reference multiplies in the integer dtype of arange
+            t, gh, gw = thw[:, 0], thw[:, 1] // merge, thw[:, 2] // merge
+            n = t * gh * gw
+            ed = s + 1
+            st = torch.cat([ed.new_zeros(1), (ed + n)[:-1]])
+            text_len = ed - st
+            t_max = ((t - 1) * sec_i * tps).long()
+            span = torch.maximum(torch.maximum(t_max, gh - 1), gw - 1) + 1
+            base = torch.cumsum(text_len + span, 0) - span      # first coordinate of block b's grid
+            nxt = base - text_len                               # first position of the text in front of block b
+            tail_st, tail_nxt = ed[-1] + n[-1], base[-1] + span[-1]
+            p = torch.arange(L, device=dev)
+            bnd = torch.cat([torch.stack([st, ed], 1).reshape(-1), tail_st.view(1)])
+            idx = torch.bucketize(p, bnd, right=True) - 1       # 2b: text of block b, 2b + 1: its placeholders, 2nb: tail
+            blk = (idx // 2).clamp(max=nb - 1)
+            vis = (idx % 2 == 1) & (idx < 2 * nb)
+            tail = idx == 2 * nb
+            # well-formedness (one host sync): runs in order, exactly the placeholders where the grids say, none elsewhere
+            ok = (text_len >= 0).all() & (tail_st <= L) & (n > 0).all() & \
+                 (((row == IMG) | (row == VID)) == vis).all() & (row[vis] == kind[blk[vis]]).all()
+            if not bool(ok):
+                return None
+            text_pos = torch.where(tail, tail_nxt + (p - tail_st), nxt[blk] + (p - st[blk]))
+            kk = (p - ed[blk]).clamp(min=0)
+            ghb, gwb = gh[blk].clamp(min=1), gw[blk].clamp(min=1)
+            t_idx = ((kk // (ghb * gwb)) * sec_i[blk] * tps).long()
+            h_idx, w_idx = (kk // gwb) % ghb, kk % gwb
+            grid = torch.stack([t_idx, h_idx, w_idx]) + base[blk]
+            llm = torch.where(vis[None], grid, text_pos[None].expand(3, -1))
+            n_img, n_vid = n_img + ni, n_vid + nv
+        if keep is not None:
+            out[:, b, keep] = llm.to(out.dtype)
+        else:
+            out[:, b, :] = llm.to(out.dtype)
+        deltas[b] = llm.max() + 1 - T
+    return out, deltas.unsqueeze(1)
+
+
 def get_rope_index(config, input_ids=None, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None,
                    attention_mask=None):
     """M-RoPE position ids [3, B, T] and per-row deltas [B, 1] for text with image / video placeholders
@@ -725,6 +809,9 @@ def get_rope_index(config, input_ids=None, image_grid_thw=None, video_grid_thw=N
         pos = torch.arange(T, device=input_ids.device).view(1, 1, -1).expand(3, B, -1)
         return pos, torch.zeros([B, 1], device=input_ids.device, dtype=input_ids.dtype)
     B, T = input_ids.shape
+    fast = _rope_index_vectorized(config, input_ids, image_grid_thw, video_grid_thw, second_per_grid_ts, attention_mask)
+    if fast is not None:
+        return fast
     ids_cpu = input_ids.cpu()
     mask_cpu = (attention_mask == 1).cpu() if attention_mask is not None else None
     img = image_grid_thw.cpu().tolist() if image_grid_thw is not None else []

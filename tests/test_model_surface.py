@@ -133,3 +133,46 @@ def test_left_context_table_and_stacked_projections():
     outs = M._packed_linear(owner, "_stack", mods, x)
     assert owner._stack[1] is not first and torch.allclose(mods[1](x), outs[1], atol=1e-6)
     assert "_stack" not in owner.state_dict()
+
+
+def test_vectorised_rope_index_is_the_reference_function(golden_dir, monkeypatch):
+    """the device-side, loop-free get_rope_index (one tensor operation per step over all vision blocks
+    and tokens) reproduces the reference's own outputs (golden vectors) and, on random well-formed prompts -- images,
+    videos with fractional seconds per grid, batches with left padding -- the block-by-block path bit for bit; rows
+    that are not well formed fall back to that path."""
+    import random
+    from infinitevl_b200 import modeling as MM
+    z = np.load(os.path.join(golden_dir, "ref_rope_index.npz"))
+    cfg = _small()
+    t = lambda x, dt=torch.long: None if x is None else torch.tensor(x, dtype=dt)
+    for i, c in enumerate(cases()):
+        fast = MM._rope_index_vectorized(cfg, t(c["ids"]), t(c["img"]), t(c["vid"]), t(c["spg"], torch.float32), t(c["mask"]))
+        assert fast is not None, i
+        assert np.array_equal(fast[0].numpy(), z[f"pos{i}"]) and np.array_equal(fast[1].numpy(), z[f"delta{i}"]), i
+    IMG, VID, VS, VE = 151655, 151656, 151652, 151653
+    rng = random.Random(7)
+    for trial in range(40):
+        rows, img, vid, spg = [], [], [], []
+        for _ in range(rng.choice([1, 1, 2, 3])):
+            ids = [rng.randint(10, 99) for _ in range(rng.randint(0, 6))]
+            for _ in range(rng.randint(1, 5)):
+                tt, hh, ww = rng.choice([1, 1, 2, 3]), 2 * rng.randint(1, 4), 2 * rng.randint(1, 4)
+                if rng.random() < 0.5:
+                    img.append([1, hh, ww]); kind, tt = IMG, 1
+                else:
+                    vid.append([tt, hh, ww]); spg.append(rng.choice([0.5, 1.0, 1.5, 2.0, 3.7])); kind = VID
+                ids += [VS] + [kind] * (tt * (hh // 2) * (ww // 2)) + [VE] + [rng.randint(10, 99) for _ in range(rng.randint(0, 5))]
+            rows.append(ids)
+        L = max(len(r) for r in rows)
+        mask = [[0] * (L - len(r)) + [1] * len(r) for r in rows]
+        ids = [[0] * (L - len(r)) + r for r in rows]
+        args = (cfg, t(ids), t(img) if img else None, t(vid) if vid else None, t(spg, torch.float32) if spg else None, t(mask))
+        fast = MM._rope_index_vectorized(*args)
+        assert fast is not None, trial
+        monkeypatch.setattr(MM, "_rope_index_vectorized", lambda *a, **k: None)
+        slow = MM.get_rope_index(*args)
+        monkeypatch.undo()
+        assert torch.equal(fast[0], slow[0]) and torch.equal(fast[1], slow[1]), trial
+    # a row whose placeholder run is one token short is not well formed: block-by-block path
+    bad = [5, VS] + [IMG] * 5 + [VE, 6]
+    assert MM._rope_index_vectorized(cfg, t([bad]), t([[1, 4, 6]]), None, None, None) is None
