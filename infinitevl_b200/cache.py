@@ -145,6 +145,19 @@ class StaticSlidingWindowLayerPrealloc(_HFCacheLayer):
             self.keys = self._buf_keys[:, :, :0, :]
             self.values = self._buf_values[:, :, :0, :]
 
+    # -- snapshots -------------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        return {"keys": self.keys.contiguous().clone(), "values": self.values.contiguous().clone(),
+                "size": torch.tensor(int(self.size)), "cumulative_length": torch.tensor(int(self.cumulative_length))}
+
+    def load_state_dict(self, sd: dict) -> None:
+        n = int(sd["size"])
+        if n > 0:
+            self._buf_keys[:, :, :n, :].copy_(sd["keys"])
+            self._buf_values[:, :, :n, :].copy_(sd["values"])
+        self.keys, self.values = self._buf_keys[:, :, :n, :], self._buf_values[:, :, :n, :]
+        self.size, self.cumulative_length = n, int(sd["cumulative_length"])
+
 
 class RingSlidingWindowLayer(StaticSlidingWindowLayerPrealloc):
     """Ring-buffer form of the sliding-window cache layer.
@@ -459,6 +472,22 @@ class StaticLinearLayerPrealloc(_HFCacheLayer):
         self.seq_len = 0
         self.start = False
 
+    # -- snapshots -------------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        sd = {"recurrent_state": self.recurrent_state.clone(), "seq_len": torch.tensor(int(self.seq_len)),
+              "start": torch.tensor(int(bool(self.start)))}
+        if self.use_short_conv:
+            sd.update(conv_state_q=self.conv_state_q.clone(), conv_state_k=self.conv_state_k.clone(),
+                      conv_state_v=self.conv_state_v.clone())
+        return sd
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.recurrent_state.copy_(sd["recurrent_state"])
+        if self.use_short_conv:
+            for n in ("conv_state_q", "conv_state_k", "conv_state_v"):
+                getattr(self, n).copy_(sd[n])
+        self.seq_len, self.start = int(sd["seq_len"]), bool(int(sd["start"]))
+
 
 class StaticCachePrealloc(_HFCache):
     """Per-layer caches built from config.layer_types (std:366-443)."""
@@ -515,6 +544,31 @@ class StaticCachePrealloc(_HFCache):
         for layer in self.layers:
             if hasattr(layer, "sync_from_device"):
                 layer.sync_from_device()
+
+    # -- snapshots on disk (resume a stream, branch it for a question) -------------------------------
+    def state_dict(self) -> dict:
+        """Flat {"layers.<i>.<name>": tensor}: the windows in logical order, the recurrent / conv states and the
+        integer bookkeeping as 0-d tensors (safetensors-friendly).  Call `sync_from_device()` first if the cache was
+        advanced by CUDA-graph replays."""
+        out = {}
+        for i, layer in enumerate(self.layers):
+            for k, v in layer.state_dict().items():
+                out[f"layers.{i}.{k}"] = v.detach().contiguous()
+        return out
+
+    def load_state_dict(self, sd: dict) -> "StaticCachePrealloc":
+        for i, layer in enumerate(self.layers):
+            pre = f"layers.{i}."
+            layer.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+        return self
+
+    def save(self, path: str) -> None:
+        from safetensors.torch import save_file
+        save_file({k: v.cpu() for k, v in self.state_dict().items()}, path)
+
+    def load(self, path: str) -> "StaticCachePrealloc":
+        from safetensors.torch import load_file
+        return self.load_state_dict(load_file(path))
 
     def copy_from(self, src: "StaticCachePrealloc") -> "StaticCachePrealloc":
         """Device-side snapshot of another cache of the same geometry (what the demo's clone_inference_cache does

@@ -202,3 +202,47 @@ def test_ring_layer_equals_reference_layer_on_the_reference_trace():
         return
     cache = StaticCachePrealloc(config=cfg, batch_size=1)
     assert isinstance(cache, Cache) and all(isinstance(l, CacheLayerMixin) for l in cache.layers)
+
+
+@pytest.mark.parametrize("ring", [False, True])
+def test_cache_snapshot_on_disk(tmp_path, ring):
+    """the whole inference cache as one safetensors file -- windows in logical order, recurrent / conv
+    states, the integer bookkeeping -- and back: the restored cache is equal and continues the stream identically."""
+    import torch
+    from infinitevl_b200.cache import StaticCachePrealloc
+    from infinitevl_b200.modeling import HybridTextConfig
+    cfg = HybridTextConfig(num_hidden_layers=4, sliding_window=8, num_key_value_heads=1, num_attention_heads=2,
+                           hidden_size=8, num_linear_heads=2, num_linear_key_value_heads=2, linear_head_dim=4)
+    cfg.head_dim = 4
+
+    def feed(c, n, seed):
+        g = torch.Generator().manual_seed(seed)
+        kv = torch.randn(1, 1, n, 4, generator=g)
+        c.update(0, kv, kv * 2)
+        for li in (1, 2, 3):
+            lin = c.layers[li]
+            lin.update(conv_state=None, recurrent_state=None, cache_kwargs={"op": "get"})
+            mk = lambda t: torch.randn(t.shape, generator=g)
+            lin.update(conv_state=(mk(lin.conv_state_q), mk(lin.conv_state_k), mk(lin.conv_state_v)),
+                       recurrent_state=mk(lin.recurrent_state), cache_kwargs={"op": "set", "delta_len": n})
+
+    a = StaticCachePrealloc(config=cfg, batch_size=1, ring=ring, zero_init=True)
+    for i, n in enumerate([3, 5, 2, 9]):
+        feed(a, n, i)
+    path = str(tmp_path / "cache.safetensors")
+    a.save(path)
+    b = StaticCachePrealloc(config=cfg, batch_size=1, ring=ring, zero_init=True).load(path)
+
+    def same(x, y):
+        for la, lb in zip(x.layers, y.layers):
+            if la.is_sliding:
+                assert (la.size, la.cumulative_length) == (lb.size, lb.cumulative_length)
+                assert torch.equal(la.keys, lb.keys) and torch.equal(la.values, lb.values)
+            else:
+                assert (la.seq_len, la.start) == (lb.seq_len, lb.start)
+                assert torch.equal(la.recurrent_state, lb.recurrent_state) and torch.equal(la.conv_state_v, lb.conv_state_v)
+    same(a, b)
+    feed(a, 4, 99)
+    feed(b, 4, 99)
+    same(a, b)
+    assert a.layers[0].cumulative_length == 23
