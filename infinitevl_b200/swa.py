@@ -185,3 +185,12 @@ def sliding_window_attention_forward(module, query: torch.Tensor, key: torch.Ten
     out = swa_attention(query, key, value, window=sliding_window, scale=scaling,
                         key_pos0=int(kwargs.get("key_position_offset", 0) or 0))
     return out, None
+
+
+def register_attention_interface(name: str = "ivl_b200_swa") -> str:
+    """Register `sliding_window_attention_forward` with the HF attention interface, so that a model whose
+    `config._attn_implementation` is `name` (the reference forces "flash_attention_2" at std:1028 and looks the callable
+    up in ALL_ATTENTION_FUNCTIONS at std:1092-1108) reaches the B200 kernel.  Returns the name."""
+    from transformers import AttentionInterface
+    AttentionInterface.register(name, sliding_window_attention_forward)
+    return name

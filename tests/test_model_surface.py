@@ -176,3 +176,19 @@ def test_vectorised_rope_index_is_the_reference_function(golden_dir, monkeypatch
     # a row whose placeholder run is one token short is not well formed: block-by-block path
     bad = [5, VS] + [IMG] * 5 + [VE, 6]
     assert MM._rope_index_vectorized(cfg, t([bad]), t([[1, 4, 6]]), None, None, None) is None
+
+
+def test_attention_interface_registration():
+    """The drop-in point of the SWA operator is the HF attention interface (std:1092-1108): registering the B200
+    entry makes `ALL_ATTENTION_FUNCTIONS[name]` resolve to it, and it refuses what it cannot do instead of ignoring it."""
+    from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+    from infinitevl_b200 import swa
+    name = swa.register_attention_interface("ivl_b200_swa_test")
+    assert ALL_ATTENTION_FUNCTIONS[name] is swa.sliding_window_attention_forward
+    q = torch.zeros(2, 4, 3, 128)
+    with pytest.raises(NotImplementedError):     # a real padding mask
+        swa.sliding_window_attention_forward(None, q, q, q, attention_mask=torch.tensor([[0, 1, 1], [1, 1, 1]]))
+    with pytest.raises(NotImplementedError):     # dropout
+        swa.sliding_window_attention_forward(None, q, q, q, dropout=0.1)
+    with pytest.raises(Exception):               # CPU tensors: there is no CPU fallback
+        swa.sliding_window_attention_forward(None, q.bfloat16(), q.bfloat16(), q.bfloat16())
